@@ -1,0 +1,208 @@
+"""histbook_b200 -- a B200-native backend for the fill hot path of scikit-hep/histbook.
+
+    import histbook_b200            # installs the backend into histbook's Hist / Book
+    from histbook import Hist, Book, bin, profile
+    h = Hist(bin("x + y", 200, -5, 5), weight="w")
+    h.fill(x=x, y=y, w=w)           # numpy arrays, torch CUDA tensors, anything with __cuda_array_interface__
+    h.pandas()                      # read side untouched: works on a host copy of the device-resident bins
+
+What changes (BASELINE.json north_star): ``Hist.fill`` / ``Book.fill`` (histbook/hist.py:337-379,
+histbook/book.py:540-586), the expression evaluation of ``Fillable._fill`` + ``calc`` (histbook/fill.py:85-162,
+histbook/calc/__init__.py) and the content storage behind ``Hist._content``.  Nothing else moves:
+``axis.py``, ``expr.py``, ``proj.py``, ``export.py``, ``vega.py`` stay the reference's own code.
+
+There is no CPU fallback.  ``uninstall()`` gives the reference's numpy path back (used by the tests and
+the benchmark's CPU baseline as the oracle).
+"""
+import numpy
+
+from histbook_b200 import _ref
+from histbook_b200.codegen import UnsupportedError          # noqa: F401
+from histbook_b200.engine import EngineError                 # noqa: F401
+
+__version__ = "0.1.0"
+
+_originals = {}
+_installed = False
+
+
+def reference():
+    """The (unmodified) histbook module this backend plugs into."""
+    return _ref.load()
+
+
+# ----------------------------------------------------------------------------- patched methods
+
+def _content_get(self):
+    st = self.__dict__.get("_hb")
+    return None if st is None else st.get()
+
+
+def _content_set(self, value):
+    # always a *fresh* store: Hist.__add__/__mul__ clone with out.__dict__.update(self.__dict__) and then
+    # assign out._content (hist.py:539-541,587-589) -- the source histogram's store must not be touched.
+    from histbook_b200.store import Store
+    if isinstance(value, numpy.ndarray) or value is None or isinstance(value, dict):
+        self.__dict__["_hb"] = Store(self._shape, [], value)
+    else:
+        raise TypeError("Hist content must be None, a numpy array or a dict")
+
+
+def _plan_for_hist(self):
+    from histbook_b200.fillable import Plan
+    plan = self.__dict__.get("_hb_plan")
+    if plan is None:
+        plan = self.__dict__["_hb_plan"] = Plan([self])
+    return plan
+
+
+def _hist_fill(self, arrays=None, **more):
+    """``Hist.fill`` (histbook/hist.py:337-379) on the device."""
+    hb = _ref.load()
+    from histbook_b200 import fillable
+    if hb.calc.spark.isspark(arrays, more):
+        raise UnsupportedError("Spark DataFrames are not supported by the B200 fill backend")
+    if arrays.__class__.__name__ == "DataFrame" and arrays.__class__.__module__.startswith("pandas"):
+        if len(more) > 0:
+            raise TypeError("if arrays is a Pandas DataFrame, keyword arguments are not allowed")
+        return _hist_fill(self, dict((n, arrays[n].values) for n in arrays.columns))
+    if arrays is None:
+        arrays = more
+    elif len(more) == 0:
+        pass
+    else:
+        arrays = hb.util.ChainedDict(arrays, more)
+    fillable.fill_hists(_plan_for_hist(self), [self], arrays)
+
+
+def _book_hists(book):
+    seen, out = set(), []
+    for x in book.itervalues(recursive=True, onlyhist=True):
+        if id(x) not in seen:            # one Hist stored under several names is filled once
+            seen.add(id(x))
+            out.append(x)
+    return out
+
+
+def _book_fill(self, arrays=None, **more):
+    """``Book.fill`` (histbook/book.py:540-586): every histogram of the book in one fused pass."""
+    hb = _ref.load()
+    from histbook_b200 import fillable
+    if hb.calc.spark.isspark(arrays, more):
+        raise UnsupportedError("Spark DataFrames are not supported by the B200 fill backend")
+    if arrays.__class__.__name__ == "DataFrame" and arrays.__class__.__module__.startswith("pandas"):
+        if len(more) > 0:
+            raise TypeError("if arrays is a Pandas DataFrame, keyword arguments are not allowed")
+        return _book_fill(self, dict((n, arrays[n].values) for n in arrays.columns))
+    if arrays is None:
+        arrays = more
+    elif len(more) == 0:
+        pass
+    else:
+        arrays = hb.util.ChainedDict(arrays, more)
+    hists = _book_hists(self)
+    ids = tuple(id(h) for h in hists)
+    cached = self.__dict__.get("_hb_plan")
+    if cached is None or cached[0] != ids:
+        cached = self.__dict__["_hb_plan"] = (ids, fillable.Plan(hists), hists)
+    fillable.fill_hists(cached[1], hists, arrays)
+
+
+def _hist_copy(self):
+    """``Hist.copy`` (hist.py:80-84) without a device->host->device round trip."""
+    from histbook_b200 import fillable
+    out = _originals["Hist.cleared"](self)
+    st = self.__dict__.get("_hb")
+    if st is not None:
+        out.__dict__["_hb"] = fillable._clone_store(st)
+    return out
+
+
+def _hist_copyonfill(self):
+    """``Hist.copyonfill`` (hist.py:86-91): share the store until the first fill of the copy."""
+    out = _originals["Hist.cleared"](self)
+    out._copyonfill = True
+    st = self.__dict__.get("_hb")
+    if st is not None:
+        out.__dict__["_hb"] = st
+    return out
+
+
+# ----------------------------------------------------------------------------- install / uninstall
+
+def install():
+    """Route histbook's fill path through the device engine (idempotent)."""
+    global _installed
+    if _installed:
+        return
+    hb = _ref.load()
+    Hist, Book = hb.hist.Hist, hb.book.Book
+    _originals.update({
+        "Hist.fill": Hist.__dict__["fill"], "Book.fill": Book.__dict__["fill"],
+        "Hist.copy": Hist.__dict__["copy"], "Hist.copyonfill": Hist.__dict__["copyonfill"],
+        "Hist.cleared": Hist.__dict__["cleared"],
+    })
+    Hist._content = property(_content_get, _content_set)
+    Hist.fill = _hist_fill
+    Book.fill = _book_fill
+    Hist.copy = _hist_copy
+    Hist.copyonfill = _hist_copyonfill
+    _installed = True
+
+
+def uninstall():
+    """Give the reference's own numpy fill path back.  Histograms created while installed keep their
+    contents (moved back into a plain ``_content`` attribute is not possible for live objects: create new ones)."""
+    global _installed
+    if not _installed:
+        return
+    hb = _ref.load()
+    Hist, Book = hb.hist.Hist, hb.book.Book
+    del Hist._content
+    Hist.fill = _originals["Hist.fill"]
+    Book.fill = _originals["Book.fill"]
+    Hist.copy = _originals["Hist.copy"]
+    Hist.copyonfill = _originals["Hist.copyonfill"]
+    _installed = False
+
+
+def installed():
+    return _installed
+
+
+class reference_path(object):
+    """Context manager: run the enclosed code on the reference's numpy path (oracle use only)."""
+
+    def __enter__(self):
+        self.was = _installed
+        uninstall()
+        return _ref.load()
+
+    def __exit__(self, *exc):
+        if self.was:
+            install()
+        return False
+
+
+def peek(hist):
+    """Host copy of a histogram's content that does not invalidate the device copy (read-only use)."""
+    st = hist.__dict__.get("_hb")
+    return None if st is None else st.peek()
+
+
+def set_options(**kwargs):
+    from histbook_b200 import fillable
+    fillable.set_options(**kwargs)
+
+
+def last_stats():
+    from histbook_b200 import fillable
+    return dict(fillable.last_stats)
+
+
+if _ref.available():
+    install()
+    _hb = _ref.load()
+    Hist, Book = _hb.Hist, _hb.Book
+    bin, intbin, split, cut, profile, groupby, groupbin = (_hb.bin, _hb.intbin, _hb.split, _hb.cut, _hb.profile,
+                                                           _hb.groupby, _hb.groupbin)

@@ -1,0 +1,836 @@
+"""Lower a fill spec to one fused CUDA kernel (text) for NVRTC.
+
+Replaces, for the fill hot path, the reference's instruction compiler and interpreter
+(histbook/instr.py:241-381 ``walkdown``/``instructions``; histbook/fill.py:85-162 ``_fill``;
+histbook/calc/__init__.py:327-357 ``calculate``) and ``Hist._postfill`` (histbook/hist.py:392-504):
+
+* common-subexpression elimination over *all* histograms of a book is done here on the goal
+  trees (``spec.tree_key``) -- the reference does it with ``CallGraphNode.grow`` (instr.py:67-91);
+* every node becomes one SSA register statement of a per-event device function, evaluated in the
+  dtype numpy would use (``ufunc.resolve_dtypes`` is asked at plan time, so NEP-50 weak scalars,
+  float32 columns staying float32, int/float comparisons etc. follow numpy by construction);
+* every histogram gets an accumulation plan: which (bin, column) receives which term, and where
+  the bins live while the kernel runs (shared-memory privatised u32 / f64, or global float64 REDs).
+
+The arithmetic *shape* (operand order, balanced sums, ``x*(1/3)`` instead of ``x/3`` ...) is
+whatever histbook's ``expr.py``/``instr.totree`` produced; it is not re-derived here.
+"""
+import hashlib
+import math
+import struct
+
+import numpy
+
+from histbook_b200 import spec as hbspec
+
+THREADS = 256
+VEC = 4                    # events per thread per tile (hb_load4)
+
+MAYBECONSTANTS = {"pi": numpy.pi, "Pi": numpy.pi, "e": numpy.e, "E": numpy.e,
+                  "inf": numpy.inf, "Inf": numpy.inf, "infinity": numpy.inf, "Infinity": numpy.inf,
+                  "nan": numpy.nan, "NaN": numpy.nan, "Nan": numpy.nan}     # expr.py:328-331
+
+CTYPE = {
+    "float64": "double", "float32": "float", "int64": "hb_i64", "uint64": "hb_u64",
+    "int32": "int", "uint32": "hb_u32", "int16": "short", "uint16": "unsigned short",
+    "int8": "signed char", "uint8": "unsigned char", "bool": "bool",
+}
+# dtype codes of the C ABI (include/hbfill.h, enum hb_dtype)
+DTYPE_CODE = {"float64": 0, "float32": 1, "int64": 2, "int32": 3, "int16": 4, "int8": 5,
+              "uint64": 6, "uint32": 7, "uint16": 8, "uint8": 9, "bool": 10}
+
+
+class UnsupportedError(NotImplementedError):
+    pass
+
+
+def ctype(dtype):
+    name = numpy.dtype(dtype).name
+    if name not in CTYPE:
+        raise UnsupportedError("dtype {0} is not supported by the B200 fill backend".format(name))
+    return CTYPE[name]
+
+
+def lit(value, dtype):
+    """Exact C literal of ``value`` converted to ``dtype`` the way numpy converts a scalar."""
+    dtype = numpy.dtype(dtype)
+    with numpy.errstate(all="ignore"):
+        v = numpy.array(value).astype(dtype)
+    if dtype == numpy.float64:
+        bits, = struct.unpack("<q", struct.pack("<d", float(v)))
+        return "__longlong_as_double(%dLL)" % bits if bits != -2**63 else "__longlong_as_double((hb_i64)0x8000000000000000ULL)"
+    if dtype == numpy.float32:
+        bits, = struct.unpack("<i", struct.pack("<f", float(v)))
+        return "__int_as_float(%d)" % bits if bits != -2**31 else "__int_as_float(HB_INT_MIN)"
+    if dtype == numpy.bool_:
+        return "true" if bool(v) else "false"
+    if dtype.kind == "i":
+        iv = int(v)
+        if iv == -2**63:
+            return "((hb_i64)0x8000000000000000ULL)"
+        return "((%s)%dLL)" % (ctype(dtype), iv)
+    if dtype.kind == "u":
+        return "((%s)%dULL)" % (ctype(dtype), int(v))
+    raise UnsupportedError(str(dtype))
+
+
+class Value(object):
+    """An SSA value of the per-event program."""
+    __slots__ = ("c", "dtype", "const", "kind", "extra")
+
+    def __init__(self, c=None, dtype=None, const=None, kind="arr", extra=None):
+        self.c = c            # C expression (a variable name) or None for constants
+        self.dtype = numpy.dtype(dtype) if dtype is not None else None
+        self.const = const    # python value for ("const", v) leaves
+        self.kind = kind      # arr | const | index | group
+        self.extra = extra
+
+    @property
+    def isconst(self):
+        return self.kind == "const"
+
+
+def _pytype(v):
+    """What ufunc.resolve_dtypes wants for a Python literal (NEP 50 weak scalars)."""
+    if isinstance(v, bool):
+        return numpy.dtype(numpy.bool_)
+    if isinstance(v, int):
+        return int
+    if isinstance(v, float):
+        return float
+    raise UnsupportedError("constant {0!r} in arithmetic".format(v))
+
+
+def _resolve(ufunc, args):
+    sig = tuple(_pytype(a.const) if a.isconst else a.dtype for a in args) + (None,) * ufunc.nout
+    try:
+        return ufunc.resolve_dtypes(sig)
+    except TypeError:
+        # all-Python-scalar calls: numpy would use default dtypes
+        sig = tuple(numpy.array(a.const).dtype if a.isconst else a.dtype for a in args) + (None,) * ufunc.nout
+        return ufunc.resolve_dtypes(sig)
+
+
+# unary float functions: library name -> (numpy ufunc, C name for double, C name for float)
+_FLOAT1 = {
+    "sqrt": (numpy.sqrt, "sqrt", "sqrtf"), "exp": (numpy.exp, "exp", "expf"), "exp2": (numpy.exp2, "exp2", "exp2f"),
+    "expm1": (numpy.expm1, "expm1", "expm1f"), "log": (numpy.log, "log", "logf"), "log2": (numpy.log2, "log2", "log2f"),
+    "log10": (numpy.log10, "log10", "log10f"), "log1p": (numpy.log1p, "log1p", "log1pf"),
+    "sin": (numpy.sin, "sin", "sinf"), "cos": (numpy.cos, "cos", "cosf"), "tan": (numpy.tan, "tan", "tanf"),
+    "arcsin": (numpy.arcsin, "asin", "asinf"), "arccos": (numpy.arccos, "acos", "acosf"), "arctan": (numpy.arctan, "atan", "atanf"),
+    "sinh": (numpy.sinh, "sinh", "sinhf"), "cosh": (numpy.cosh, "cosh", "coshf"), "tanh": (numpy.tanh, "tanh", "tanhf"),
+    "arcsinh": (numpy.arcsinh, "asinh", "asinhf"), "arccosh": (numpy.arccosh, "acosh", "acoshf"), "arctanh": (numpy.arctanh, "atanh", "atanhf"),
+}
+# bit-exact with numpy (IEEE-754 correctly rounded or exact); everything else in _FLOAT1 is "libm-class"
+EXACT_FLOAT1 = {"sqrt"}
+_ROUND1 = {"floor": (numpy.floor, "floor", "floorf"), "ceil": (numpy.ceil, "ceil", "ceilf"),
+           "trunc": (numpy.trunc, "trunc", "truncf"), "rint": (numpy.rint, "rint", "rintf")}
+_FLOAT2 = {"arctan2": (numpy.arctan2, "atan2", "atan2f"), "hypot": (numpy.hypot, "hypot", "hypotf"),
+           "copysign": (numpy.copysign, "copysign", "copysignf")}
+_CMP = {"numpy.equal": (numpy.equal, "=="), "numpy.not_equal": (numpy.not_equal, "!="),
+        "numpy.less": (numpy.less, "<"), "numpy.less_equal": (numpy.less_equal, "<=")}
+_ARITH = {"numpy.add": (numpy.add, "hb_add"), "numpy.subtract": (numpy.subtract, "hb_sub"),
+          "numpy.multiply": (numpy.multiply, "hb_mul")}
+_ERFLIKE = {"erf": "hb_erf", "erfc": "hb_erfc", "lgamma": "hb_lgamma", "gamma": "hb_gamma", "factorial": "hb_factorial"}
+
+
+class Program(object):
+    """Builds the per-event SSA program (with CSE) for one spec and one set of column dtypes."""
+
+    def __init__(self, spec, coltypes):
+        """coltypes: field name -> (numpy dtype, is_scalar).  Fields that are missing but are
+        ``maybeconstants`` must have been added by the caller as float64 scalars (fill.py:133-134)."""
+        self.spec = spec
+        self.coltypes = coltypes
+        self.cols = []          # [(name, dtype, is_scalar)] in slot order
+        self.colslot = {}
+        self.body = []          # C statements of the event function
+        self.memo = {}
+        self.counter = 0
+        self.consts = []        # __constant__ array definitions (split edges)
+        self.inexact = set()    # library functions used that are not bit-identical to numpy
+
+    # ------------------------------------------------------------------ helpers
+    def new(self, prefix="t"):
+        self.counter += 1
+        return "%s%d" % (prefix, self.counter)
+
+    def emit(self, dtype, expr, prefix="t"):
+        name = self.new(prefix)
+        self.body.append("const %s %s = %s;" % (ctype(dtype), name, expr))
+        return Value(name, dtype)
+
+    def cast(self, value, dtype):
+        """C expression of ``value`` as ``dtype`` (numpy 'safe' casts only: ints widen, int -> float, bool -> anything)."""
+        dtype = numpy.dtype(dtype)
+        if value.isconst:
+            return lit(value.const, dtype)
+        if value.dtype == dtype:
+            return value.c
+        if dtype == numpy.bool_:
+            return "(%s != 0)" % value.c
+        return "((%s)%s)" % (ctype(dtype), value.c)
+
+    def tobool(self, value):
+        if value.isconst:
+            return "true" if value.const else "false"
+        if value.dtype == numpy.bool_:
+            return value.c
+        return "(%s != 0)" % value.c
+
+    # ------------------------------------------------------------------ leaves
+    def column(self, name):
+        if name not in self.colslot:
+            if name not in self.coltypes:
+                raise ValueError("required field {0} not found in fill arguments".format(repr(name)))
+            dtype, is_scalar = self.coltypes[name]
+            ctype(dtype)
+            self.colslot[name] = len(self.cols)
+            self.cols.append((name, numpy.dtype(dtype), bool(is_scalar)))
+        slot = self.colslot[name]
+        return Value("c%d" % slot, self.cols[slot][1])
+
+    # ------------------------------------------------------------------ trees
+    def lower(self, tree):
+        kind = tree[0]
+        if kind == "const":
+            return Value(const=hbspec.decode_value(tree[1]), kind="const")
+        key = hbspec.tree_key(tree)
+        if key in self.memo:
+            return self.memo[key]
+        if kind in ("name", "pred"):
+            out = self.column(tree[1])
+        elif kind == "bconst":
+            v = hbspec.decode_value(tree[2])
+            dt = numpy.array(v).dtype                 # numpy.full(length, value), fill.py:112-120
+            out = self.emit(dt, lit(v, dt))
+        elif kind == "call":
+            out = self.call(tree[1], [self.lower(x) for x in tree[2:]])
+        else:
+            raise AssertionError(tree)
+        self.memo[key] = out
+        return out
+
+    def call(self, fcn, args):
+        if fcn.startswith("histbook."):
+            return self.index_op(fcn, args)
+
+        if fcn in _ARITH:
+            ufunc, helper = _ARITH[fcn]
+            a, b, out = _resolve(ufunc, args)
+            if fcn == "numpy.subtract" and out == numpy.bool_:
+                raise TypeError("numpy boolean subtract, the `-` operator, is not supported")
+            return self.emit(out, "%s<%s>(%s, %s)" % (helper, ctype(out), self.cast(args[0], a), self.cast(args[1], b)))
+
+        if fcn == "numpy.true_divide":
+            a, b, out = _resolve(numpy.true_divide, args)
+            ctype(out)
+            return self.emit(out, "(%s / %s)" % (self.cast(args[0], a), self.cast(args[1], b)))
+
+        if fcn in _CMP:
+            ufunc, op = _CMP[fcn]
+            a, b, out = _resolve(ufunc, args)
+            return self.emit(numpy.bool_, "(%s %s %s)" % (self.cast(args[0], a), op, self.cast(args[1], b)))
+
+        if fcn == "numpy.logical_and":
+            return self.emit(numpy.bool_, "(%s && %s)" % (self.tobool(args[0]), self.tobool(args[1])))
+        if fcn == "numpy.logical_or":
+            return self.emit(numpy.bool_, "(%s || %s)" % (self.tobool(args[0]), self.tobool(args[1])))
+        if fcn == "numpy.logical_not":
+            return self.emit(numpy.bool_, "(!%s)" % self.tobool(args[0]))
+
+        if fcn == "numpy.isin":
+            # the right-hand side is a Python set (expr.py:185-193); numpy.isin turns a set into a 0-d
+            # object array, so the reference's answer is False for every element (kept for parity).
+            if args[1].isconst and isinstance(args[1].const, (set, frozenset)):
+                return self.emit(numpy.bool_, "false")
+            raise UnsupportedError("numpy.isin with a non-set right-hand side")
+
+        if fcn in _FLOAT1:
+            ufunc, cd, cf = _FLOAT1[fcn]
+            a, out = _resolve(ufunc, args)
+            if fcn not in EXACT_FLOAT1:
+                self.inexact.add(fcn)
+            name = cd if out == numpy.float64 else cf
+            ctype(out)
+            if out not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("{0} in dtype {1}".format(fcn, out))
+            return self.emit(out, "%s(%s)" % (name, self.cast(args[0], a)))
+
+        if fcn in _ROUND1:
+            ufunc, cd, cf = _ROUND1[fcn]
+            a, out = _resolve(ufunc, args)
+            if out.kind in "iub":
+                return self.emit(out, self.cast(args[0], a))         # numpy >= 2.1: integer input is returned as is
+            if out not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("{0} in dtype {1}".format(fcn, out))
+            return self.emit(out, "%s(%s)" % (cd if out == numpy.float64 else cf, self.cast(args[0], a)))
+
+        if fcn in _FLOAT2:
+            ufunc, cd, cf = _FLOAT2[fcn]
+            a, b, out = _resolve(ufunc, args)
+            if out not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("{0} in dtype {1}".format(fcn, out))
+            if fcn != "copysign":
+                self.inexact.add(fcn)
+            return self.emit(out, "%s(%s, %s)" % (cd if out == numpy.float64 else cf, self.cast(args[0], a), self.cast(args[1], b)))
+
+        if fcn in ("abs", "fabs"):
+            a, out = _resolve(numpy.absolute, args)
+            return self.emit(out, "hb_abs<%s>(%s)" % (ctype(out), self.cast(args[0], a)))
+        if fcn == "conj":
+            a, out = _resolve(numpy.conjugate, args)
+            return self.emit(out, self.cast(args[0], a))
+        if fcn == "sign":
+            a, out = _resolve(numpy.sign, args)
+            if out.kind == "u" or out == numpy.bool_:
+                return self.emit(out, "(%s)(%s != 0)" % (ctype(out), self.cast(args[0], a)))
+            return self.emit(out, "hb_sign<%s>(%s)" % (ctype(out), self.cast(args[0], a)))
+        if fcn in ("max", "fmax", "min", "fmin"):
+            ufunc = numpy.maximum if fcn in ("max", "fmax") else numpy.minimum
+            a, b, out = _resolve(ufunc, args)
+            helper = "hb_max" if fcn in ("max", "fmax") else "hb_min"
+            if out == numpy.bool_:
+                op = "||" if helper == "hb_max" else "&&"
+                return self.emit(out, "(%s %s %s)" % (self.cast(args[0], a), op, self.cast(args[1], b)))
+            return self.emit(out, "%s<%s>(%s, %s)" % (helper, ctype(out), self.cast(args[0], a), self.cast(args[1], b)))
+        if fcn == "heaviside":
+            if len(args) == 1:
+                args = args + [Value(const=0.5, kind="const")]
+            a, b, out = _resolve(numpy.heaviside, args)
+            if out not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("heaviside in dtype {0}".format(out))
+            return self.emit(out, "hb_heaviside<%s>(%s, %s)" % (ctype(out), self.cast(args[0], a), self.cast(args[1], b)))
+        if fcn in ("isnan", "isinf", "isfinite"):
+            ufunc = getattr(numpy, fcn)
+            a, out = _resolve(ufunc, args)
+            x = self.cast(args[0], a)
+            if a.kind != "f":
+                return self.emit(numpy.bool_, "true" if fcn == "isfinite" else "false")
+            big = lit(numpy.inf, a)
+            if fcn == "isnan":
+                return self.emit(numpy.bool_, "(%s != %s)" % (x, x))
+            if fcn == "isinf":
+                return self.emit(numpy.bool_, "(hb_abs<%s>(%s) == %s)" % (ctype(a), x, big))
+            return self.emit(numpy.bool_, "(hb_abs<%s>(%s) < %s)" % (ctype(a), x, big))
+        if fcn in ("mod", "fmod"):
+            a, b, out = _resolve(numpy.remainder, args)      # calc/__init__.py:95: both are numpy.remainder
+            x, y = self.cast(args[0], a), self.cast(args[1], b)
+            if out.kind == "f":
+                if out not in (numpy.float64, numpy.float32):
+                    raise UnsupportedError("remainder in dtype {0}".format(out))
+                return self.emit(out, "hb_remainder(%s, %s)" % (x, y))
+            if out.kind == "i":
+                return self.emit(out, "hb_remainder_int<%s>(%s, %s)" % (ctype(out), x, y))
+            if out.kind == "u":
+                return self.emit(out, "hb_remainder_uint<%s>(%s, %s)" % (ctype(out), x, y))
+            raise TypeError("remainder of booleans")
+        if fcn == "pow":
+            a, b, out = _resolve(numpy.power, args)
+            x, y = self.cast(args[0], a), self.cast(args[1], b)
+            if out.kind == "f":
+                if out not in (numpy.float64, numpy.float32):
+                    raise UnsupportedError("power in dtype {0}".format(out))
+                self.inexact.add("pow")
+                return self.emit(out, "%s(%s, %s)" % ("pow" if out == numpy.float64 else "powf", x, y))
+            if args[1].isconst and args[1].const < 0:
+                raise ValueError("Integers to negative integer powers are not allowed.")
+            return self.emit(out, "hb_ipow<%s>(%s, %s)" % (ctype(out), x, y))
+        if fcn in ("deg2rad", "rad2deg"):
+            ufunc = getattr(numpy, fcn)
+            a, out = _resolve(ufunc, args)
+            if out not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("{0} in dtype {1}".format(fcn, out))
+            # numpy loops: x * (pi/180) and x * (180/pi), constant formed in the loop dtype
+            if out == numpy.float64:
+                k = (numpy.pi / 180.0) if fcn == "deg2rad" else (180.0 / numpy.pi)
+            else:
+                k = (numpy.float32(numpy.pi) / numpy.float32(180.0)) if fcn == "deg2rad" else (numpy.float32(180.0) / numpy.float32(numpy.pi))
+            return self.emit(out, "(%s * %s)" % (self.cast(args[0], a), lit(k, out)))
+        if fcn in ("logaddexp", "logaddexp2"):
+            a, b, out = _resolve(getattr(numpy, fcn), args)
+            if out != numpy.float64:
+                raise UnsupportedError("{0} in dtype {1}".format(fcn, out))
+            self.inexact.add(fcn)
+            return self.emit(out, "hb_%s(%s, %s)" % (fcn, self.cast(args[0], a), self.cast(args[1], b)))
+        if fcn == "where":
+            # numpy.where(c, yes, no): result dtype by ordinary promotion of yes/no (weak Python scalars)
+            yes, no = args[1], args[2]
+            if yes.isconst and no.isconst:
+                out = numpy.result_type(numpy.array(yes.const).dtype, numpy.array(no.const).dtype)
+                if isinstance(yes.const, bool) != isinstance(no.const, bool) or type(yes.const) is not type(no.const):
+                    out = numpy.result_type(yes.const, no.const)
+            else:
+                out = numpy.result_type(yes.const if yes.isconst else yes.dtype, no.const if no.isconst else no.dtype)
+            return self.emit(out, "(%s ? %s : %s)" % (self.tobool(args[0]), self.cast(yes, out), self.cast(no, out)))
+        if fcn in _ERFLIKE:
+            x = args[0]
+            dt = numpy.result_type(x.const if x.isconst else x.dtype, 1.0)
+            if dt != numpy.float64:
+                raise UnsupportedError("{0} of a {1} value (the reference mixes float32 and float64 inside its approximation)".format(fcn, dt))
+            self.inexact.add(fcn)
+            return self.emit(numpy.float64, "%s(%s)" % (_ERFLIKE[fcn], self.cast(x, numpy.float64)))
+
+        # calc/__init__.py:353-357: no library entry ("round", "//", "^" ...) -> AssertionError at fill time
+        raise AssertionError("no library entry for {0!r}".format(fcn))
+
+    # ------------------------------------------------------------------ index ops (calc/__init__.py:149-325)
+    def index_op(self, fcn, args):
+        v = args[0]
+        if v.isconst:
+            raise UnsupportedError("axis expression that is a bare constant call")
+        if fcn.startswith("histbook.bin"):
+            f = fcn[len("histbook.bin"):]
+            numbins, low, high = (a.const for a in args[1:4])
+            # values - float(low): numpy picks the dtype; float32 stays float32, ints become float64
+            r = numpy.subtract.resolve_dtypes((v.dtype, float, None))[2]
+            if r not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("bin axis on a {0} value".format(v.dtype))
+            scale = float(numbins) / float(high - low)
+            name, ok = self.new("i"), self.new("ok")
+            self.body.append("bool %s = true;" % ok)
+            self.body.append("const int %s = hb_bin_axis<%s, %s>(%s, %s, %s, %d, %s);" % (
+                name, ctype(r), ", ".join("true" if c != "_" and c != "H" else "false" for c in f),
+                self.cast(v, r), lit(float(low), r), lit(scale, r), int(numbins), ok))
+            return Value(name, numpy.int32, kind="index", extra=ok)
+
+        if fcn.startswith("histbook.intbin"):
+            f = fcn[len("histbook.intbin"):]
+            lo, hi = args[1].const, args[2].const
+            shift = 1 if f[0] == "U" else 0
+            a, b, r = numpy.add.resolve_dtypes((v.dtype, int, None))
+            shifted = self.emit(r, "hb_add<%s>(%s, %s)" % (ctype(r), self.cast(v, r), lit(shift - lo, r)))
+            name, ok = self.new("i"), self.new("ok")
+            self.body.append("bool %s = true;" % ok)
+            self.body.append("const int %s = hb_intbin_axis<%s, %s, %s>(%s, %d, %s);" % (
+                name, ctype(r), "true" if f[0] == "U" else "false", "true" if f[1] == "O" else "false",
+                shifted.c, int(hi - lo), ok))
+            return Value(name, numpy.int32, kind="index", extra=ok)
+
+        if fcn.startswith("histbook.split"):
+            f = fcn[len("histbook.split"):]
+            edges = args[1].const
+            earr = numpy.asarray(edges)
+            # numpy.digitize -> searchsorted compares in the common dtype of column and edges
+            common = numpy.result_type(v.dtype, earr.dtype)
+            if common.kind in "iub":
+                cmp_t = numpy.dtype(numpy.int64)
+            elif common in (numpy.float64, numpy.float32):
+                cmp_t = numpy.dtype(numpy.float64)      # float32 -> float64 is exact, comparisons are unchanged
+            else:
+                raise UnsupportedError("split axis comparing in {0}".format(common))
+            cname = self.new("hb_edges")
+            bits = numpy.array(edges).astype(cmp_t).view(numpy.int64)
+            self.consts.append("__constant__ hb_i64 %s[%d] = {%s};" % (
+                cname, len(edges), ", ".join(("%dLL" % b) if b != -2**63 else "(-9223372036854775807LL - 1)" for b in bits.tolist())))
+            name, ok = self.new("i"), self.new("ok")
+            isnan = "(%s != %s)" % (v.c, v.c) if v.dtype.kind == "f" else "false"
+            self.body.append("bool %s = true;" % ok)
+            self.body.append("const int %s = hb_split_axis<%s, %s>(%s, %s, %s, %d, %s);" % (
+                name, ctype(cmp_t), ", ".join("true" if c != "_" and c != "H" else "false" for c in f),
+                self.cast(v, cmp_t), isnan, cname, len(edges), ok))
+            return Value(name, numpy.int32, kind="index", extra=ok)
+
+        if fcn == "histbook.cut":
+            name, ok = self.new("i"), self.new("ok")
+            self.body.append("bool %s = true;" % ok)
+            self.body.append("const int %s = hb_cut_axis<%s>(%s, %s);" % (name, ctype(v.dtype), v.c, ok))
+            return Value(name, numpy.int32, kind="index", extra=ok)
+
+        if fcn.startswith("histbook.groupbin"):
+            f = fcn[len("histbook.groupbin"):]
+            binwidth, origin = args[1].const, args[2].const
+            # calc/__init__.py:158-172, every step in the dtype of the first product
+            if origin == 0:
+                r = numpy.multiply.resolve_dtypes((v.dtype, float, None))[2]
+                k = self.emit(r, "(%s * %s)" % (self.cast(v, r), lit(1.0 / float(binwidth), r)))
+            else:
+                r = numpy.subtract.resolve_dtypes((v.dtype, float, None))[2]
+                k = self.emit(r, "(%s - %s)" % (self.cast(v, r), lit(float(origin), r)))
+                k = self.emit(r, "(%s * %s)" % (k.c, lit(1.0 / float(binwidth), r)))
+            if r not in (numpy.float64, numpy.float32):
+                raise UnsupportedError("groupbin axis on a {0} value".format(v.dtype))
+            fl, ce = ("floor", "ceil") if r == numpy.float64 else ("floorf", "ceilf")
+            if f[1] == "L":
+                k = self.emit(r, "%s(%s)" % (fl, k.c))
+            else:
+                k = self.emit(r, "%s(%s)" % (ce, k.c))
+                k = self.emit(r, "(%s - %s)" % (k.c, lit(1, r)))
+            k = self.emit(r, "(%s * %s)" % (k.c, lit(float(binwidth), r)))
+            if origin != 0:
+                k = self.emit(r, "(%s + %s)" % (k.c, lit(float(origin), r)))
+            key = self.emit(numpy.float64, "((double)%s)" % k.c, prefix="gk")
+            return Value(key.c, numpy.float64, kind="group", extra={"nanflow": f[0] == "N", "keytype": "float", "dtype": r})
+
+        if fcn == "histbook.groupby":
+            if v.dtype.kind == "f":
+                key = self.emit(numpy.float64, "((double)%s)" % v.c, prefix="gk")
+                return Value(key.c, numpy.float64, kind="group", extra={"nanflow": True, "keytype": "float", "dtype": v.dtype})
+            key = self.emit(numpy.int64, "((hb_i64)%s)" % v.c, prefix="gk")
+            return Value(key.c, numpy.int64, kind="group", extra={"nanflow": True, "keytype": "int", "dtype": v.dtype})
+
+        raise AssertionError("no library entry for {0!r}".format(fcn))
+
+
+# ================================================================================================
+# accumulation plans
+# ================================================================================================
+
+class HistPlan(object):
+    """Where each histogram's bins live during the kernel and which term goes to which column."""
+
+    def __init__(self, hid, h):
+        self.hid = hid
+        self.shape = tuple(h["shape"])
+        self.ncol = self.shape[-1]
+        self.nbins = int(numpy.prod(self.shape[:-1], dtype=numpy.int64)) if len(self.shape) > 1 else 1
+        self.index = []          # [(Value index, totbins)]
+        self.groups = []         # [Value group]
+        self.terms = []          # unique accumulated terms: C expression (double) or None (= count of 1)
+        self.dest = []           # per term: list of destination columns
+        self.strategy = "global"
+        self.smem_f64_off = None   # byte offset of the [nterms_f64][nbins] double block
+        self.smem_u32_off = None   # byte offset of the [nbins] u32 count block
+
+    def add_term(self, expr, col):
+        for t, e in enumerate(self.terms):
+            if e == expr:
+                self.dest[t].append(col)
+                return
+        self.terms.append(expr)
+        self.dest.append([col])
+
+    @property
+    def f64_terms(self):
+        return [t for t, e in enumerate(self.terms) if e is not None]
+
+    @property
+    def count_term(self):
+        for t, e in enumerate(self.terms):
+            if e is None:
+                return t
+        return None
+
+    def smem_bytes(self):
+        return self.nbins * (8 * len(self.f64_terms) + (4 if self.count_term is not None else 0))
+
+
+def _mulexpr(prog, a, b):
+    """C expression (double) of numpy's ``a * b`` for two Values, then cast to float64 (add.at target)."""
+    ta, tb, out = _resolve(numpy.multiply, [a, b])
+    return "((double)hb_mul<%s>(%s, %s))" % (ctype(out), prog.cast(a, ta), prog.cast(b, tb))
+
+
+def plan_hist(prog, hid, h):
+    """hist.py:392-456 restated as: linear index, row mask, and one (term -> columns) table."""
+    hp = HistPlan(hid, h)
+    for a in h["group"]:
+        hp.groups.append(prog.lower(a["goal"]))
+    for a in h["fixed"]:
+        if a["goal"] is None:
+            continue
+        hp.index.append((prog.lower(a["goal"]), int(a["totbins"])))
+
+    w = h["weight"]
+    wz = w2z = None
+    if w is not None and "w" in w:
+        wv, w2v = prog.lower(w["w"]), prog.lower(w["w2"])
+        if wv.isconst:
+            raise UnsupportedError("constant weight expression")
+        if wv.dtype.kind == "f":
+            # hist.py:422-427: rows with NaN weight contribute 0 to every column
+            sel = prog.emit(numpy.bool_, "(%s != %s)" % (wv.c, wv.c))
+            wz = prog.emit(wv.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, wv.dtype), wv.c))
+            w2z = prog.emit(w2v.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, w2v.dtype), w2v.c))
+        else:
+            wz, w2z = wv, w2v
+
+    for p in h["profile"]:
+        sx, sx2 = prog.lower(p["sumx"]), prog.lower(p["sumx2"])
+        for val, col in ((sx, p["sumwx"]), (sx2, p["sumwx2"])):
+            if val.isconst:
+                raise UnsupportedError("constant profile expression")
+            if w is None:
+                expr = "((double)%s)" % val.c               # sumx * 1
+            elif "const" in w:
+                expr = _mulexpr(prog, val, Value(lit(float(w["const"]), numpy.float64), numpy.float64))
+            else:
+                expr = _mulexpr(prog, val, wz)
+            hp.add_term(expr, col)
+
+    if w is None:
+        hp.add_term(None, h["sumw"])
+    elif "const" in w:
+        hp.add_term(lit(float(w["const"]), numpy.float64), h["sumw"])
+        hp.add_term(lit(float(w["const2"]), numpy.float64), h["sumw2"])
+    else:
+        hp.add_term("((double)%s)" % wz.c, h["sumw"])
+        hp.add_term("((double)%s)" % w2z.c, h["sumw2"])
+    return hp
+
+
+def choose_strategies(plans, options):
+    """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
+    budget = int(options.get("smem_budget", 96 * 1024))
+    forced = options.get("strategy", {})
+    order = sorted(plans, key=lambda hp: hp.smem_bytes())
+    used = 0
+    for hp in order:
+        want = forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*")))
+        if hp.groups:
+            hp.strategy = "global"
+            continue
+        need = hp.smem_bytes()
+        if want == "global":
+            hp.strategy = "global"
+        elif (want == "smem" or want is None) and used + need <= budget:
+            hp.strategy = "smem"
+        else:
+            hp.strategy = "global"
+        if hp.strategy == "smem":
+            # f64 block first (8-byte aligned), u32 block after
+            hp.smem_f64_off = used
+            hp.smem_u32_off = used + hp.nbins * 8 * len(hp.f64_terms)
+            used += (need + 7) // 8 * 8
+    return used
+
+
+# ================================================================================================
+# kernel text
+# ================================================================================================
+
+class Kernel(object):
+    """Result of codegen: CUDA source + everything the host needs to launch it."""
+
+    def __init__(self):
+        self.source = None
+        self.name = "hb_fill_kernel"
+        self.cols = None            # [(name, dtype, is_scalar)]
+        self.plans = None           # [HistPlan] (fill kernels)
+        self.smem_bytes = 0
+        self.threads = THREADS
+        self.tile = THREADS * VEC
+        self.inexact = set()
+        self.key = None
+        self.group_aux = {}         # fill kernel: hist id -> aux slot of its group table
+        self.group_goals = []       # keys kernel: [(tree key, info dict)] in aux order
+
+
+def _colarg(slot, dtype, is_scalar, loaded):
+    src = ("s%d" % slot) if is_scalar else loaded
+    if dtype == numpy.bool_:
+        return "(%s != 0)" % src
+    return src
+
+
+def _loadtype(dtype):
+    return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
+
+
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks):
+    """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
+    over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
+    takes the scalar path), shared-memory zeroing before and block merge after."""
+    src = []
+    src.append('#include "hb_template.cuh"')
+    src.append("#define HB_THREADS %d" % threads)
+    src.append("#define HB_TILE (HB_THREADS * 4)")
+    src.extend(prog.consts)
+    src.append("")
+    sig = ["const HbParams& p", "unsigned char* hb_smem"]
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        sig.append("const %s c%d /* %s */" % (ctype(dtype), slot, name))
+    src.append("__device__ __forceinline__ void hb_event(%s)\n{" % ", ".join(sig))
+    src.extend("    " + line for line in event_lines)
+    src.append("}\n")
+
+    src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % minblocks)
+    src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
+    if smem:
+        src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (smem // 4))
+        src.append("    __syncthreads();")
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        if is_scalar:
+            src.append("    const %s s%d = hb_scalar<%s>(p.scal[%d]);" % (_loadtype(dtype), slot, _loadtype(dtype), slot))
+    src.append("    const hb_i64 ntiles = (p.n + HB_TILE - 1) / HB_TILE;")
+    src.append("    for (hb_i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {")
+    src.append("        const hb_i64 first = tile * HB_TILE;")
+    src.append("        if (p.vec_ok && first + HB_TILE <= p.n) {")
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        if not is_scalar:
+            src.append("            %s v%d[4]; hb_load4<%s>(p.cols[%d], first, threadIdx.x, HB_THREADS, v%d);" % (_loadtype(dtype), slot, _loadtype(dtype), slot, slot))
+    src.append("#pragma unroll")
+    src.append("            for (int k = 0; k < 4; ++k) {")
+    src.append("                hb_event(p, hb_smem%s);" % "".join(
+        ", " + _colarg(slot, dtype, is_scalar, "v%d[k]" % slot) for slot, (name, dtype, is_scalar) in enumerate(prog.cols)))
+    src.append("            }")
+    src.append("        } else {")
+    src.append("            for (int k = 0; k < 4; ++k) {")
+    src.append("                const hb_i64 i = first + (hb_i64)threadIdx.x * 4 + k;")
+    src.append("                if (i < p.n) {")
+    src.append("                    hb_event(p, hb_smem%s);" % "".join(
+        ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], i)" % (_loadtype(dtype), slot))
+        for slot, (name, dtype, is_scalar) in enumerate(prog.cols)))
+    src.append("                }")
+    src.append("            }")
+    src.append("        }")
+    src.append("    }")
+    if merge_lines:
+        src.append("    __syncthreads();")
+        src.extend("    " + line for line in merge_lines)
+    src.append("}")
+    return "\n".join(src) + "\n"
+
+
+def _group_lookup(hp, aux_slot):
+    """C lines that turn the group keys of one event into the slab slot of hist ``hp`` (or reject the row)."""
+    K = len(hp.groups)
+    out = ["const hb_u64* const gt = reinterpret_cast<const hb_u64*>(p.aux[%d]);" % aux_slot,
+           "bool okg = true; hb_i64 comb = 0;"]
+    for a, g in enumerate(hp.groups):
+        out.append("{")
+        if g.dtype.kind == "f" and not g.extra["nanflow"]:
+            out.append("    if (%s != %s) okg = false;        // nanflow=False: NaN rows are dropped (calc/__init__.py:189-192)" % (g.c, g.c))
+        out.append("    const int pos = hb_key_find(gt + gt[%d], (int)gt[%d], hb_keybits(%s));" % (1 + K + a, 1 + a, g.c))
+        out.append("    if (pos < 0) okg = false;")
+        out.append("    comb = comb * (hb_i64)gt[%d] + pos;" % (1 + a))
+        out.append("}")
+    out.append("int slot = -1;")
+    out.append("if (okg) slot = (int)reinterpret_cast<const hb_i64*>(gt + gt[%d])[comb];" % (1 + 2 * K))
+    return out
+
+
+def generate(spec, coltypes, options=None):
+    """The fill kernel of a spec for one set of column dtypes."""
+    options = options or {}
+    prog = Program(spec, coltypes)
+    plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
+    if len(plans) > 256:
+        raise UnsupportedError("more than 256 histograms in one fill")
+    smem = choose_strategies(plans, options)
+    if len(prog.cols) > 32:
+        raise UnsupportedError("more than 32 input fields in one fill")
+    threads = int(options.get("threads", THREADS))
+    minblocks = int(options.get("min_blocks", 2))
+
+    group_aux = {}
+    ev = list(prog.body)
+    for hp in plans:
+        ev.append("// ---- hist %d: shape %s, %s" % (hp.hid, hp.shape, hp.strategy))
+        conds = []
+        if hp.index:
+            idx = hp.index[0][0].c
+            conds.append(hp.index[0][0].extra)
+            for v, totbins in hp.index[1:]:
+                idx = "(%s) * %d + %s" % (idx, totbins, v.c)          # hist.py:402-403
+                conds.append(v.extra)
+        else:
+            idx = "0"
+        ev.append("{")
+        if hp.groups:
+            if len(group_aux) >= 64:
+                raise UnsupportedError("more than 64 histograms with group axes in one fill")
+            group_aux[hp.hid] = len(group_aux)
+            ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
+            conds = ["okg", "slot >= 0"] + conds
+        ev.append("    if (%s) {" % (" && ".join(conds) if conds else "true"))
+        ev.append("        const int bin = %s;" % idx)
+        if hp.strategy == "smem":
+            nf = 0
+            for t, e in enumerate(hp.terms):
+                if e is None:
+                    ev.append("        hb_sadd_u32(reinterpret_cast<hb_u32*>(hb_smem + %d) + bin, 1u);" % hp.smem_u32_off)
+                else:
+                    ev.append("        hb_sadd_f64(reinterpret_cast<double*>(hb_smem + %d) + %d + bin, %s);" % (hp.smem_f64_off, nf * hp.nbins, e))
+                    nf += 1
+        else:
+            if hp.groups:
+                ev.append("        double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
+            else:
+                ev.append("        double* const row = p.hist[%d] + (hb_i64)bin * %d;" % (hp.hid, hp.ncol))
+            for t, e in enumerate(hp.terms):
+                val = "1.0" if e is None else e
+                if len(hp.dest[t]) > 1:
+                    ev.append("        { const double v = %s;" % val)
+                    for col in hp.dest[t]:
+                        ev.append("          hb_red_f64(row + %d, v);" % col)
+                    ev.append("        }")
+                else:
+                    ev.append("        hb_red_f64(row + %d, %s);" % (hp.dest[t][0], val))
+        ev.append("    }")
+        ev.append("}")
+
+    merge = []
+    for hp in plans:
+        if hp.strategy != "smem":
+            continue
+        merge.append("// merge hist %d" % hp.hid)
+        merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nbins)
+        merge.append("    double* const row = p.hist[%d] + (hb_i64)b * %d;" % (hp.hid, hp.ncol))
+        nf = 0
+        for t, e in enumerate(hp.terms):
+            if e is None:
+                merge.append("    { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d)[b];" % hp.smem_u32_off)
+                merge.append("      if (c != 0u) { const double v = (double)c;")
+            else:
+                merge.append("    { const double v = reinterpret_cast<const double*>(hb_smem + %d)[%d + b];" % (hp.smem_f64_off, nf * hp.nbins))
+                merge.append("      if (v != 0.0) {")
+                nf += 1
+            for col in hp.dest[t]:
+                merge.append("        hb_red_f64(row + %d, v);" % col)
+            merge.append("      } }")
+        merge.append("}")
+
+    k = Kernel()
+    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks)
+    k.cols = list(prog.cols)
+    k.plans = plans
+    k.smem_bytes = smem
+    k.threads = threads
+    k.tile = threads * VEC
+    k.inexact = set(prog.inexact)
+    k.group_aux = group_aux
+    k.key = hashlib.sha256(k.source.encode()).hexdigest()
+    return k
+
+
+def group_goals(spec):
+    """Distinct group-axis goals of a spec: [(tree key, tree)] in first-appearance order."""
+    seen, out = set(), []
+    for h in spec["hists"]:
+        for a in h["group"]:
+            key = hbspec.tree_key(a["goal"])
+            if key not in seen:
+                seen.add(key)
+                out.append((key, a["goal"]))
+    return out
+
+
+def generate_keys(spec, coltypes, options=None):
+    """The key-discovery kernel: evaluates only the group-axis expressions and inserts every key
+    seen into one device key set per distinct group goal (numpy.unique, calc/__init__.py:150,178,182)."""
+    options = options or {}
+    goals = group_goals(spec)
+    if not goals:
+        return None
+    if len(goals) > 64:
+        raise UnsupportedError("more than 64 distinct group axes in one fill")
+    prog = Program(spec, coltypes)
+    values = [prog.lower(tree) for key, tree in goals]
+    ev = list(prog.body)
+    infos = []
+    for j, g in enumerate(values):
+        cond = ""
+        if g.dtype.kind == "f" and not g.extra["nanflow"]:
+            cond = "if (!(%s != %s)) " % (g.c, g.c)
+        ev.append("%shb_keyset_insert(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), hb_keybits(%s));" % (cond, j, g.c))
+        infos.append(dict(g.extra, kind="f" if g.dtype.kind == "f" else "i"))
+    threads = int(options.get("threads", THREADS))
+    k = Kernel()
+    k.source = _emit_kernel(prog, ev, 0, [], threads, 2)
+    k.cols = list(prog.cols)
+    k.threads = threads
+    k.tile = threads * VEC
+    k.group_goals = [(key, info) for (key, tree), info in zip(goals, infos)]
+    k.key = hashlib.sha256(k.source.encode()).hexdigest()
+    return k

@@ -1,0 +1,133 @@
+"""Bind the user's ``fill`` arguments to kernel columns.
+
+Mirrors the Param handling of ``Fillable._fill`` (histbook/fill.py:88-146): look every field up in the
+dict-like ``arrays`` (``KeyError`` -> the ``maybeconstants`` pi/e/inf/nan, else the reference's
+``ValueError``), turn non-arrays into numpy arrays, broadcast scalars, and insist on one common
+length.  New here: values may live on the device (anything with ``__cuda_array_interface__`` or
+``__dlpack__``, e.g. torch CUDA tensors); those are used in place, never copied to the host.
+"""
+import numpy
+
+from histbook_b200.codegen import DTYPE_CODE, MAYBECONSTANTS, UnsupportedError
+
+
+class Column(object):
+    __slots__ = ("name", "dtype", "is_scalar", "ptr", "location", "length", "scalar_bits", "keepalive")
+
+    def __init__(self, name):
+        self.name = name
+        self.dtype = None
+        self.is_scalar = False
+        self.ptr = None
+        self.location = 0          # 0 host, 1 device
+        self.length = None
+        self.scalar_bits = 0
+        self.keepalive = None      # whatever owns the memory `ptr` points into
+
+    def abi(self):
+        code = DTYPE_CODE[self.dtype.name]
+        if self.is_scalar:
+            return ("scalar", code, self.scalar_bits)
+        return (self.ptr, code, self.location)
+
+
+def _scalar(col, value):
+    arr = numpy.array(value)
+    if arr.dtype.name not in DTYPE_CODE:
+        raise UnsupportedError("field {0!r}: scalars of dtype {1} are not supported".format(col.name, arr.dtype))
+    col.dtype = arr.dtype
+    col.is_scalar = True
+    raw = arr.tobytes() + b"\0" * 8
+    col.scalar_bits = int.from_bytes(raw[:8], "little")
+    return col
+
+
+def _from_cuda_array_interface(col, obj, cai):
+    shape = tuple(cai["shape"])
+    dtype = numpy.dtype(cai["typestr"])
+    if len(shape) == 0:
+        # 0-d device value: fetch it (one element) and broadcast
+        import torch
+        return _scalar(col, torch.as_tensor(obj).item())
+    if len(shape) != 1:
+        raise UnsupportedError("field {0!r}: only one-dimensional device arrays can be filled".format(col.name))
+    strides = cai.get("strides")
+    if strides is not None and shape[0] > 1 and tuple(strides) != (dtype.itemsize,):
+        raise UnsupportedError("field {0!r}: device arrays must be contiguous".format(col.name))
+    if dtype.name not in DTYPE_CODE or dtype.byteorder == ">":
+        raise UnsupportedError("field {0!r}: dtype {1} is not supported by the B200 fill backend".format(col.name, dtype))
+    col.dtype = dtype
+    col.ptr = int(cai["data"][0]) if shape[0] > 0 else 0
+    col.location = 1
+    col.length = int(shape[0])
+    col.keepalive = obj
+    return col
+
+
+def bind(name, value):
+    """One fill argument -> Column."""
+    col = Column(name)
+    mod = type(value).__module__ or ""
+    if mod.startswith("torch"):
+        import torch
+        if isinstance(value, torch.Tensor):
+            if value.is_cuda:
+                if value.dim() == 1 and not value.is_contiguous():
+                    value = value.contiguous()
+                if value.dtype == torch.bool:
+                    value = value.view(torch.uint8)
+                    col = _from_cuda_array_interface(col, value, value.__cuda_array_interface__)
+                    col.dtype = numpy.dtype(numpy.bool_)
+                    return col
+                return _from_cuda_array_interface(col, value, value.__cuda_array_interface__)
+            value = value.detach().numpy()
+    cai = getattr(value, "__cuda_array_interface__", None)
+    if cai is not None:
+        return _from_cuda_array_interface(col, value, cai)
+    if not isinstance(value, numpy.ndarray):
+        if hasattr(value, "__dlpack__") and not isinstance(value, (list, tuple)):
+            import torch
+            return bind(name, torch.from_dlpack(value))
+        value = numpy.array(value)                         # fill.py:101-102,138-139
+    if value.shape == ():
+        return _scalar(col, value)
+    if value.ndim != 1:
+        raise UnsupportedError("field {0!r}: only one-dimensional arrays can be filled".format(name))
+    if value.dtype.name not in DTYPE_CODE:
+        raise UnsupportedError("field {0!r}: dtype {1} is not supported by the B200 fill backend "
+                               "(strings/objects need dictionary encoding first)".format(name, value.dtype))
+    if not value.flags.c_contiguous or value.dtype.byteorder == ">":
+        value = numpy.ascontiguousarray(value, dtype=value.dtype.newbyteorder("="))
+    col.dtype = value.dtype
+    col.ptr = value.ctypes.data if value.shape[0] > 0 else 0
+    col.location = 0
+    col.length = int(value.shape[0])
+    col.keepalive = value
+    return col
+
+
+def bind_all(fields, arrays):
+    """fields: sorted names the program needs.  Returns (columns by name, length)."""
+    cols = {}
+    for name in fields:
+        try:
+            value = arrays[name]
+        except KeyError:
+            if name in MAYBECONSTANTS:                     # fill.py:96,133-134
+                cols[name] = _scalar(Column(name), numpy.float64(MAYBECONSTANTS[name]))
+                continue
+            raise ValueError("required field {0} not found in fill arguments".format(repr(name)))
+        cols[name] = bind(name, value)
+
+    length = None
+    for name in fields:                                    # fill.py:88-110
+        if not cols[name].is_scalar:
+            length = cols[name].length
+            break
+    if length is None:
+        length = 1
+    for name in fields:                                    # fill.py:143-144
+        c = cols[name]
+        if not c.is_scalar and c.length != length:
+            raise ValueError("array {0} has len {1} but other arrays have len {2}".format(repr(name), c.length, length))
+    return cols, length

@@ -1,0 +1,681 @@
+// hbfill.cu -- libhbfill.so: C ABI (include/hbfill.h) of the B200-native histbook fill engine.
+//
+// Host side: NVRTC compile + module load of the generated per-book kernel, float64 arenas for the bin
+// contents, the launch loop (device-resident columns in place, host columns through double-buffered
+// staging), and a few hand-written utility kernels (arena algebra, L2 flush).  The per-event work is in
+// the generated kernel (histbook_b200/codegen.py + csrc/hb_template.cuh).
+//
+// Built by __graft_entry__.build():
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC hbfill.cu -ldl
+// Neither libcuda nor libnvrtc is linked: both are resolved with dlopen (driver at hb_init, NVRTC at the first
+// compile), so the library loads -- and can NVRTC-compile -- on a machine without a GPU.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hbfill.h"
+#include "hb_template.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(HB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+extern "C" const char* hb_last_error(void) { return g_err.c_str(); }
+extern "C" int hb_version(void) { return 1; }
+extern "C" void hb_free(void* p) { free(p); }
+
+// ------------------------------------------------------------------------------------------------
+// driver API through dlopen
+
+struct Driver {
+    void* lib = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+};
+
+static Driver g_drv;
+static std::mutex g_mutex;
+static int g_device = -1;
+static int g_sm_count = 0;
+static int g_max_smem_optin = 0;
+static cudaStream_t g_stream = 0;          // compute stream (default: legacy stream 0, ordered with torch's default)
+static cudaStream_t g_copy_stream = 0;     // non-blocking stream for host -> device staging
+static int64_t g_chunk_events = (int64_t)1 << 24;
+
+static std::string drv_err(CUresult r) {
+    const char* s = nullptr;
+    if (g_drv.GetErrorString && g_drv.GetErrorString(r, &s) == CUDA_SUCCESS && s) return s;
+    return "CUresult " + std::to_string((int)r);
+}
+
+#define DRV_TRY(call)                                                                          \
+    do {                                                                                       \
+        CUresult r_ = (call);                                                                  \
+        if (r_ != CUDA_SUCCESS) return fail(HB_ERR_CUDA, std::string(#call) + ": " + drv_err(r_)); \
+    } while (0)
+
+static int load_driver() {
+    if (g_drv.lib) return HB_OK;
+    void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(HB_ERR_CUDA, "libcuda.so.1 not found: no NVIDIA driver on this machine (there is no CPU fallback)");
+#define SYM(field, name)                                                                       \
+    *(void**)(&g_drv.field) = dlsym(lib, name);                                                \
+    if (!g_drv.field) return fail(HB_ERR_CUDA, std::string("missing driver symbol ") + name)
+    SYM(ModuleLoadData, "cuModuleLoadData");
+    SYM(ModuleUnload, "cuModuleUnload");
+    SYM(ModuleGetFunction, "cuModuleGetFunction");
+    SYM(FuncSetAttribute, "cuFuncSetAttribute");
+    SYM(FuncGetAttribute, "cuFuncGetAttribute");
+    SYM(LaunchKernel, "cuLaunchKernel");
+    SYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    SYM(GetErrorString, "cuGetErrorString");
+#undef SYM
+    g_drv.lib = lib;
+    return HB_OK;
+}
+
+static int ensure_device() {
+    if (g_device < 0) return fail(HB_ERR_CUDA, "hb_init has not been called");
+    CUDA_TRY(cudaSetDevice(g_device));
+    return HB_OK;
+}
+
+extern "C" int hb_init(int device) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int rc = load_driver();
+    if (rc) return rc;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(HB_ERR_ARG, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(0));                        // make the primary context current
+    if (g_device != device) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        g_sm_count = prop.multiProcessorCount;
+        g_max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        if (g_copy_stream) { cudaStreamDestroy(g_copy_stream); g_copy_stream = 0; }
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        g_device = device;
+    }
+    return HB_OK;
+}
+
+extern "C" int hb_device_info(int* sm_count, int* max_smem_optin, int64_t* free_bytes, int64_t* total_bytes) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    size_t f = 0, t = 0;
+    CUDA_TRY(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = g_sm_count;
+    if (max_smem_optin) *max_smem_optin = g_max_smem_optin;
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return HB_OK;
+}
+
+extern "C" int hb_set_stream(void* s) { g_stream = (cudaStream_t)s; return HB_OK; }
+
+extern "C" int hb_sync(void) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_copy_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_set_chunk_events(int64_t events) {
+    if (events < 4096) return fail(HB_ERR_ARG, "chunk too small");
+    g_chunk_events = events;
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// programs
+
+struct hb_program {
+    CUmodule module = nullptr;
+    CUfunction fn = nullptr;
+    int threads = 256;
+    int smem = 0;
+    int blocks_per_sm = 1;
+    int regs = 0;
+    int static_smem = 0;
+};
+
+// NVRTC is resolved with dlopen by absolute path first: a process that imported torch already holds torch's
+// bundled libnvrtc.so.12 (CUDA 12.8), and a plain -lnvrtc would silently bind to that older copy (same soname),
+// whose ptxas rejects the 256-bit loads of hb_template.cuh.  Opening the toolkit's file by path gives a
+// separate, private copy.
+struct Nvrtc {
+    void* lib = nullptr;
+    nvrtcResult (*Version)(int*, int*) = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    int major = 0, minor = 0;
+};
+static Nvrtc g_nvrtc;
+
+static int load_nvrtc() {
+    if (g_nvrtc.lib) return HB_OK;
+    std::vector<std::string> names;
+    if (const char* env = getenv("HB_NVRTC_PATH")) names.push_back(env);
+    names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    names.push_back("/usr/local/cuda/targets/x86_64-linux/lib/libnvrtc.so.12");
+    names.push_back("libnvrtc.so.12");
+    names.push_back("libnvrtc.so");
+    void* lib = nullptr;
+    std::string tried;
+    for (const std::string& n : names) {
+        lib = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (lib) break;
+        tried += n + " ";
+    }
+    if (!lib) return fail(HB_ERR_NVRTC, "libnvrtc not found (tried: " + tried + ")");
+#define SYM(field, name)                                                                       \
+    *(void**)(&g_nvrtc.field) = dlsym(lib, name);                                              \
+    if (!g_nvrtc.field) return fail(HB_ERR_NVRTC, std::string("missing NVRTC symbol ") + name)
+    SYM(Version, "nvrtcVersion");
+    SYM(CreateProgram, "nvrtcCreateProgram");
+    SYM(CompileProgram, "nvrtcCompileProgram");
+    SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    SYM(GetProgramLog, "nvrtcGetProgramLog");
+    SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    SYM(GetCUBIN, "nvrtcGetCUBIN");
+    SYM(DestroyProgram, "nvrtcDestroyProgram");
+    SYM(GetErrorString, "nvrtcGetErrorString");
+#undef SYM
+    g_nvrtc.Version(&g_nvrtc.major, &g_nvrtc.minor);
+    g_nvrtc.lib = lib;
+    return HB_OK;
+}
+
+extern "C" int hb_nvrtc_version(void) {
+    if (load_nvrtc()) return -1;
+    return g_nvrtc.major * 1000 + g_nvrtc.minor * 10;
+}
+
+extern "C" int hb_program_compile(const char* source, const char* header, int lineinfo,
+                                  void** cubin, size_t* cubin_size) {
+    if (!source || !header || !cubin || !cubin_size) return fail(HB_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int rc = load_nvrtc();
+    if (rc) return rc;
+    nvrtcProgram prog;
+    const char* headers[1] = {header};
+    const char* names[1] = {"hb_template.cuh"};
+    nvrtcResult r = g_nvrtc.CreateProgram(&prog, source, "hb_fill_generated.cu", 1, headers, names);
+    if (r != NVRTC_SUCCESS) return fail(HB_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r));
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17",
+                                     "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
+    // LDG.256 (ld.global.v4.u64) needs the CUDA >= 12.9 ptxas
+    if (g_nvrtc.major > 12 || (g_nvrtc.major == 12 && g_nvrtc.minor >= 9)) opts.push_back("-DHB_LDG256=1");
+    if (lineinfo) opts.push_back("-lineinfo");
+    r = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        g_nvrtc.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+        g_nvrtc.DestroyProgram(&prog);
+        return fail(HB_ERR_NVRTC, std::string("NVRTC: ") + g_nvrtc.GetErrorString(r) + "\n" + log);
+    }
+    size_t n = 0;
+    r = g_nvrtc.GetCUBINSize(prog, &n);
+    if (r != NVRTC_SUCCESS || n == 0) {
+        g_nvrtc.DestroyProgram(&prog);
+        return fail(HB_ERR_NVRTC, "nvrtcGetCUBINSize failed");
+    }
+    void* out = malloc(n);
+    g_nvrtc.GetCUBIN(prog, (char*)out);
+    g_nvrtc.DestroyProgram(&prog);
+    *cubin = out;
+    *cubin_size = n;
+    return HB_OK;
+}
+
+extern "C" int hb_program_load(const void* cubin, size_t cubin_size, const char* kernel_name,
+                               int threads, int smem_bytes, hb_program** out) {
+    (void)cubin_size;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!cubin || !kernel_name || !out) return fail(HB_ERR_ARG, "null argument");
+    if (smem_bytes > g_max_smem_optin)
+        return fail(HB_ERR_ARG, "kernel needs more dynamic shared memory than the device allows");
+    hb_program* p = new hb_program();
+    p->threads = threads;
+    p->smem = smem_bytes;
+    CUresult r = g_drv.ModuleLoadData(&p->module, cubin);
+    if (r != CUDA_SUCCESS) { delete p; return fail(HB_ERR_CUDA, "cuModuleLoadData: " + drv_err(r)); }
+    r = g_drv.ModuleGetFunction(&p->fn, p->module, kernel_name);
+    if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(p->module); delete p; return fail(HB_ERR_CUDA, "cuModuleGetFunction: " + drv_err(r)); }
+    if (smem_bytes > 48 * 1024) {
+        r = g_drv.FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_bytes);
+        if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(p->module); delete p; return fail(HB_ERR_CUDA, "cuFuncSetAttribute(smem): " + drv_err(r)); }
+    }
+    g_drv.FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn);
+    g_drv.FuncGetAttribute(&p->static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn);
+    int occ = 0;
+    r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->fn, threads, (size_t)smem_bytes);
+    if (r != CUDA_SUCCESS || occ < 1) { g_drv.ModuleUnload(p->module); delete p; return fail(HB_ERR_CUDA, "kernel cannot be resident on an SM (occupancy 0)"); }
+    p->blocks_per_sm = occ;
+    *out = p;
+    return HB_OK;
+}
+
+extern "C" int hb_program_destroy(hb_program* p) {
+    if (!p) return HB_OK;
+    if (p->module && g_drv.ModuleUnload) g_drv.ModuleUnload(p->module);
+    delete p;
+    return HB_OK;
+}
+
+extern "C" int hb_program_info(const hb_program* p, int* regs, int* static_smem, int* blocks_per_sm) {
+    if (!p) return fail(HB_ERR_ARG, "null program");
+    if (regs) *regs = p->regs;
+    if (static_smem) *static_smem = p->static_smem;
+    if (blocks_per_sm) *blocks_per_sm = p->blocks_per_sm;
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// arenas
+
+struct hb_arena {
+    double* ptr = nullptr;
+    int64_t n = 0;
+};
+
+__global__ void hb_axpy_kernel(double* __restrict__ dst, const double* __restrict__ src, double alpha, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = dst[i] + alpha * src[i];
+}
+__global__ void hb_scale_kernel(double* __restrict__ dst, double alpha, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = dst[i] * alpha;
+}
+__global__ void hb_flush_kernel(float4* __restrict__ buf, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+static int grid_for(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    int64_t cap = (int64_t)(g_sm_count > 0 ? g_sm_count : 148) * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int hb_arena_create(int64_t ndoubles, hb_arena** out) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (ndoubles < 0 || !out) return fail(HB_ERR_ARG, "bad arena size");
+    hb_arena* a = new hb_arena();
+    a->n = ndoubles;
+    size_t bytes = (size_t)(ndoubles > 0 ? ndoubles : 1) * sizeof(double);
+    cudaError_t e = cudaMalloc((void**)&a->ptr, bytes);
+    if (e != cudaSuccess) { delete a; return fail(HB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    e = cudaMemsetAsync(a->ptr, 0, bytes, g_stream);
+    if (e != cudaSuccess) { cudaFree(a->ptr); delete a; return fail(HB_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); }
+    *out = a;
+    return HB_OK;
+}
+
+extern "C" int hb_arena_destroy(hb_arena* a) {
+    if (!a) return HB_OK;
+    if (a->ptr) cudaFree(a->ptr);
+    delete a;
+    return HB_OK;
+}
+
+extern "C" int hb_arena_clear(hb_arena* a) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!a) return fail(HB_ERR_ARG, "null arena");
+    CUDA_TRY(cudaMemsetAsync(a->ptr, 0, (size_t)a->n * sizeof(double), g_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_arena_clone(const hb_arena* src, hb_arena** out) {
+    if (!src) return fail(HB_ERR_ARG, "null arena");
+    int rc = hb_arena_create(src->n, out);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync((*out)->ptr, src->ptr, (size_t)src->n * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_arena_resize(hb_arena* a, int64_t ndoubles) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!a || ndoubles < 0) return fail(HB_ERR_ARG, "bad arena size");
+    if (ndoubles == a->n) return HB_OK;
+    double* fresh = nullptr;
+    size_t bytes = (size_t)(ndoubles > 0 ? ndoubles : 1) * sizeof(double);
+    CUDA_TRY(cudaMalloc((void**)&fresh, bytes));
+    CUDA_TRY(cudaMemsetAsync(fresh, 0, bytes, g_stream));
+    int64_t keep = ndoubles < a->n ? ndoubles : a->n;
+    if (keep > 0) CUDA_TRY(cudaMemcpyAsync(fresh, a->ptr, (size_t)keep * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    cudaFree(a->ptr);
+    a->ptr = fresh;
+    a->n = ndoubles;
+    return HB_OK;
+}
+
+extern "C" int hb_arena_read(const hb_arena* a, int64_t offset, int64_t count, double* host_out) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!a || offset < 0 || count < 0 || offset + count > a->n || !host_out) return fail(HB_ERR_ARG, "arena read out of range");
+    CUDA_TRY(cudaMemcpyAsync(host_out, a->ptr + offset, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_arena_write(hb_arena* a, int64_t offset, int64_t count, const double* host_in) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!a || offset < 0 || count < 0 || offset + count > a->n || !host_in) return fail(HB_ERR_ARG, "arena write out of range");
+    CUDA_TRY(cudaMemcpyAsync(a->ptr + offset, host_in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_arena_axpy(hb_arena* dst, const hb_arena* src, double alpha) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!dst || !src || dst->n != src->n) return fail(HB_ERR_ARG, "arena sizes differ");
+    if (dst->n == 0) return HB_OK;
+    hb_axpy_kernel<<<grid_for(dst->n), 256, 0, g_stream>>>(dst->ptr, src->ptr, alpha, dst->n);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+extern "C" int hb_arena_scale(hb_arena* dst, double alpha) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!dst) return fail(HB_ERR_ARG, "null arena");
+    if (dst->n == 0) return HB_OK;
+    hb_scale_kernel<<<grid_for(dst->n), 256, 0, g_stream>>>(dst->ptr, alpha, dst->n);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+extern "C" void* hb_arena_ptr(const hb_arena* a) { return a ? (void*)a->ptr : nullptr; }
+extern "C" int64_t hb_arena_size(const hb_arena* a) { return a ? a->n : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// fill
+
+static const int kDtypeSize[11] = {8, 4, 8, 4, 2, 1, 8, 4, 2, 1, 1};
+
+struct Staging {
+    void* dev[2][HB_MAX_COLS] = {};
+    size_t cap[2][HB_MAX_COLS] = {};
+    cudaEvent_t copied[2] = {};
+    cudaEvent_t consumed[2] = {};
+    bool init = false;
+};
+static Staging g_stage;
+
+static int staging_reserve(int buf, int col, size_t bytes) {
+    if (g_stage.cap[buf][col] >= bytes) return HB_OK;
+    if (g_stage.dev[buf][col]) cudaFree(g_stage.dev[buf][col]);
+    g_stage.dev[buf][col] = nullptr;
+    g_stage.cap[buf][col] = 0;
+    CUDA_TRY(cudaMalloc(&g_stage.dev[buf][col], bytes));
+    g_stage.cap[buf][col] = bytes;
+    return HB_OK;
+}
+
+static int launch(hb_program* prog, const HbParams& params, int grid) {
+    void* args[1] = {(void*)&params};
+    DRV_TRY(g_drv.LaunchKernel(prog->fn, (unsigned)grid, 1, 1, (unsigned)prog->threads, 1, 1,
+                               (unsigned)prog->smem, (CUstream)g_stream, args, nullptr));
+    return HB_OK;
+}
+
+extern "C" int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
+                       int nhists, hb_arena* const* hists, int naux, const void* const* aux,
+                       int flags, hb_stats* stats) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!prog || ncols < 0 || ncols > HB_MAX_COLS || nhists < 0 || nhists > HB_MAX_HISTS || naux < 0 || naux > HB_MAX_AUX || n < 0)
+        return fail(HB_ERR_ARG, "bad hb_fill arguments");
+    std::lock_guard<std::mutex> lock(g_mutex);
+
+    HbParams base;
+    memset(&base, 0, sizeof(base));
+    bool any_host = false;
+    for (int c = 0; c < ncols; ++c) {
+        if (cols[c].dtype < 0 || cols[c].dtype > 10) return fail(HB_ERR_ARG, "bad column dtype");
+        if (cols[c].is_scalar) base.scal[c] = cols[c].scalar_bits;
+        else {
+            if (!cols[c].ptr && n > 0) return fail(HB_ERR_ARG, "null column pointer");
+            if (cols[c].location == 0) any_host = true;
+        }
+    }
+    for (int h = 0; h < nhists; ++h) {
+        if (!hists[h]) return fail(HB_ERR_ARG, "null arena");
+        base.hist[h] = hists[h]->ptr;
+    }
+    for (int a = 0; a < naux; ++a) base.aux[a] = aux[a];
+
+    const int tile = prog->threads * 4;
+    const int resident = g_sm_count * prog->blocks_per_sm;
+    int64_t per_launch = any_host ? g_chunk_events : ((int64_t)1 << 30);
+    per_launch = per_launch / tile * tile;
+    if (per_launch < tile) per_launch = tile;
+
+    hb_stats st;
+    memset(&st, 0, sizeof(st));
+    st.blocks_per_sm = prog->blocks_per_sm;
+
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (flags & HB_FILL_TIMED) {
+        CUDA_TRY(cudaEventCreate(&t0));
+        CUDA_TRY(cudaEventCreate(&t1));
+        CUDA_TRY(cudaEventRecord(t0, g_stream));
+    }
+    if (any_host && !g_stage.init) {
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&g_stage.copied[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&g_stage.consumed[b], cudaEventDisableTiming));
+        }
+        g_stage.init = true;
+    }
+
+    int chunk_index = 0;
+    for (int64_t off = 0; off < n; off += per_launch, ++chunk_index) {
+        const int64_t m = (n - off < per_launch) ? (n - off) : per_launch;
+        HbParams p = base;
+        p.n = m;
+        p.flags = flags;
+        const int buf = chunk_index & 1;
+        if (any_host && chunk_index >= 2)        // staging buffer reuse: wait until the kernel two chunks back is done
+            CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, g_stage.consumed[buf], 0));
+        bool aligned = true;
+        for (int c = 0; c < ncols; ++c) {
+            if (cols[c].is_scalar) continue;
+            const size_t esize = (size_t)kDtypeSize[cols[c].dtype];
+            const char* src = (const char*)cols[c].ptr + (size_t)off * esize;
+            if (cols[c].location == 0) {
+                rc = staging_reserve(buf, c, (size_t)per_launch * esize);
+                if (rc) return rc;
+                CUDA_TRY(cudaMemcpyAsync(g_stage.dev[buf][c], src, (size_t)m * esize, cudaMemcpyHostToDevice, g_copy_stream));
+                st.h2d_bytes += (int64_t)((size_t)m * esize);
+                p.cols[c] = g_stage.dev[buf][c];
+            } else {
+                p.cols[c] = src;
+            }
+            if (((uintptr_t)p.cols[c]) % (4 * esize) != 0) aligned = false;
+        }
+        p.vec_ok = aligned ? 1 : 0;
+        if (any_host) {
+            CUDA_TRY(cudaEventRecord(g_stage.copied[buf], g_copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(g_stream, g_stage.copied[buf], 0));
+        }
+        int64_t ntiles = (m + tile - 1) / tile;
+        int grid = (int)(ntiles < resident ? ntiles : resident);
+        if (grid < 1) grid = 1;
+        rc = launch(prog, p, grid);
+        if (rc) return rc;
+        if (any_host) CUDA_TRY(cudaEventRecord(g_stage.consumed[buf], g_stream));
+        st.launches += 1;
+        st.grid = grid;
+    }
+    st.events = n;
+    if (any_host) CUDA_TRY(cudaStreamSynchronize(g_copy_stream));   // caller may now reuse / free its host columns
+    if (flags & HB_FILL_TIMED) {
+        CUDA_TRY(cudaEventRecord(t1, g_stream));
+        CUDA_TRY(cudaEventSynchronize(t1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, t0, t1));
+        st.ms_kernel = ms;
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+    }
+    if (stats) *stats = st;
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// key sets
+
+struct hb_keyset {
+    hb_u64* table = nullptr;     // HbKeySet header (4 words) + slots
+    int capacity = 0;
+};
+
+__global__ void hb_keyset_init_kernel(hb_u64* table, int capacity) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { table[0] = (hb_u64)capacity; table[1] = 0; table[2] = 0; table[3] = 0; }
+    if (i < capacity) table[4 + i] = HB_KEY_EMPTY;
+}
+
+extern "C" int hb_keyset_clear(hb_keyset* ks) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!ks) return fail(HB_ERR_ARG, "null keyset");
+    hb_keyset_init_kernel<<<(ks->capacity + 255) / 256, 256, 0, g_stream>>>(ks->table, ks->capacity);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+extern "C" int hb_keyset_create(int capacity, hb_keyset** out) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (capacity < 2 || (capacity & (capacity - 1)) != 0 || !out) return fail(HB_ERR_ARG, "keyset capacity must be a power of two");
+    hb_keyset* ks = new hb_keyset();
+    ks->capacity = capacity;
+    cudaError_t e = cudaMalloc((void**)&ks->table, (size_t)(capacity + 4) * sizeof(hb_u64));
+    if (e != cudaSuccess) { delete ks; return fail(HB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    rc = hb_keyset_clear(ks);
+    if (rc) { cudaFree(ks->table); delete ks; return rc; }
+    *out = ks;
+    return HB_OK;
+}
+
+extern "C" int hb_keyset_destroy(hb_keyset* ks) {
+    if (!ks) return HB_OK;
+    if (ks->table) cudaFree(ks->table);
+    delete ks;
+    return HB_OK;
+}
+
+extern "C" void* hb_keyset_ptr(const hb_keyset* ks) { return ks ? (void*)ks->table : nullptr; }
+
+extern "C" int hb_keyset_read(const hb_keyset* ks, uint64_t* keys_out, int max_keys, int* nkeys, int* overflowed) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!ks || !nkeys) return fail(HB_ERR_ARG, "null keyset");
+    std::vector<hb_u64> host((size_t)ks->capacity + 4);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), ks->table, host.size() * sizeof(hb_u64), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    int count = 0;
+    for (int i = 0; i < ks->capacity; ++i) {
+        if (host[4 + i] != HB_KEY_EMPTY) {
+            if (keys_out && count < max_keys) keys_out[count] = host[4 + i];
+            ++count;
+        }
+    }
+    *nkeys = count;
+    if (overflowed) *overflowed = (int)host[2];
+    if (count > max_keys && keys_out) return fail(HB_ERR_OVERFLOW, "more keys than the output buffer holds");
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utilities
+
+static void* g_flush_buf = nullptr;
+static const size_t kFlushBytes = (size_t)256 << 20;     // 256 MiB > 126 MB L2
+
+extern "C" int hb_flush_l2(void) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!g_flush_buf) CUDA_TRY(cudaMalloc(&g_flush_buf, kFlushBytes));
+    hb_flush_kernel<<<g_sm_count * 8, 256, 0, g_stream>>>((float4*)g_flush_buf, (int64_t)(kFlushBytes / sizeof(float4)));
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+extern "C" int hb_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return HB_OK;
+}
+
+extern "C" int hb_device_malloc(size_t bytes, void** out) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+    return HB_OK;
+}
+
+extern "C" int hb_device_free(void* p) {
+    if (p) cudaFree(p);
+    return HB_OK;
+}

@@ -1,0 +1,138 @@
+/* hbfill.h -- C ABI of libhbfill.so, the B200-native fill engine behind histbook's Hist/Book API.
+ *
+ * The reference (scikit-hep/histbook 1.2.5) is pure Python + numpy and has no FFI of its own; the only
+ * alternate-backend precedent is the Spark dispatch in Hist.fill / Book.fill (histbook/hist.py:355-359,
+ * histbook/book.py:557-565).  The entry points below are what a binding for the fill hot path needs, and
+ * each one names the reference code it stands in for:
+ *
+ *   hb_program_compile / hb_program_load   Fillable.fields (histbook/fill.py:41-59): build the instruction
+ *                                          program once per Hist/Book -- here: NVRTC-compile one fused
+ *                                          sm_100a kernel generated from the goal trees
+ *   hb_arena_create / _clear / _clone      Hist._prefill (histbook/hist.py:381-390), Hist.clear (:93-95),
+ *                                          Hist.copy / copyonfill (:80-91): float64 bin contents
+ *   hb_fill                                Fillable._fill (histbook/fill.py:85-162) + Hist._postfill
+ *                                          (histbook/hist.py:392-504): evaluate, index, scatter-accumulate
+ *   hb_arena_read / hb_arena_write         every reader / writer of Hist._content (histbook/proj.py:498-640,
+ *                                          histbook/hist.py:731,741): host copies of device-resident bins
+ *   hb_arena_axpy / hb_arena_scale         Hist.__add__/__iadd__/__mul__/__imul__ (histbook/hist.py:506-607)
+ *   hb_keyset_*                            numpy.unique in histbook_groupby / histbook_groupbin
+ *                                          (histbook/calc/__init__.py:149-201)
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a non-zero status otherwise,
+ * with a thread-local message available from hb_last_error().  The library never keeps a column pointer
+ * after hb_fill returns and never frees caller memory.  Handles are owned by the caller.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with HB_ERR_CUDA.
+ */
+#ifndef HBFILL_H
+#define HBFILL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_CUDA 1       /* CUDA runtime / driver error, or no device */
+#define HB_ERR_NVRTC 2      /* kernel compilation failed (log in hb_last_error) */
+#define HB_ERR_ARG 3        /* invalid argument */
+#define HB_ERR_OVERFLOW 4   /* a device-side table is full (key sets) */
+
+#define HB_MAX_COLS 32
+#define HB_MAX_HISTS 256
+#define HB_MAX_AUX 64
+
+/* column dtypes (numpy names) */
+enum hb_dtype {
+    HB_F64 = 0, HB_F32 = 1, HB_I64 = 2, HB_I32 = 3, HB_I16 = 4, HB_I8 = 5,
+    HB_U64 = 6, HB_U32 = 7, HB_U16 = 8, HB_U8 = 9, HB_BOOL = 10
+};
+
+typedef struct hb_program hb_program;   /* a loaded fill kernel */
+typedef struct hb_arena hb_arena;       /* float64 bin contents on the device */
+
+typedef struct {
+    const void* ptr;        /* first element (host or device memory); ignored for scalars */
+    int32_t dtype;          /* enum hb_dtype */
+    int32_t location;       /* 0 = host memory, 1 = device memory of the current device */
+    int32_t is_scalar;      /* 1 = broadcast scalar, value in scalar_bits */
+    int32_t reserved;
+    uint64_t scalar_bits;   /* raw little-endian bits of the scalar, in `dtype` */
+} hb_column;
+
+typedef struct {
+    int64_t events;         /* events processed */
+    int64_t h2d_bytes;      /* bytes copied host -> device for this call */
+    int32_t launches;       /* fill-kernel launches */
+    int32_t grid;           /* blocks per launch */
+    int32_t blocks_per_sm;  /* resident blocks per SM the grid was sized for */
+    int32_t reserved;
+    double ms_kernel;       /* device time of the launches (only with HB_FILL_TIMED) */
+} hb_stats;
+
+#define HB_FILL_TIMED 1     /* bracket the launches with CUDA events and synchronise (fills hb_stats.ms_kernel) */
+
+const char* hb_last_error(void);
+int hb_version(void);
+int hb_nvrtc_version(void);                               /* e.g. 12090; -1 if NVRTC cannot be loaded */
+
+/* device ------------------------------------------------------------------------------------------------ */
+int hb_init(int device);                                 /* select the device (idempotent), load the driver */
+int hb_device_info(int* sm_count, int* max_smem_optin, int64_t* free_bytes, int64_t* total_bytes);
+int hb_set_stream(void* cuda_stream);                    /* compute stream for all later calls (default: stream 0) */
+int hb_sync(void);
+int hb_set_chunk_events(int64_t events);                 /* staging chunk for host-resident columns */
+
+/* programs ---------------------------------------------------------------------------------------------- */
+/* NVRTC only -- needs no GPU.  `header` is the text of hb_template.cuh, made available as
+ * #include "hb_template.cuh".  On success *cubin is malloc'ed (release with hb_free). */
+int hb_program_compile(const char* source, const char* header, int lineinfo,
+                       void** cubin, size_t* cubin_size);
+int hb_program_load(const void* cubin, size_t cubin_size, const char* kernel_name,
+                    int threads, int smem_bytes, hb_program** out);
+int hb_program_destroy(hb_program* prog);
+int hb_program_info(const hb_program* prog, int* regs, int* static_smem, int* blocks_per_sm);
+void hb_free(void* p);
+
+/* arenas ------------------------------------------------------------------------------------------------ */
+int hb_arena_create(int64_t ndoubles, hb_arena** out);   /* zero-filled */
+int hb_arena_destroy(hb_arena* a);
+int hb_arena_clear(hb_arena* a);
+int hb_arena_clone(const hb_arena* src, hb_arena** out);
+int hb_arena_resize(hb_arena* a, int64_t ndoubles);      /* keeps the common prefix, zero-fills growth */
+int hb_arena_read(const hb_arena* a, int64_t offset, int64_t count, double* host_out);
+int hb_arena_write(hb_arena* a, int64_t offset, int64_t count, const double* host_in);
+int hb_arena_axpy(hb_arena* dst, const hb_arena* src, double alpha);   /* dst += alpha * src */
+int hb_arena_scale(hb_arena* dst, double alpha);                       /* dst *= alpha */
+void* hb_arena_ptr(const hb_arena* a);                   /* device pointer (for NCCL / DLPack wrapping) */
+int64_t hb_arena_size(const hb_arena* a);
+
+/* fill -------------------------------------------------------------------------------------------------- */
+/* One pass over n events: every histogram of the program is updated in place.  Device columns are used
+ * where they lie; host columns are streamed through double-buffered staging.  Returns after the work is
+ * enqueued (device columns) or after the last host chunk has been copied (host columns). */
+int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
+            int nhists, hb_arena* const* hists, int naux, const void* const* aux,
+            int flags, hb_stats* stats);
+
+/* key sets (group axes) --------------------------------------------------------------------------------- */
+/* A device-side set of 64-bit keys (raw bits of float64 / int64 group keys), capacity a power of two. */
+typedef struct hb_keyset hb_keyset;
+int hb_keyset_create(int capacity, hb_keyset** out);
+int hb_keyset_destroy(hb_keyset* ks);
+int hb_keyset_clear(hb_keyset* ks);
+void* hb_keyset_ptr(const hb_keyset* ks);                /* device table, passed to discovery kernels via aux[] */
+int hb_keyset_read(const hb_keyset* ks, uint64_t* keys_out, int max_keys, int* nkeys, int* overflowed);
+
+/* utilities ---------------------------------------------------------------------------------------------- */
+int hb_flush_l2(void);                                   /* overwrite a buffer larger than L2 (benchmark hygiene) */
+int hb_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+int hb_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int hb_device_malloc(size_t bytes, void** out);
+int hb_device_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBFILL_H */

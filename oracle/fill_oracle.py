@@ -46,10 +46,6 @@ MAYBECONSTANTS = {"pi": numpy.pi, "Pi": numpy.pi, "e": numpy.e, "E": numpy.e,
 # ----------------------------------------------------------------------------- elementwise library
 # calc/__init__.py:38-103: the name -> numpy ufunc table
 
-def _isin(x, values):
-    return numpy.isin(x, values if not isinstance(values, (set, frozenset)) else list(values))
-
-
 LIBRARY = {
     "numpy.add": numpy.add, "numpy.subtract": numpy.subtract, "numpy.multiply": numpy.multiply,
     "numpy.true_divide": numpy.true_divide, "numpy.equal": numpy.equal,
@@ -246,8 +242,8 @@ def _call(fcn, args):
     if fcn.startswith("histbook.groupbin"):
         f = fcn[len("histbook.groupbin"):]
         return op_groupbin(args[0], args[1], args[2], f[0] == "N", f[1] == "L")
-    if fcn == "numpy.isin":
-        return _isin(args[0], args[1])
+    # note: "x in {1, 2}" reaches numpy.isin with a Python *set* (expr.py:185-193), which numpy
+    # turns into a 0-d object array -> every element compares False (reference behaviour, kept).
     if fcn in LIBRARY:
         return LIBRARY[fcn](*args)
     # calc/__init__.py:353-357: anything else (e.g. "round", "//") is an AssertionError at fill time
@@ -374,8 +370,10 @@ def _new_content(h, level):
     return {}
 
 
-def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length):
-    """hist.py:429-456 (fillblock)."""
+def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length, absolute=False):
+    """hist.py:429-456 (fillblock).  ``absolute`` (tests only) accumulates |term| instead of term: the
+    per-bin sum of magnitudes that the float tolerance is stated against."""
+    A = numpy.absolute if absolute else (lambda v: v)
     ncol = h["shape"][-1]
     flat = content.reshape((-1, ncol))
     for p, sumx, sumx2 in zip(h["profile"], sumxs, sumx2s):
@@ -386,14 +384,14 @@ def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length):
             if mask is not numpy.ma.nomask:
                 weight = weight[~mask]
                 weight2 = weight2[~mask]
-        numpy.add.at(flat[:, p["sumwx"]], indexes.compressed(), sumx * weight)
-        numpy.add.at(flat[:, p["sumwx2"]], indexes.compressed(), sumx2 * weight)
+        numpy.add.at(flat[:, p["sumwx"]], indexes.compressed(), A(sumx * weight))
+        numpy.add.at(flat[:, p["sumwx2"]], indexes.compressed(), A(sumx2 * weight))
 
     if weight2 is None:
         if indexes is None:
-            flat[:, h["sumw"]] += (1 if length is None else length) * weight
+            flat[:, h["sumw"]] += A((1 if length is None else length) * weight)
         else:
-            numpy.add.at(flat[:, h["sumw"]], indexes.compressed(), weight)
+            numpy.add.at(flat[:, h["sumw"]], indexes.compressed(), A(weight))
     else:
         if indexes is None:
             indexes = numpy.ma.zeros(len(weight), dtype=INDEXTYPE)
@@ -401,14 +399,14 @@ def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length):
         if mask is not numpy.ma.nomask:
             weight = weight[~mask]
             weight2 = weight2[~mask]
-        numpy.add.at(flat[:, h["sumw"]], indexes.compressed(), weight)
-        numpy.add.at(flat[:, h["sumw2"]], indexes.compressed(), weight2)
+        numpy.add.at(flat[:, h["sumw"]], indexes.compressed(), A(weight))
+        numpy.add.at(flat[:, h["sumw2"]], indexes.compressed(), A(weight2))
 
 
-def _fill_dict(h, groups, level, content, indexes, sumxs, sumx2s, weight, weight2, allsel, length):
+def _fill_dict(h, groups, level, content, indexes, sumxs, sumx2s, weight, weight2, allsel, length, absolute=False):
     """hist.py:458-499 (filldict): one boolean selection per unique key."""
     if level == len(groups):
-        _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length)
+        _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length, absolute)
         return
     uniques, inverse = groups[level]
     for idx, unique in enumerate(uniques):
@@ -434,10 +432,10 @@ def _fill_dict(h, groups, level, content, indexes, sumxs, sumx2s, weight, weight
             suball = allsel.copy()
             suball[inverse != idx] = False
         _fill_dict(h, groups, level + 1, content[unique], subindexes, subsumxs, subsumx2s,
-                   subweight, subweight2, suball, length)
+                   subweight, subweight2, suball, length, absolute)
 
 
-def _postfill(h, interp, content, length):
+def _postfill(h, interp, content, length, absolute=False):
     # hist.py:393-405: row-major linearisation in (masked) int32
     indexes = None
     step = 0
@@ -475,10 +473,10 @@ def _postfill(h, interp, content, length):
             weight2[sel] = 0.0
 
     groups = [interp(a["goal"]) for a in h["group"]]
-    _fill_dict(h, groups, 0, content, indexes, sumxs, sumx2s, weight, weight2, None, length)
+    _fill_dict(h, groups, 0, content, indexes, sumxs, sumx2s, weight, weight2, None, length, absolute)
 
 
-def fill(spec, arrays, contents=None):
+def fill(spec, arrays, contents=None, absolute=False):
     """One ``Book.fill`` (book.py:540-586) / ``Hist.fill`` (hist.py:337-379) over ``arrays``.
 
     ``contents`` is the list of previous per-hist contents (``None`` entries = never
@@ -494,5 +492,5 @@ def fill(spec, arrays, contents=None):
     length = fill_length(spec, arrays)
     interp = _Interp(arrays, length)
     for i, h in enumerate(hists):
-        _postfill(h, interp, contents[i], length)
+        _postfill(h, interp, contents[i], length, absolute)
     return contents

@@ -1,0 +1,164 @@
+"""GPU parity (run on the B200 with -m gpu): the CUDA fill path, called through the C ABI, against
+
+  * the golden outputs of the unmodified reference (tests/golden, every case), and
+  * the CPU oracle on fresh seeded inputs.
+
+Bars (BASELINE.json north_star): bin indices and unweighted counts bit-exact; weighted / profile sums
+within 1e-12 * (per-bin sum of |term|), which the oracle computes with ``absolute=True``.
+"""
+import numpy
+import pytest
+
+import golden_util
+from oracle import fill_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+# functions evaluated by CUDA's libm instead of numpy's: not bit-identical, an event within an ulp of a bin
+# edge may land in the neighbouring bin ("hard parts")
+LIBM_CASES = {"library_transcendental"}
+CASES = golden_util.names()
+
+
+def run_spec(spec, fills, device=False):
+    import torch
+    from histbook_b200 import fillable
+    sf = fillable.SpecFill(spec)
+    for arrays in fills:
+        if device:
+            arrays = dict((k, torch.from_numpy(numpy.ascontiguousarray(v)).cuda() if isinstance(v, numpy.ndarray) and v.dtype != numpy.bool_ and v.ndim == 1 else v)
+                          for k, v in arrays.items())
+        sf.fill(arrays)
+    return sf.contents()
+
+
+def compare(name, spec, got, exp, bound):
+    assert len(got) == len(exp)
+    for hid, (g, e, b) in enumerate(zip(got, exp, bound)):
+        fg, fe, fb = golden_util.flatten(g), e, golden_util.flatten(b)
+        assert [k for k, _ in fg] == [k for k, _ in fe], (name, hid)
+        h = spec["hists"][hid]
+        for (k, ga), (_, ea), (_, ba) in zip(fg, fe, fb):
+            assert ga.shape == ea.shape and ga.dtype == numpy.float64
+            nan_g, nan_e = numpy.isnan(ga), numpy.isnan(ea)
+            assert numpy.array_equal(nan_g, nan_e), (name, hid, k)
+            ok = ~nan_e
+            diff = numpy.abs(ga[ok] - ea[ok])
+            tol = RTOL * numpy.where(numpy.isfinite(ba[ok]), ba[ok], numpy.inf)
+            assert numpy.all(diff <= tol), (name, hid, k, float(diff.max()))
+            if h["weight"] is None:       # unweighted counts: bit-exact
+                assert numpy.array_equal(ga[..., h["sumw"]], ea[..., h["sumw"]]), (name, hid, k)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n not in LIBM_CASES])
+def test_golden_host_columns(name):
+    case = golden_util.load()[name]
+    fills = golden_util.fills(case)
+    got = run_spec(case["spec"], fills)
+    bound = None
+    for arrays in fills:
+        bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
+    compare(name, case["spec"], got, golden_util.outputs(case), bound)
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "c2_nanlaced", "dtype_float32", "dtype_int64", "dtype_int16", "bin_big_1111"])
+def test_golden_device_columns(name):
+    case = golden_util.load()[name]
+    fills = golden_util.fills(case)
+    got = run_spec(case["spec"], fills, device=True)
+    bound = None
+    for arrays in fills:
+        bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
+    compare(name, case["spec"], got, golden_util.outputs(case), bound)
+
+
+def test_libm_class_functions_flip_budget():
+    """sin/exp/log/... come from CUDA's libm: totals must agree exactly, and at most a handful of
+    events may sit in a neighbouring bin."""
+    case = golden_util.load()["library_transcendental"]
+    got = run_spec(case["spec"], golden_util.fills(case))
+    for hid, (g, e) in enumerate(zip(got, golden_util.outputs(case))):
+        ea = e[0][1]
+        assert g.sum() == ea.sum(), hid
+        assert numpy.abs(g - ea).sum() <= 2 * 4, (hid, case["hists"][hid], float(numpy.abs(g - ea).sum()))
+
+
+@pytest.mark.parametrize("name,n", [("c1", 3000017), ("c2", 2000003), ("c3", 2000003), ("c5", 1500001), ("c4", 300007)])
+def test_against_oracle_fresh_inputs(name, n):
+    """Sizes the oracle finishes in seconds; unaligned N exercises the tail path; two fills accumulate."""
+    case = golden_util.load()[name]
+    rs = numpy.random.RandomState(2024)
+    cols = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n), "z": rs.normal(0, 1, n),
+            "w": rs.uniform(0.5, 1.5, n), "n": rs.poisson(3, n).astype(numpy.int64)}
+    cols["x"][::4099] = numpy.nan
+    cols["w"][1::5003] = numpy.nan
+    cols["y"][2::6007] = numpy.inf
+    from histbook_b200 import spec as hbspec
+    fields = hbspec.spec_fields(case["spec"])
+    half = n // 2 + 1
+    fills = [dict((f, cols[f][:half]) for f in fields), dict((f, cols[f][half:]) for f in fields)]
+    got = run_spec(case["spec"], fills, device=(name != "c4"))
+    exp = bound = None
+    for arrays in fills:
+        exp = fill_oracle.fill(case["spec"], arrays, exp)
+        bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
+    compare(name, case["spec"], got, [golden_util.flatten(e) for e in exp], bound)
+
+
+def test_unaligned_device_pointer_takes_scalar_path():
+    import torch
+    case = golden_util.load()["c2"]
+    rs = numpy.random.RandomState(5)
+    n = 100001
+    x, y, w = rs.normal(0, 1, n + 1), rs.normal(0, 1, n + 1), rs.uniform(0.5, 1.5, n + 1)
+    dx, dy, dw = (torch.from_numpy(a).cuda()[1:] for a in (x, y, w))      # 8-byte, not 32-byte aligned
+    from histbook_b200 import fillable
+    sf = fillable.SpecFill(case["spec"])
+    sf.fill(x=dx, y=dy, w=dw)
+    arrays = {"x": x[1:], "y": y[1:], "w": w[1:]}
+    exp = fill_oracle.fill(case["spec"], arrays)
+    bound = fill_oracle.fill(case["spec"], arrays, absolute=True)
+    compare("c2-unaligned", case["spec"], sf.contents(), [golden_util.flatten(e) for e in exp], bound)
+
+
+def test_empty_and_tiny_fills():
+    case = golden_util.load()["c2"]
+    from histbook_b200 import fillable
+    sf = fillable.SpecFill(case["spec"])
+    sf.fill(x=numpy.zeros(0), y=numpy.zeros(0), w=numpy.zeros(0))
+    assert sf.contents()[0].shape == (203, 203, 2) and sf.contents()[0].sum() == 0
+    sf.fill(x=numpy.array([0.25]), y=numpy.array([0.5]), w=numpy.array([2.0]))
+    c = sf.contents()[0]
+    assert c.sum() == 6.0 and numpy.count_nonzero(c) == 2
+
+
+def test_errors_match_reference_messages():
+    case = golden_util.load()["c2"]
+    from histbook_b200 import fillable
+    sf = fillable.SpecFill(case["spec"])
+    with pytest.raises(ValueError, match="required field 'w' not found in fill arguments"):
+        sf.fill(x=numpy.zeros(3), y=numpy.zeros(3))
+    with pytest.raises(ValueError, match="has len 2 but other arrays have len 3"):
+        sf.fill(x=numpy.zeros(3), y=numpy.zeros(3), w=numpy.zeros(2))
+
+
+def test_strategies_agree():
+    """Shared-memory privatised and global-RED accumulation give the same histogram."""
+    from histbook_b200 import fillable
+    case = golden_util.load()["c3"]
+    rs = numpy.random.RandomState(11)
+    n = 400000
+    arrays = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n)}
+    out = {}
+    try:
+        for mode in ("smem", "global"):
+            fillable.set_options(strategy={"*": mode})
+            sf = fillable.SpecFill(case["spec"])
+            sf.fill(arrays)
+            out[mode] = sf.contents()[0]
+    finally:
+        fillable.set_options(strategy=None)
+    bound = fill_oracle.fill(case["spec"], arrays, absolute=True)[0]
+    assert numpy.all(numpy.abs(out["smem"] - out["global"]) <= 2e-12 * bound)
+    assert numpy.array_equal(out["smem"][..., 4], out["global"][..., 4])

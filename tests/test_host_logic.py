@@ -1,0 +1,130 @@
+"""CPU-side checks (no GPU): the C ABI library loads and exports every declared symbol, the code
+generator lowers every golden spec and NVRTC accepts the result for sm_100a, column binding follows
+histbook/fill.py:88-146, and the device path refuses to run without a device."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+import golden_util
+from histbook_b200 import codegen, columns, engine, spec as hbspec
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "hbfill.h")).read()
+    declared = set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = engine.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libhbfill.so does not export " + name
+    assert declared == set(engine.SYMBOLS), (declared ^ set(engine.SYMBOLS))
+    assert lib.hb_version() == 1
+
+
+def test_no_cpu_fallback():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from histbook_b200 import fillable
+    sf = fillable.SpecFill(golden_util.load()["c1"]["spec"])
+    with pytest.raises(engine.EngineError):
+        sf.fill(x=numpy.zeros(10))
+
+
+def _coltypes(case):
+    f = golden_util.fills(case)[0]
+    out = {}
+    for n, v in f.items():
+        a = numpy.asarray(v)
+        out[n] = (a.dtype, a.shape == ())
+    for n in hbspec.spec_fields(case["spec"]):
+        if n not in out and n in codegen.MAYBECONSTANTS:
+            out[n] = (numpy.dtype("float64"), True)
+    return out
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5", "library_exact", "dtype_float32", "dtype_uint8",
+                                  "groupby_groupbin_num", "split3_flags_0110", "scalar_broadcast", "maybeconstants"])
+def test_generated_kernels_compile_for_sm100a(name):
+    case = golden_util.load()[name]
+    kern = codegen.generate(case["spec"], _coltypes(case))
+    cubin = engine.compile_source(kern.source)
+    assert cubin[:4] == b"\x7fELF"
+    assert "--fmad" not in kern.source and "hb_fill_kernel" in kern.source
+    keys = codegen.generate_keys(case["spec"], _coltypes(case))
+    if any(h["group"] for h in case["spec"]["hists"]):
+        assert engine.compile_source(keys.source)[:4] == b"\x7fELF"
+    else:
+        assert keys is None
+
+
+def test_every_golden_spec_lowers():
+    for name in golden_util.names():
+        case = golden_util.load()[name]
+        kern = codegen.generate(case["spec"], _coltypes(case))
+        assert len(kern.plans) == len(case["spec"]["hists"])
+
+
+def test_common_subexpressions_are_shared_across_a_book():
+    case = golden_util.load()["c4"]
+    kern = codegen.generate(case["spec"], _coltypes(case))
+    # x*x appears in sqrt(x**2+y**2) and sqrt(x**2+y**2+z**2), for 8 histograms each: one multiply
+    assert kern.source.count("hb_mul<double>(c3, c3)") + kern.source.count("hb_mul<double>(c2, c2)") <= 2
+    assert len([l for l in kern.source.splitlines() if "sqrt(" in l]) == 2
+
+
+def test_identical_accumulations_are_merged():
+    # c3: profile("y")'s sum-of-squares and profile("y**2")'s sum are the same term (y*y)
+    case = golden_util.load()["c3"]
+    kern = codegen.generate(case["spec"], _coltypes(case))
+    hp = kern.plans[0]
+    assert len(hp.terms) == 4 and sorted(len(d) for d in hp.dest) == [1, 1, 1, 2]
+
+
+def test_dtype_follows_numpy_promotion():
+    spec = golden_util.load()["dtype_float32"]["spec"]
+    k32 = codegen.generate(spec, {"x": (numpy.dtype("float32"), False)})
+    k64 = codegen.generate(spec, {"x": (numpy.dtype("float64"), False)})
+    assert "hb_bin_axis<float," in k32.source and "hb_bin_axis<double," in k64.source
+
+
+def test_unknown_function_is_an_assertion_error_like_the_reference():
+    spec = {"version": 1, "hists": [{"group": [], "fixed": [{"kind": "bin", "totbins": 13, "goal":
+            ["call", "histbook.binUONL", ["call", "round", ["name", "x"]], ["const", 10], ["const", 0.0], ["const", 1.0]]}],
+            "profile": [], "weight": None, "shape": [13, 1], "sumw": 0, "sumw2": None}]}
+    with pytest.raises(AssertionError):
+        codegen.generate(spec, {"x": (numpy.dtype("float64"), False)})
+
+
+def test_bind_columns_errors_and_broadcast():
+    cols, n = columns.bind_all(["pi", "w", "x"], {"x": [1.0, 2.0, 3.0], "w": 2})
+    assert n == 3 and cols["w"].is_scalar and cols["w"].dtype == numpy.int64 and cols["pi"].is_scalar
+    assert cols["x"].dtype == numpy.float64 and cols["x"].location == 0
+    with pytest.raises(ValueError, match="required field 'x' not found in fill arguments"):
+        columns.bind_all(["x"], {})
+    with pytest.raises(ValueError, match="array 'y' has len 2 but other arrays have len 3"):
+        columns.bind_all(["x", "y"], {"x": numpy.zeros(3), "y": numpy.zeros(2)})
+    with pytest.raises(codegen.UnsupportedError):
+        columns.bind_all(["c"], {"c": ["a", "b"]})
+    cols, n = columns.bind_all(["x"], {"x": numpy.arange(10.0)[::2]})      # strided -> contiguous copy
+    assert n == 5 and cols["x"].keepalive.flags.c_contiguous
+
+
+def test_group_table_layout_roundtrip():
+    from histbook_b200.store import GroupInfo, KEY_NAN
+    g = GroupInfo("groupbin", False, True, "float64", True, None)
+    for key in (0.0, -2.5, 10.0, 1e300):
+        assert g.key_object(g.pattern(key)) == key
+    assert g.pattern(-0.0) == g.pattern(0.0)
+    assert g.key_object(KEY_NAN) == "NaN" and g.pattern("NaN") == KEY_NAN
+    order = g.sort_patterns([g.pattern(3.0), KEY_NAN, g.pattern(-1.0), g.pattern(0.5)])
+    assert [g.key_object(p) for p in order] == [-1.0, 0.5, 3.0, "NaN"]
+    gi = GroupInfo("groupby", False, False, "int64", True, None)
+    assert [gi.key_object(p) for p in gi.sort_patterns([gi.pattern(5), gi.pattern(-3), gi.pattern(0)])] == [-3, 0, 5]

@@ -1,0 +1,252 @@
+// atomics_microbench.cu -- measures, on the B200, the accumulation primitives the fill kernels can choose from.
+// Not part of the product path: it exists so that strategy choices in histbook_b200/codegen.py are made from
+// measurements (profiles/atomics_microbench_r01.txt) instead of guesses.
+//
+//   ./atomics_microbench [N events, default 1e8]
+//
+// Columns x,y,z ~ N(0,1), w ~ U(0.5,1.5) are generated on the device; every variant streams them from HBM
+// with the same 4-events-per-thread LDG.256 tile loop as the generated kernels and differs only in how it
+// accumulates.  Times are CUDA-event averages over 5 launches after 2 warm-ups; inputs (>= 800 MB per column
+// at the default N) are larger than L2.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+typedef long long i64;
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+__device__ __forceinline__ u64 mix(u64 x) { x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31; return x; }
+
+__global__ void gen_normal(double* out, i64 n, u64 seed) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        u64 a = mix(seed + 2 * (u64)i), b = mix(seed + 2 * (u64)i + 1);
+        double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0), u2 = (b >> 11) * (1.0 / 9007199254740992.0);
+        out[i] = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+    }
+}
+__global__ void gen_uniform(double* out, i64 n, u64 seed, double lo, double hi) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = lo + (hi - lo) * ((mix(seed + (u64)i) >> 11) * (1.0 / 9007199254740992.0));
+}
+
+__device__ __forceinline__ void load4(const double* p, double (&o)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void red_f64(double* a, double v) { asm volatile("red.global.add.f64 [%0], %1;" :: "l"(a), "d"(v) : "memory"); }
+
+__device__ __forceinline__ int bin1d(double v, double low, double scale, int nb) {     // binUONL
+    double t = floor((v - low) * scale) + 1.0;
+    int i = (t > -2147483649.0 && t < 2147483648.0) ? (int)t : (-2147483647 - 1);
+    i = max(i, 0); i = min(i, nb + 1);
+    if (t != t) i = nb + 2;
+    return i;
+}
+
+enum Mode {
+    READ_ONLY = 0,        // sum of x: the streaming ceiling
+    C1_SMEM_U32,          // 103 bins, shared u32 atomicAdd per event
+    C1_SMEM_U32_MATCH,    // same, warp-aggregated with __match_any_sync
+    C1_TPRIV_U8,          // thread-private packed 8-bit counters in shared memory, no atomics, flushed every 252 events
+    C1_GLOBAL_RED,        // 103 bins, global f64 RED per event (worst case contention)
+    C2_GLOBAL_RED,        // 203x203x2 f64, two REDs per event
+    C2_GLOBAL_RED_PAIR,   // same, lanes paired so one RED instruction carries (w, w2) of 16 events
+    C2_INDEX_ONLY,        // index math only (no accumulate): compute ceiling of c2
+    C3_SMEM_F64,          // 1003x2 bins: 3 shared f64 CAS adds + 1 shared u32 per event
+    C3_GLOBAL_RED,        // same terms as global REDs into an 80 KB L2-resident table
+    C5_GLOBAL_RED,        // 203^3 x 2 f64 (134 MB), two REDs per event
+    C5_INDEX_ONLY,
+    NMODES
+};
+static const char* kNames[NMODES] = {"read_only", "c1_smem_u32", "c1_smem_u32_match", "c1_tpriv_u8", "c1_global_red",
+                                     "c2_global_red", "c2_global_red_pair", "c2_index_only", "c3_smem_f64", "c3_global_red",
+                                     "c5_global_red", "c5_index_only"};
+static const int kBytesPerEvent[NMODES] = {8, 8, 8, 8, 8, 24, 24, 24, 16, 16, 32, 32};
+
+#define THREADS 256
+#define TILE (THREADS * 4)
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 2) k(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                const double* __restrict__ w, i64 n, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    u32* s32 = reinterpret_cast<u32*>(smem);
+    double* s64 = reinterpret_cast<double*>(smem);
+    const int NB1 = 103, NB3 = 1003 * 2;
+    int zero_words = 0;
+    if (MODE == C1_SMEM_U32 || MODE == C1_SMEM_U32_MATCH) zero_words = 104;
+    if (MODE == C1_TPRIV_U8) zero_words = 26 * THREADS;
+    if (MODE == C3_SMEM_F64) zero_words = NB3 * 3 * 2 + NB3;
+    for (int i = threadIdx.x; i < zero_words; i += THREADS) s32[i] = 0u;
+    __syncthreads();
+    double acc = 0.0;
+    int since_flush = 0;
+    const i64 ntiles = n / TILE;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 first = tile * TILE + (i64)threadIdx.x * 4;
+        double vx[4], vy[4], vz[4], vw[4];
+        load4(x + first, vx);
+        if (MODE >= C2_GLOBAL_RED) load4(y + first, vy);
+        if (MODE == C5_GLOBAL_RED || MODE == C5_INDEX_ONLY) load4(z + first, vz);
+        if (MODE == C2_GLOBAL_RED || MODE == C2_GLOBAL_RED_PAIR || MODE == C2_INDEX_ONLY || MODE == C5_GLOBAL_RED || MODE == C5_INDEX_ONLY) load4(w + first, vw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (MODE == READ_ONLY) acc += vx[e];
+            if (MODE == C1_SMEM_U32) atomicAdd(&s32[bin1d(vx[e], -5.0, 10.0, 100)], 1u);
+            if (MODE == C1_SMEM_U32_MATCH) {
+                int b = bin1d(vx[e], -5.0, 10.0, 100);
+                unsigned peers = __match_any_sync(0xffffffffu, b);
+                if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s32[b], (u32)__popc(peers));
+            }
+            if (MODE == C1_TPRIV_U8) {
+                int b = bin1d(vx[e], -5.0, 10.0, 100);
+                u32* word = &s32[(b >> 2) * THREADS + threadIdx.x];      // bank = threadIdx.x % 32: conflict-free
+                *word += 1u << ((b & 3) * 8);
+            }
+            if (MODE == C1_GLOBAL_RED) red_f64(out + bin1d(vx[e], -5.0, 10.0, 100), 1.0);
+            if (MODE == C2_GLOBAL_RED || MODE == C2_GLOBAL_RED_PAIR || MODE == C2_INDEX_ONLY) {
+                int b0 = bin1d(vx[e] + vy[e], -5.0, 20.0, 200);
+                int b1 = bin1d(sqrt(vx[e] * vx[e] + vy[e] * vy[e]), 0.0, 40.0, 200);
+                i64 idx = ((i64)b0 * 203 + b1) * 2;
+                double ww = vw[e], w2 = vw[e] * vw[e];
+                if (MODE == C2_GLOBAL_RED) { red_f64(out + idx, ww); red_f64(out + idx + 1, w2); }
+                if (MODE == C2_INDEX_ONLY) acc += (double)idx + w2;
+                if (MODE == C2_GLOBAL_RED_PAIR) {
+                    // lanes 2k and 2k+1 cooperate: first serve the even lane's event, then the odd lane's
+                    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int src = (lane & ~1u) + r;
+                        i64 sidx = __shfl_sync(0xffffffffu, idx, src);
+                        double sw = __shfl_sync(0xffffffffu, ww, src), sw2 = __shfl_sync(0xffffffffu, w2, src);
+                        red_f64(out + sidx + (lane & 1u), (lane & 1u) ? sw2 : sw);
+                    }
+                }
+            }
+            if (MODE == C3_SMEM_F64 || MODE == C3_GLOBAL_RED) {
+                int b0 = bin1d(vx[e], -5.0, 100.0, 1000);
+                int b = b0 * 2 + (0.0 < vx[e] ? 1 : 0);
+                double y1 = vy[e], y2 = y1 * y1, y4 = y2 * y2;
+                if (MODE == C3_SMEM_F64) {
+                    atomicAdd(&s64[b], y1); atomicAdd(&s64[NB3 + b], y2); atomicAdd(&s64[2 * NB3 + b], y4);
+                    atomicAdd(&s32[NB3 * 6 + b], 1u);
+                } else {
+                    double* row = out + (i64)b * 5;
+                    red_f64(row, y1); red_f64(row + 1, y2); red_f64(row + 2, y2); red_f64(row + 3, y4); red_f64(row + 4, 1.0);
+                }
+            }
+            if (MODE == C5_GLOBAL_RED || MODE == C5_INDEX_ONLY) {
+                int b0 = bin1d(vx[e], -5.0, 20.0, 200), b1 = bin1d(vy[e], -5.0, 20.0, 200), b2 = bin1d(vz[e], -5.0, 20.0, 200);
+                i64 idx = (((i64)b0 * 203 + b1) * 203 + b2) * 2;
+                if (MODE == C5_GLOBAL_RED) { red_f64(out + idx, vw[e]); red_f64(out + idx + 1, vw[e] * vw[e]); }
+                else acc += (double)idx + vw[e];
+            }
+        }
+        if (MODE == C1_TPRIV_U8) {
+            since_flush += 4;
+            if (since_flush >= 252) {                      // a byte counter can hold 255
+                since_flush = 0;
+#pragma unroll 1
+                for (int wd = 0; wd < 26; ++wd) {
+                    u32 v = s32[wd * THREADS + threadIdx.x];
+                    if (v) {
+                        s32[wd * THREADS + threadIdx.x] = 0u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { u32 c = (v >> (8 * q)) & 0xffu; if (c) red_f64(out + wd * 4 + q, (double)c); }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (MODE == READ_ONLY || MODE == C2_INDEX_ONLY || MODE == C5_INDEX_ONLY) { if (acc == 123.456) out[0] = acc; }
+    if (MODE == C1_SMEM_U32 || MODE == C1_SMEM_U32_MATCH)
+        for (int b = threadIdx.x; b < NB1; b += THREADS) if (s32[b]) red_f64(out + b, (double)s32[b]);
+    if (MODE == C1_TPRIV_U8) {
+        for (int wd = 0; wd < 26; ++wd) {
+            u32 v = s32[wd * THREADS + threadIdx.x];
+            for (int q = 0; q < 4; ++q) { u32 c = (v >> (8 * q)) & 0xffu; if (c) red_f64(out + wd * 4 + q, (double)c); }
+        }
+    }
+    if (MODE == C3_SMEM_F64) {
+        for (int b = threadIdx.x; b < NB3; b += THREADS) {
+            double* row = out + (i64)b * 5;
+            double a = s64[b], c = s64[NB3 + b], d = s64[2 * NB3 + b]; u32 cnt = s32[NB3 * 6 + b];
+            if (a != 0.0) red_f64(row, a);
+            if (c != 0.0) { red_f64(row + 1, c); red_f64(row + 2, c); }
+            if (d != 0.0) red_f64(row + 3, d);
+            if (cnt) red_f64(row + 4, (double)cnt);
+        }
+    }
+}
+
+template <int MODE>
+static void run(const double* x, const double* y, const double* z, const double* w, i64 n, double* out, size_t out_bytes, int sms) {
+    size_t smem = 0;
+    if (MODE == C1_SMEM_U32 || MODE == C1_SMEM_U32_MATCH) smem = 104 * 4;
+    if (MODE == C1_TPRIV_U8) smem = 26 * THREADS * 4;
+    if (MODE == C3_SMEM_F64) smem = (size_t)(1003 * 2) * (3 * 8 + 4);
+    CK(cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<MODE>, THREADS, smem));
+    int grid = sms * occ;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f, total = 0.f;
+    const int reps = 5;
+    for (int it = 0; it < 2 + reps; ++it) {
+        CK(cudaMemsetAsync(out, 0, out_bytes));
+        CK(cudaEventRecord(e0));
+        k<MODE><<<grid, THREADS, smem>>>(x, y, z, w, n, out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 2) { total += ms; if (ms < best) best = ms; }
+    }
+    CK(cudaGetLastError());
+    // checksum: total of all counts / weights, to prove the variants did the same work
+    std::vector<double> host(out_bytes / 8 > (1 << 22) ? (1 << 22) : out_bytes / 8);
+    CK(cudaMemcpy(host.data(), out, host.size() * 8, cudaMemcpyDeviceToHost));
+    double sum = 0; for (double v : host) sum += v;
+    double ms = total / reps;
+    double gev = n / ms * 1e-6, gbs = gev * kBytesPerEvent[MODE];
+    printf("%-22s occ=%d grid=%4d smem=%6zu  avg %8.3f ms  best %8.3f ms  %8.2f Gev/s  %8.1f GB/s (%5.1f%% of 6551)  checksum(first 4M) %.6g\n",
+           kNames[MODE], occ, grid, smem, ms, best, gev, gbs, 100.0 * gbs / 6551.0, sum);
+    fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+    i64 n = argc > 1 ? (i64)atof(argv[1]) : 100000000;
+    n = n / TILE * TILE;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    printf("device %s, %d SMs, N = %lld events\n", prop.name, prop.multiProcessorCount, n);
+    double *x, *y, *z, *w, *out;
+    CK(cudaMalloc(&x, n * 8)); CK(cudaMalloc(&y, n * 8)); CK(cudaMalloc(&z, n * 8)); CK(cudaMalloc(&w, n * 8));
+    size_t out_bytes = (size_t)203 * 203 * 203 * 2 * 8;
+    CK(cudaMalloc(&out, out_bytes));
+    gen_normal<<<prop.multiProcessorCount * 8, 256>>>(x, n, 1);
+    gen_normal<<<prop.multiProcessorCount * 8, 256>>>(y, n, 1ull << 40);
+    gen_normal<<<prop.multiProcessorCount * 8, 256>>>(z, n, 2ull << 40);
+    gen_uniform<<<prop.multiProcessorCount * 8, 256>>>(w, n, 3ull << 40, 0.5, 1.5);
+    CK(cudaDeviceSynchronize());
+    int sms = prop.multiProcessorCount;
+    run<READ_ONLY>(x, y, z, w, n, out, out_bytes, sms);
+    run<C1_SMEM_U32>(x, y, z, w, n, out, out_bytes, sms);
+    run<C1_SMEM_U32_MATCH>(x, y, z, w, n, out, out_bytes, sms);
+    run<C1_TPRIV_U8>(x, y, z, w, n, out, out_bytes, sms);
+    run<C1_GLOBAL_RED>(x, y, z, w, n, out, out_bytes, sms);
+    run<C2_INDEX_ONLY>(x, y, z, w, n, out, out_bytes, sms);
+    run<C2_GLOBAL_RED>(x, y, z, w, n, out, out_bytes, sms);
+    run<C2_GLOBAL_RED_PAIR>(x, y, z, w, n, out, out_bytes, sms);
+    run<C3_SMEM_F64>(x, y, z, w, n, out, out_bytes, sms);
+    run<C3_GLOBAL_RED>(x, y, z, w, n, out, out_bytes, sms);
+    run<C5_INDEX_ONLY>(x, y, z, w, n, out, out_bytes, sms);
+    run<C5_GLOBAL_RED>(x, y, z, w, n, out, out_bytes, sms);
+    return 0;
+}
