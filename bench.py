@@ -208,6 +208,7 @@ def run_gpu(args):
         sampler.start()
     ms, launches = measure(torch, dist, filler, cols, args.steps, args.warmup, world, merge)
     clocks = sampler.stop() if rank == 0 else None
+    main_stats = dict(fillable.last_stats)
     ms_step = ms / args.steps
     value = world * n / (ms_step * 1e-3)
 
@@ -245,7 +246,7 @@ def run_gpu(args):
                "sample": "%d processes x %d events (fill-in-parallel-then-add), best of 2 after 1 warm-up, fill time only" % (procs, per_proc)}
 
     if rank == 0:
-        stats = dict(fillable.last_stats)
+        stats = main_stats
         line = {
             "metric": "fill events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -255,7 +256,8 @@ def run_gpu(args):
                        if n * bytes_per_event > 256e6 else "L2 flushed between steps is NOT done; inputs fit L2",
                        "rank_merge": "none (1 GPU)" if world == 1 else "NCCL all-reduce / reduce-scatter of the bin contents every step",
                        "kernel": {"regs": stats.get("regs"), "smem_bytes": stats.get("smem_bytes"), "grid": stats.get("grid"),
-                                  "blocks_per_sm": stats.get("blocks_per_sm")}},
+                                  "blocks_per_sm": stats.get("blocks_per_sm"), "hot_window": stats.get("window"),
+                                  "hot_window_coverage_est": stats.get("window_coverage")}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": None, "peak_source": hbm_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -320,15 +322,11 @@ def run_extra(torch, dist, workload, device, hbm):
         times = []
         for it in range(3 + steps):
             engine.flush_l2()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            filler.fill(cols)
-            e1.record()
-            torch.cuda.synchronize()
+            filler.fill(cols, timed=True)          # CUDA events recorded around the launch inside hb_fill (stream 0)
             if it >= 3:
-                times.append(e0.elapsed_time(e1))
+                times.append(fillable.last_stats["ms_kernel"])
         ms_step = sum(times) / len(times)
-        l2 = "L2 flushed between steps"
+        l2 = "L2 flushed between steps; kernel time from CUDA events around the launch (host launch overhead excluded)"
     else:
         ms, _ = measure(torch, dist, filler, cols, steps, 3, 1, lambda: None)
         ms_step = ms / steps

@@ -491,6 +491,7 @@ class HistPlan(object):
         self.strategy = "global"
         self.smem_f64_off = None   # byte offset of the [nterms_f64][nbins] double block
         self.smem_u32_off = None   # byte offset of the [nbins] u32 count block
+        self.win_off = None        # "window" strategy: byte offset of the runtime-sized hot window region
 
     def add_term(self, expr, col):
         for t, e in enumerate(self.terms):
@@ -592,7 +593,17 @@ def choose_strategies(plans, options):
             hp.smem_f64_off = used
             hp.smem_u32_off = used + hp.nbins * 8 * len(hp.f64_terms)
             used += (need + 7) // 8 * 8
-    return used
+    # Hot-window privatisation: ONE histogram that is too large for shared memory keeps a runtime-placed
+    # hyper-rectangle of its bins (where most events land) in shared memory; the rest goes to global REDs.
+    window = None
+    if options.get("window", True):
+        cands = [hp for hp in plans if hp.strategy == "global" and not hp.groups and hp.index
+                 and forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) in (None, "window")]
+        if cands:
+            window = min(cands, key=lambda hp: hp.nbins)
+            window.strategy = "window"
+            window.win_off = used
+    return used, window
 
 
 # ================================================================================================
@@ -613,6 +624,7 @@ class Kernel(object):
         self.inexact = set()
         self.key = None
         self.group_aux = {}         # fill kernel: hist id -> aux slot of its group table
+        self.window = None          # hot-window histogram: dict(hid, bpb, wmax, totbins, ncol, col, nf)
         self.group_goals = []       # keys kernel: [(tree key, info dict)] in aux order
 
 
@@ -627,7 +639,7 @@ def _loadtype(dtype):
     return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
 
 
-def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks):
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, has_window=False):
     """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
     over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
     takes the scalar path), shared-memory zeroing before and block merge after."""
@@ -637,7 +649,7 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks):
     src.append("#define HB_TILE (HB_THREADS * 4)")
     src.extend(prog.consts)
     src.append("")
-    sig = ["const HbParams& p", "unsigned char* hb_smem"]
+    sig = ["const HbParams& p", "unsigned char* hb_smem", "const bool live"]
     for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
         sig.append("const %s c%d /* %s */" % (ctype(dtype), slot, name))
     src.append("__device__ __forceinline__ void hb_event(%s)\n{" % ", ".join(sig))
@@ -646,8 +658,9 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks):
 
     src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % minblocks)
     src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
-    if smem:
-        src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (smem // 4))
+    if smem or has_window:
+        bound = "%d + p.win[0]" % (smem // 4) if has_window else "%d" % (smem // 4)
+        src.append("    for (int i = threadIdx.x; i < %s; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % bound)
         src.append("    __syncthreads();")
     for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
         if is_scalar:
@@ -661,17 +674,18 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks):
             src.append("            %s v%d[4]; hb_load4<%s>(p.cols[%d], first, threadIdx.x, HB_THREADS, v%d);" % (_loadtype(dtype), slot, _loadtype(dtype), slot, slot))
     src.append("#pragma unroll")
     src.append("            for (int k = 0; k < 4; ++k) {")
-    src.append("                hb_event(p, hb_smem%s);" % "".join(
+    src.append("                hb_event(p, hb_smem, true%s);" % "".join(
         ", " + _colarg(slot, dtype, is_scalar, "v%d[k]" % slot) for slot, (name, dtype, is_scalar) in enumerate(prog.cols)))
     src.append("            }")
     src.append("        } else {")
+    src.append("            // tail / unaligned input: scalar loads; every lane still calls hb_event (warp-cooperative accumulates)")
     src.append("            for (int k = 0; k < 4; ++k) {")
-    src.append("                const hb_i64 i = first + (hb_i64)threadIdx.x * 4 + k;")
-    src.append("                if (i < p.n) {")
-    src.append("                    hb_event(p, hb_smem%s);" % "".join(
-        ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], i)" % (_loadtype(dtype), slot))
+    src.append("                const hb_i64 i = first + (hb_i64)k * HB_THREADS + threadIdx.x;")
+    src.append("                const bool live = i < p.n;")
+    src.append("                const hb_i64 j = live ? i : 0;")
+    src.append("                hb_event(p, hb_smem, live%s);" % "".join(
+        ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], j)" % (_loadtype(dtype), slot))
         for slot, (name, dtype, is_scalar) in enumerate(prog.cols)))
-    src.append("                }")
     src.append("            }")
     src.append("        }")
     src.append("    }")
@@ -707,11 +721,20 @@ def generate(spec, coltypes, options=None):
     plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
     if len(plans) > 256:
         raise UnsupportedError("more than 256 histograms in one fill")
-    smem = choose_strategies(plans, options)
+    smem, window = choose_strategies(plans, options)
     if len(prog.cols) > 32:
         raise UnsupportedError("more than 32 input fields in one fill")
     threads = int(options.get("threads", THREADS))
     minblocks = int(options.get("min_blocks", 2))
+    smem_cap = smem
+    if window is not None:
+        # one resident block per SM that owns (almost) all of the SM's shared memory
+        threads = int(options.get("win_threads", 1024))
+        minblocks = 1
+        smem_cap = int(options.get("win_smem", 200 * 1024))
+        if len(window.index) * 2 + 2 > 32 or smem_cap - smem < 4096:
+            window.strategy, window = "global", None
+            smem_cap = smem
 
     group_aux = {}
     ev = list(prog.body)
@@ -733,6 +756,45 @@ def generate(spec, coltypes, options=None):
             group_aux[hp.hid] = len(group_aux)
             ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
             conds = ["okg", "slot >= 0"] + conds
+        conds = ["live"] + conds
+        pair = (hp.strategy in ("global", "window") and options.get("pair_red", True) and hp.ncol == 2 and len(hp.terms) == 2
+                and sorted(hp.dest[0] + hp.dest[1]) == [0, 1])
+        outside = ""
+        if hp.strategy == "window":
+            # inside the hot window -> shared memory; p.win = [words, W, lo_0, n_0, lo_1, n_1, ...]
+            nf = len(hp.f64_terms)
+            ev.append("    const bool okw = %s;" % " && ".join(conds))
+            ev.append("    bool inside = okw; int wb = 0;")
+            for a, (v, totbins) in enumerate(hp.index):
+                ev.append("    { const unsigned a = (unsigned)(%s - p.win[%d]); inside = inside && (a < (unsigned)p.win[%d]); wb = wb * p.win[%d] + (int)a; }"
+                          % (v.c, 2 + 2 * a, 3 + 2 * a, 3 + 2 * a))
+            ev.append("    if (inside) {")
+            if nf:
+                ev.append("        double* const wrow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)wb * %d;" % (hp.win_off, nf))
+            k = 0
+            for t, e in enumerate(hp.terms):
+                if e is None:
+                    ev.append("        hb_sadd_u32(reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb, 1u);" % (hp.win_off, nf * 8))
+                else:
+                    ev.append("        hb_sadd_f64(wrow + %d, %s);" % (k, e))
+                    k += 1
+            ev.append("    }")
+            conds = ["okw", "!inside"]
+        if pair:
+            # Two adjacent float64 columns (sumw, sumw2): lanes 2k / 2k+1 serve each other's event so that one RED
+            # instruction carries both columns of 16 events -- L2 handles the pair as one 16-byte sector update
+            # (measured 1.9x over two separate REDs, profiles/atomics_microbench_r01.txt).
+            t0 = 0 if hp.dest[0] == [0] else 1
+            v0 = "1.0" if hp.terms[t0] is None else hp.terms[t0]
+            v1 = "1.0" if hp.terms[1 - t0] is None else hp.terms[1 - t0]
+            rowexpr = ("((hb_i64)slot * %d + bin)" % hp.nbins) if hp.groups else "(hb_i64)bin"
+            ev.append("    {")
+            ev.append("        const bool okrow = %s;" % " && ".join(conds))
+            ev.append("        const int bin = okrow ? (%s) : 0;" % idx)
+            ev.append("        hb_red_pair(p.hist[%d], okrow ? %s : (hb_i64)-1, %s, %s);" % (hp.hid, rowexpr, v0, v1))
+            ev.append("    }")
+            ev.append("}")
+            continue
         ev.append("    if (%s) {" % (" && ".join(conds) if conds else "true"))
         ev.append("        const int bin = %s;" % idx)
         if hp.strategy == "smem":
@@ -781,11 +843,40 @@ def generate(spec, coltypes, options=None):
             merge.append("      } }")
         merge.append("}")
 
+    if window is not None:
+        hp = window
+        nf = len(hp.f64_terms)
+        merge.append("// merge the hot window of hist %d" % hp.hid)
+        merge.append("for (int wb = threadIdx.x; wb < p.win[1]; wb += HB_THREADS) {")
+        merge.append("    int rest = wb; hb_i64 bin = 0;")
+        stride = 1
+        for a in range(len(hp.index) - 1, -1, -1):
+            merge.append("    bin += (hb_i64)(p.win[%d] + rest %% p.win[%d]) * %d; rest /= p.win[%d];" % (2 + 2 * a, 3 + 2 * a, stride, 3 + 2 * a))
+            stride *= hp.index[a][1]
+        merge.append("    double* const row = p.hist[%d] + bin * %d;" % (hp.hid, hp.ncol))
+        k_ = 0
+        for t, e in enumerate(hp.terms):
+            if e is None:
+                merge.append("    { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb];" % (hp.win_off, nf * 8))
+                merge.append("      if (c != 0u) { const double v = (double)c;")
+            else:
+                merge.append("    { const double v = reinterpret_cast<const double*>(hb_smem + %d)[(hb_i64)wb * %d + %d];" % (hp.win_off, nf, k_))
+                merge.append("      if (v != 0.0) {")
+                k_ += 1
+            for col in hp.dest[t]:
+                merge.append("        hb_red_f64(row + %d, v);" % col)
+            merge.append("      } }")
+        merge.append("}")
+
     k = Kernel()
-    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks)
+    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, has_window=window is not None)
     k.cols = list(prog.cols)
     k.plans = plans
-    k.smem_bytes = smem
+    k.smem_bytes = smem_cap
+    if window is not None:
+        bpb = 8 * len(window.f64_terms) + (4 if window.count_term is not None else 0)
+        k.window = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "totbins": [t for v, t in window.index],
+                    "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"]}
     k.threads = threads
     k.tile = threads * VEC
     k.inexact = set(prog.inexact)
@@ -820,9 +911,9 @@ def generate_keys(spec, coltypes, options=None):
     ev = list(prog.body)
     infos = []
     for j, g in enumerate(values):
-        cond = ""
+        cond = "if (live) "
         if g.dtype.kind == "f" and not g.extra["nanflow"]:
-            cond = "if (!(%s != %s)) " % (g.c, g.c)
+            cond = "if (live && !(%s != %s)) " % (g.c, g.c)
         ev.append("%shb_keyset_insert(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), hb_keybits(%s));" % (cond, j, g.c))
         infos.append(dict(g.extra, kind="f" if g.dtype.kind == "f" else "i"))
     threads = int(options.get("threads", THREADS))

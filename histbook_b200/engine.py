@@ -64,7 +64,8 @@ SYMBOLS = {
     "hb_arena_scale": (_I, [_P, ctypes.c_double]),
     "hb_arena_ptr": (_P, [_P]),
     "hb_arena_size": (_I64, [_P]),
-    "hb_fill": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _I, _PP, _I, ctypes.POINTER(hb_stats)]),
+    "hb_fill": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
+    "hb_arena_marginals": (_I, [_P, _I, ctypes.POINTER(_I64), _I, _I, _P]),
     "hb_keyset_create": (_I, [_I, _PP]),
     "hb_keyset_destroy": (_I, [_P]),
     "hb_keyset_clear": (_I, [_P]),
@@ -264,6 +265,18 @@ class Arena(object):
     def scale(self, alpha):
         check(lib().hb_arena_scale(self._h, float(alpha)))
 
+    def marginals(self, shape, ncol, col):
+        """Per-axis marginals of |content[..., col]| (list of arrays), computed on the device."""
+        shape = [int(x) for x in shape]
+        out = numpy.zeros(sum(shape), dtype=numpy.float64)
+        arr = (ctypes.c_int64 * len(shape))(*shape)
+        check(lib().hb_arena_marginals(self._h, len(shape), arr, int(ncol), int(col), out.ctypes.data_as(ctypes.c_void_p)))
+        res, off = [], 0
+        for t in shape:
+            res.append(out[off:off + t])
+            off += t
+        return res
+
     @property
     def __cuda_array_interface__(self):
         return {"shape": (int(self.size),), "typestr": "<f8", "data": (int(self.ptr or 0), False), "version": 3, "strides": None}
@@ -324,8 +337,12 @@ class DeviceBuffer(object):
 
 # ----------------------------------------------------------------------------- fill
 
-def fill(program, columns, n, arenas, aux=(), timed=False):
-    """columns: list of (ptr:int, dtype_code, location 0 host / 1 device) or ("scalar", dtype_code, bits)."""
+_ITEMSIZE = [8, 4, 8, 4, 2, 1, 8, 4, 2, 1, 1]
+
+
+def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0):
+    """columns: list of (ptr:int, dtype_code, location 0 host / 1 device) or ("scalar", dtype_code, bits).
+    ``offset``/``n`` select the event range [offset, offset + n) of every column."""
     init()
     ncols = len(columns)
     cols = (hb_column * max(ncols, 1))()
@@ -333,11 +350,13 @@ def fill(program, columns, n, arenas, aux=(), timed=False):
         if c[0] == "scalar":
             cols[i].ptr, cols[i].dtype, cols[i].location, cols[i].is_scalar, cols[i].scalar_bits = None, c[1], 0, 1, c[2]
         else:
-            cols[i].ptr, cols[i].dtype, cols[i].location, cols[i].is_scalar, cols[i].scalar_bits = c[0], c[1], c[2], 0, 0
+            cols[i].ptr, cols[i].dtype, cols[i].location, cols[i].is_scalar, cols[i].scalar_bits = (
+                (c[0] + offset * _ITEMSIZE[c[1]]) if c[0] else c[0], c[1], c[2], 0, 0)
     hist = (ctypes.c_void_p * max(len(arenas), 1))(*[a._h for a in arenas])
     auxp = (ctypes.c_void_p * max(len(aux), 1))(*[ctypes.c_void_p(int(x)) for x in aux])
+    winp = (ctypes.c_int32 * max(len(win), 1))(*[int(x) for x in win])
     stats = hb_stats()
-    check(lib().hb_fill(program._h, ncols, cols, int(n), len(arenas), hist, len(aux), auxp,
+    check(lib().hb_fill(program._h, ncols, cols, int(n), len(arenas), hist, len(aux), auxp, len(win), winp,
                         HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
     return {"events": stats.events, "h2d_bytes": stats.h2d_bytes, "launches": stats.launches, "grid": stats.grid,
             "blocks_per_sm": stats.blocks_per_sm, "ms_kernel": stats.ms_kernel}

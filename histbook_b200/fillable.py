@@ -54,6 +54,70 @@ class Plan(object):
         return self.kernels[sig]
 
 
+PILOT_EVENTS = 1 << 20          # events filled through the global path before the hot window is placed
+WINDOW_MIN_COVERAGE = 0.25      # below this (estimated) fraction of events a window is not worth its merge
+
+
+def choose_window(marginals, wmax):
+    """Place the hot window: per axis a contiguous bin range [lo, lo+n) such that prod(n) <= wmax and the
+    (independence-estimated) fraction of events inside is as large as a greedy trim can make it.
+
+    marginals: per-axis arrays of |sum of weights| per bin (from the histogram filled so far).
+    Returns ([(lo, n), ...], estimated coverage)."""
+    los, his = [], []
+    for m in marginals:
+        nz = numpy.flatnonzero(m)
+        if len(nz) == 0:
+            return [(0, 0)] * len(marginals), 0.0
+        los.append(int(nz[0]))
+        his.append(int(nz[-1]) + 1)
+    totals = [float(m.sum()) for m in marginals]
+
+    def volume():
+        v = 1
+        for lo, hi in zip(los, his):
+            v *= hi - lo
+        return v
+    vol = volume()
+    while vol > wmax:
+        best = None
+        for k, m in enumerate(marginals):
+            nk = his[k] - los[k]
+            if nk <= 1:
+                continue
+            gain = vol // nk                       # bins saved by dropping one slice of axis k
+            for end, idx in (("lo", los[k]), ("hi", his[k] - 1)):
+                score = (m[idx] / totals[k]) / gain
+                if best is None or score < best[0]:
+                    best = (score, k, end)
+        if best is None:
+            return [(0, 0)] * len(marginals), 0.0
+        _, k, end = best
+        if end == "lo":
+            los[k] += 1
+        else:
+            his[k] -= 1
+        vol = volume()
+    coverage = 1.0
+    for k, m in enumerate(marginals):
+        coverage *= float(m[los[k]:his[k]].sum()) / totals[k]
+    return [(lo, hi - lo) for lo, hi in zip(los, his)], coverage
+
+
+def window_params(kern, window):
+    """p.win of hb_template.cuh: [u32 words to zero, bins in the window, lo_0, n_0, lo_1, n_1, ...]."""
+    info = kern.window
+    if window is None:
+        return [0, 0] + [0, 0] * len(info["totbins"])
+    w = 1
+    for lo, n in window:
+        w *= n
+    out = [(w * info["bpb"] + 3) // 4, w]
+    for lo, n in window:
+        out += [lo, n]
+    return out
+
+
 def _abi_columns(kern, cols):
     return [cols[name].abi() for name, dtype, is_scalar in kern.cols]
 
@@ -111,7 +175,34 @@ def fill_hists(plan, hists, arrays, timed=False):
 
         stats = {"events": length, "launches": 0}
         if length > 0:
-            stats = engine.fill(prog, _abi_columns(kern, cols), length, [st.arena for st in stores], aux=aux, timed=timed)
+            abi = _abi_columns(kern, cols)
+            arenas = [st.arena for st in stores]
+            if kern.window is None:
+                stats = engine.fill(prog, abi, length, arenas, aux=aux, timed=timed)
+            else:
+                # hot-window privatisation: place the window from what the histogram already holds; a histogram
+                # that is still empty first gets a pilot slice of this fill through the global path.
+                wst = stores[kern.window["hid"]]
+                done = 0
+                extra = 0.0
+                if wst.window is None:
+                    if not wst.nonempty:
+                        done = min(length, max(kern.tile, PILOT_EVENTS // kern.tile * kern.tile))
+                        pilot = engine.fill(prog, abi, done, arenas, aux=aux, win=window_params(kern, None), timed=timed)
+                        extra = pilot["ms_kernel"]
+                    marg = wst.arena.marginals(kern.window["totbins"], kern.window["ncol"], kern.window["col"])
+                    window, coverage = choose_window(marg, kern.window["wmax"])
+                    wst.window = window if coverage >= WINDOW_MIN_COVERAGE else False
+                    wst.window_coverage = coverage
+                win = window_params(kern, wst.window or None)
+                stats = {"events": length, "launches": 1 if done else 0, "ms_kernel": extra}
+                if length > done:
+                    main = engine.fill(prog, abi, length - done, arenas, aux=aux, win=win, timed=timed, offset=done)
+                    main["launches"] += stats["launches"]
+                    main["ms_kernel"] += extra
+                    stats = main
+                stats["window"] = list(wst.window) if wst.window else None
+                stats["window_coverage"] = wst.window_coverage
         for st in stores:
             st.mark_filled()
         stats["regs"] = prog.regs

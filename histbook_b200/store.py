@@ -86,6 +86,10 @@ class Store(object):
         self.skeleton = None                          # nested OrderedDict pattern -> ... -> slot, reference insertion order
         self.table = None                             # engine.DeviceBuffer with the lookup table of the last fill
         self.table_version = None
+        # hot-window privatisation (fillable.choose_window): None = not placed yet, False = not worth it
+        self.window = None
+        self.window_coverage = None
+        self.nonempty = False                         # the device copy holds at least one fill / uploaded content
 
     # ------------------------------------------------------------------ host view
     def get(self):
@@ -115,6 +119,8 @@ class Store(object):
                 self.arena.clear()
             else:
                 self.arena.write(self._check(self.host))
+            self.nonempty = self.host is not None
+            self.window = None
         else:
             self._upload_groups()
         self.dev_valid = True
@@ -123,6 +129,7 @@ class Store(object):
         self.host = None
         self.host_valid = False
         self.dev_valid = True
+        self.nonempty = True
 
     def _check(self, array):
         array = numpy.asarray(array, dtype=numpy.float64)

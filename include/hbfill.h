@@ -42,6 +42,7 @@ extern "C" {
 #define HB_MAX_COLS 32
 #define HB_MAX_HISTS 256
 #define HB_MAX_AUX 64
+#define HB_MAX_WIN 32
 
 /* column dtypes (numpy names) */
 enum hb_dtype {
@@ -114,7 +115,12 @@ int64_t hb_arena_size(const hb_arena* a);
  * enqueued (device columns) or after the last host chunk has been copied (host columns). */
 int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
             int nhists, hb_arena* const* hists, int naux, const void* const* aux,
-            int flags, hb_stats* stats);
+            int nwin, const int32_t* win, int flags, hb_stats* stats);
+
+/* Per-axis marginals of |content[..., col]| of an N-d histogram (shape = fixed-axis bins..., ncol), computed on
+ * the device; host_out receives shape[0] + ... + shape[ndim-1] doubles.  Used to place the hot window that the
+ * fill kernel privatises in shared memory. */
+int hb_arena_marginals(const hb_arena* a, int ndim, const int64_t* shape, int ncol, int col, double* host_out);
 
 /* key sets (group axes) --------------------------------------------------------------------------------- */
 /* A device-side set of 64-bit keys (raw bits of float64 / int64 group keys), capacity a power of two. */

@@ -128,3 +128,27 @@ def test_group_table_layout_roundtrip():
     assert [g.key_object(p) for p in order] == [-1.0, 0.5, 3.0, "NaN"]
     gi = GroupInfo("groupby", False, False, "int64", True, None)
     assert [gi.key_object(p) for p in gi.sort_patterns([gi.pattern(5), gi.pattern(-3), gi.pattern(0)])] == [-3, 0, 5]
+
+
+def test_hot_window_placement():
+    from histbook_b200.fillable import choose_window, window_params
+    rs = numpy.random.RandomState(3)
+    x, y = rs.normal(0, 1, 200000), rs.normal(0, 1, 200000)
+    i0 = numpy.clip(numpy.floor((x + y + 5) * 20).astype(int) + 1, 0, 201)
+    i1 = numpy.clip(numpy.floor(numpy.sqrt(x * x + y * y) * 40).astype(int) + 1, 0, 201)
+    h = numpy.zeros((203, 203))
+    numpy.add.at(h, (i0, i1), 1)
+    win, cov = choose_window([h.sum(1), h.sum(0)], 12800)
+    (l0, n0), (l1, n1) = win
+    assert n0 * n1 <= 12800 and cov > 0.9
+    assert h[l0:l0 + n0, l1:l1 + n1].sum() / h.sum() > 0.9
+    # nothing filled yet -> no window
+    assert choose_window([numpy.zeros(5), numpy.zeros(7)], 100) == ([(0, 0), (0, 0)], 0.0)
+    # everything fits -> whole populated range
+    win, cov = choose_window([numpy.array([0, 1.0, 2, 0]), numpy.array([3.0, 0, 1])], 100)
+    assert win == [(1, 2), (0, 3)] and cov == 1.0
+
+    class K(object):
+        window = {"bpb": 16, "totbins": [203, 203]}
+    assert window_params(K, [(41, 120), (4, 106)]) == [120 * 106 * 4, 120 * 106, 41, 120, 4, 106]
+    assert window_params(K, None) == [0, 0, 0, 0, 0, 0]

@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Time kernel-generation options against each other on the GPU (tuning aid, not a benchmark of record).
+
+    python tools/sweep.py c2 '{"window": false}' '{"window": true, "win_threads": 512}' ...
+"""
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import torch                                          # noqa: E402
+
+import bench                                          # noqa: E402
+import bench_cpu                                      # noqa: E402
+from histbook_b200 import engine, fillable            # noqa: E402
+
+
+def main():
+    workload = sys.argv[1]
+    n = None
+    variants = []
+    for a in sys.argv[2:]:
+        if a.startswith("n="):
+            n = int(float(a[2:]))
+        else:
+            variants.append(json.loads(a))
+    if not variants:
+        variants = [{}]
+    engine.init(0)
+    case, default_n, bpe, _ = bench_cpu.WORKLOADS[workload]
+    n = n or default_n
+    spec = bench_cpu.load_case(case)["spec"]
+    cols = bench.device_columns(torch, workload, n, 12345, torch.device("cuda", 0))
+    for opts in variants:
+        fillable._options.clear()
+        fillable.set_options(**opts)
+        f = fillable.SpecFill(spec)
+        f.fill(dict((k, v[:4096]) for k, v in cols.items()))
+        f.clear()
+        for _ in range(3):
+            f.fill(cols)
+        torch.cuda.synchronize()
+        steps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            f.fill(cols)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        st = fillable.last_stats
+        print("%s %-60s %9.3f ms  %8.2f Gev/s  %7.1f GB/s (%.1f%%)  regs=%s smem=%s grid=%s occ=%s win=%s cov=%s" % (
+            workload, json.dumps(opts), ms, n / ms * 1e-6, n * bpe / ms * 1e-6, 100 * n * bpe / ms * 1e-6 / 6551,
+            st.get("regs"), st.get("smem_bytes"), st.get("grid"), st.get("blocks_per_sm"), st.get("window"), st.get("window_coverage")), flush=True)
+
+
+if __name__ == "__main__":
+    main()
