@@ -489,7 +489,7 @@ class HistPlan(object):
         self.terms = []          # unique accumulated terms: C expression (double) or None (= count of 1)
         self.dest = []           # per term: list of destination columns
         self.strategy = "global"
-        self.smem_f64_off = None   # byte offset of the [nterms_f64][nbins] double block
+        self.smem_f64_off = None   # byte offset of the [nbins][slots] float64 rows
         self.smem_u32_off = None   # byte offset of the [nbins] u32 count block
         self.win_off = None        # "window" strategy: byte offset of the runtime-sized hot window region
 
@@ -512,8 +512,28 @@ class HistPlan(object):
                 return t
         return None
 
-    def smem_bytes(self):
-        return self.nbins * (8 * len(self.f64_terms) + (4 if self.count_term is not None else 0))
+    def row_layout(self, options=None):
+        """Shared-memory row of one bin: float64 slots (bin-major, so that two neighbouring slots can be
+        updated by ONE 128-bit CAS) and, separately, a native u32 counter.
+
+        Returns (slots, count_u32): ``slots`` = term index per float64 slot (-1 = padding); an unweighted
+        count joins the float64 slots when that makes their number even (it is exact in float64 below 2^53)."""
+        cas128 = True if options is None else options.get("cas128", True)
+        slots = list(self.f64_terms)
+        count_u32 = self.count_term is not None
+        if cas128 and count_u32 and len(slots) % 2 == 1:
+            slots.append(self.count_term)
+            count_u32 = False
+        if cas128 and len(slots) >= 2 and len(slots) % 2 == 1:
+            slots.append(-1)
+        return slots, count_u32
+
+    def row_bytes(self, options=None):
+        slots, count_u32 = self.row_layout(options)
+        return 8 * len(slots) + (4 if count_u32 else 0)
+
+    def smem_bytes(self, options=None):
+        return self.nbins * self.row_bytes(options)
 
 
 def _mulexpr(prog, a, b):
@@ -574,14 +594,14 @@ def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
     budget = int(options.get("smem_budget", 96 * 1024))
     forced = options.get("strategy", {})
-    order = sorted(plans, key=lambda hp: hp.smem_bytes())
+    order = sorted(plans, key=lambda hp: hp.smem_bytes(options))
     used = 0
     for hp in order:
         want = forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*")))
         if hp.groups:
             hp.strategy = "global"
             continue
-        need = hp.smem_bytes()
+        need = hp.smem_bytes(options)
         if want == "global":
             hp.strategy = "global"
         elif (want == "smem" or want is None) and used + need <= budget:
@@ -590,9 +610,10 @@ def choose_strategies(plans, options):
             hp.strategy = "global"
         if hp.strategy == "smem":
             # f64 block first (8-byte aligned), u32 block after
+            slots, count_u32 = hp.row_layout(options)
             hp.smem_f64_off = used
-            hp.smem_u32_off = used + hp.nbins * 8 * len(hp.f64_terms)
-            used += (need + 7) // 8 * 8
+            hp.smem_u32_off = used + hp.nbins * 8 * len(slots)
+            used += (need + 15) // 16 * 16
     # Hot-window privatisation: ONE histogram that is too large for shared memory keeps a runtime-placed
     # hyper-rectangle of its bins (where most events land) in shared memory; the rest goes to global REDs.
     window = None
@@ -602,6 +623,7 @@ def choose_strategies(plans, options):
         if cands:
             window = min(cands, key=lambda hp: hp.nbins)
             window.strategy = "window"
+            used = (used + 15) // 16 * 16
             window.win_off = used
     return used, window
 
@@ -714,6 +736,51 @@ def _group_lookup(hp, aux_slot):
     return out
 
 
+def _emit_row_adds(hp, options, rowptr, cntptr, indent):
+    """C lines adding one event's terms to the shared-memory row of its bin."""
+    slots, count_u32 = hp.row_layout(options)
+    cas128 = options.get("cas128", True)
+    out = []
+
+    def val(t):
+        return "1.0" if hp.terms[t] is None else hp.terms[t]
+    j = 0
+    while j < len(slots):
+        if cas128 and j + 1 < len(slots):
+            if slots[j + 1] == -1:
+                out.append("%shb_sadd_f64(%s + %d, %s);" % (indent, rowptr, j, val(slots[j])))
+            else:
+                out.append("%shb_sadd_f64x2(%s + %d, %s, %s);" % (indent, rowptr, j, val(slots[j]), val(slots[j + 1])))
+            j += 2
+        else:
+            out.append("%shb_sadd_f64(%s + %d, %s);" % (indent, rowptr, j, val(slots[j])))
+            j += 1
+    if count_u32:
+        out.append("%shb_sadd_u32(%s, 1u);" % (indent, cntptr))
+    return out
+
+
+def _emit_row_merge(hp, options, rowptr, cntexpr, indent):
+    """C lines adding one shared-memory row to the global row ``row`` (float64 REDs, zero slots skipped)."""
+    slots, count_u32 = hp.row_layout(options)
+    out = []
+    for j, t in enumerate(slots):
+        if t == -1:
+            continue
+        out.append("%s{ const double v = %s[%d];" % (indent, rowptr, j))
+        out.append("%s  if (v != 0.0) {" % indent)
+        for col in hp.dest[t]:
+            out.append("%s    hb_red_f64(row + %d, v);" % (indent, col))
+        out.append("%s  } }" % indent)
+    if count_u32:
+        out.append("%s{ const hb_u32 c = %s;" % (indent, cntexpr))
+        out.append("%s  if (c != 0u) { const double v = (double)c;" % indent)
+        for col in hp.dest[hp.count_term]:
+            out.append("%s    hb_red_f64(row + %d, v);" % (indent, col))
+        out.append("%s  } }" % indent)
+    return out
+
+
 def generate(spec, coltypes, options=None):
     """The fill kernel of a spec for one set of column dtypes."""
     options = options or {}
@@ -762,22 +829,15 @@ def generate(spec, coltypes, options=None):
         outside = ""
         if hp.strategy == "window":
             # inside the hot window -> shared memory; p.win = [words, W, lo_0, n_0, lo_1, n_1, ...]
-            nf = len(hp.f64_terms)
+            nf = len(hp.row_layout(options)[0])
             ev.append("    const bool okw = %s;" % " && ".join(conds))
             ev.append("    bool inside = okw; int wb = 0;")
             for a, (v, totbins) in enumerate(hp.index):
                 ev.append("    { const unsigned a = (unsigned)(%s - p.win[%d]); inside = inside && (a < (unsigned)p.win[%d]); wb = wb * p.win[%d] + (int)a; }"
                           % (v.c, 2 + 2 * a, 3 + 2 * a, 3 + 2 * a))
             ev.append("    if (inside) {")
-            if nf:
-                ev.append("        double* const wrow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)wb * %d;" % (hp.win_off, nf))
-            k = 0
-            for t, e in enumerate(hp.terms):
-                if e is None:
-                    ev.append("        hb_sadd_u32(reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb, 1u);" % (hp.win_off, nf * 8))
-                else:
-                    ev.append("        hb_sadd_f64(wrow + %d, %s);" % (k, e))
-                    k += 1
+            ev.append("        double* const wrow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)wb * %d;" % (hp.win_off, nf))
+            ev.extend(_emit_row_adds(hp, options, "wrow", "reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb" % (hp.win_off, nf * 8), "        "))
             ev.append("    }")
             conds = ["okw", "!inside"]
         if pair:
@@ -798,13 +858,10 @@ def generate(spec, coltypes, options=None):
         ev.append("    if (%s) {" % (" && ".join(conds) if conds else "true"))
         ev.append("        const int bin = %s;" % idx)
         if hp.strategy == "smem":
-            nf = 0
-            for t, e in enumerate(hp.terms):
-                if e is None:
-                    ev.append("        hb_sadd_u32(reinterpret_cast<hb_u32*>(hb_smem + %d) + bin, 1u);" % hp.smem_u32_off)
-                else:
-                    ev.append("        hb_sadd_f64(reinterpret_cast<double*>(hb_smem + %d) + %d + bin, %s);" % (hp.smem_f64_off, nf * hp.nbins, e))
-                    nf += 1
+            nslots = len(hp.row_layout(options)[0])
+            if nslots:
+                ev.append("        double* const srow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)bin * %d;" % (hp.smem_f64_off, nslots))
+            ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + bin" % hp.smem_u32_off, "        "))
         else:
             if hp.groups:
                 ev.append("        double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
@@ -829,23 +886,14 @@ def generate(spec, coltypes, options=None):
         merge.append("// merge hist %d" % hp.hid)
         merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nbins)
         merge.append("    double* const row = p.hist[%d] + (hb_i64)b * %d;" % (hp.hid, hp.ncol))
-        nf = 0
-        for t, e in enumerate(hp.terms):
-            if e is None:
-                merge.append("    { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d)[b];" % hp.smem_u32_off)
-                merge.append("      if (c != 0u) { const double v = (double)c;")
-            else:
-                merge.append("    { const double v = reinterpret_cast<const double*>(hb_smem + %d)[%d + b];" % (hp.smem_f64_off, nf * hp.nbins))
-                merge.append("      if (v != 0.0) {")
-                nf += 1
-            for col in hp.dest[t]:
-                merge.append("        hb_red_f64(row + %d, v);" % col)
-            merge.append("      } }")
+        nslots = len(hp.row_layout(options)[0])
+        merge.append("    const double* const srow = reinterpret_cast<const double*>(hb_smem + %d) + (hb_i64)b * %d;" % (hp.smem_f64_off, nslots))
+        merge.extend(_emit_row_merge(hp, options, "srow", "reinterpret_cast<const hb_u32*>(hb_smem + %d)[b]" % hp.smem_u32_off, "    "))
         merge.append("}")
 
     if window is not None:
         hp = window
-        nf = len(hp.f64_terms)
+        nf = len(hp.row_layout(options)[0])
         merge.append("// merge the hot window of hist %d" % hp.hid)
         merge.append("for (int wb = threadIdx.x; wb < p.win[1]; wb += HB_THREADS) {")
         merge.append("    int rest = wb; hb_i64 bin = 0;")
@@ -854,18 +902,8 @@ def generate(spec, coltypes, options=None):
             merge.append("    bin += (hb_i64)(p.win[%d] + rest %% p.win[%d]) * %d; rest /= p.win[%d];" % (2 + 2 * a, 3 + 2 * a, stride, 3 + 2 * a))
             stride *= hp.index[a][1]
         merge.append("    double* const row = p.hist[%d] + bin * %d;" % (hp.hid, hp.ncol))
-        k_ = 0
-        for t, e in enumerate(hp.terms):
-            if e is None:
-                merge.append("    { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb];" % (hp.win_off, nf * 8))
-                merge.append("      if (c != 0u) { const double v = (double)c;")
-            else:
-                merge.append("    { const double v = reinterpret_cast<const double*>(hb_smem + %d)[(hb_i64)wb * %d + %d];" % (hp.win_off, nf, k_))
-                merge.append("      if (v != 0.0) {")
-                k_ += 1
-            for col in hp.dest[t]:
-                merge.append("        hb_red_f64(row + %d, v);" % col)
-            merge.append("      } }")
+        merge.append("    const double* const wrow = reinterpret_cast<const double*>(hb_smem + %d) + (hb_i64)wb * %d;" % (hp.win_off, nf))
+        merge.extend(_emit_row_merge(hp, options, "wrow", "reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb]" % (hp.win_off, nf * 8), "    "))
         merge.append("}")
 
     k = Kernel()
@@ -874,7 +912,7 @@ def generate(spec, coltypes, options=None):
     k.plans = plans
     k.smem_bytes = smem_cap
     if window is not None:
-        bpb = 8 * len(window.f64_terms) + (4 if window.count_term is not None else 0)
+        bpb = window.row_bytes(options)
         k.window = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "totbins": [t for v, t in window.index],
                     "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"]}
     k.threads = threads
