@@ -853,11 +853,13 @@ def generate(spec, coltypes, options=None):
             t0 = 0 if hp.dest[0] == [0] else 1
             v0 = "1.0" if hp.terms[t0] is None else hp.terms[t0]
             v1 = "1.0" if hp.terms[1 - t0] is None else hp.terms[1 - t0]
-            rowexpr = ("((hb_i64)slot * %d + bin)" % hp.nbins) if hp.groups else "(hb_i64)bin"
             ev.append("    {")
             ev.append("        const bool okrow = %s;" % " && ".join(conds))
             ev.append("        const int bin = okrow ? (%s) : 0;" % idx)
-            ev.append("        hb_red_pair(p.hist[%d], okrow ? %s : (hb_i64)-1, %s, %s);" % (hp.hid, rowexpr, v0, v1))
+            if hp.groups:
+                ev.append("        hb_red_pair(p.hist[%d], okrow ? ((hb_i64)slot * %d + bin) : (hb_i64)-1, %s, %s);" % (hp.hid, hp.nbins, v0, v1))
+            else:
+                ev.append("        hb_red_pair(p.hist[%d], okrow ? bin : -1, %s, %s);" % (hp.hid, v0, v1))
             ev.append("    }")
             ev.append("}")
             continue
