@@ -492,6 +492,8 @@ class HistPlan(object):
         self.smem_f64_off = None   # byte offset of the [nbins][slots] float64 rows
         self.smem_u32_off = None   # byte offset of the [nbins] u32 count block
         self.win_off = None        # "window" strategy: byte offset of the runtime-sized hot window region
+        self.gcap = 0              # group histograms: slab slots [0, gcap) are privatised in shared memory
+        self.skip_zero = False     # filter-derived weight: rows whose every term is exactly 0.0 are not accumulated
 
     def add_term(self, expr, col):
         for t, e in enumerate(self.terms):
@@ -535,8 +537,12 @@ class HistPlan(object):
         slots, count_u32 = self.row_layout(options)
         return 8 * len(slots) + (4 if count_u32 else 0)
 
+    @property
+    def nrows(self):
+        return self.nbins * max(self.gcap, 1)
+
     def smem_bytes(self, options=None):
-        return self.nbins * self.row_bytes(options)
+        return self.nrows * self.row_bytes(options)
 
 
 def _mulexpr(prog, a, b):
@@ -569,6 +575,9 @@ def plan_hist(prog, hid, h):
         else:
             wz, w2z = wv, w2v
 
+    if w is not None and "w" in w and "where" in hbspec.dumps(w["w"]):
+        hp.skip_zero = True          # filter: where(cond, 1, 0) [* weight] is exactly 0 for rejected rows
+
     for p in h["profile"]:
         sx, sx2 = prog.lower(p["sumx"]), prog.lower(p["sumx2"])
         for val, col in ((sx, p["sumwx"]), (sx2, p["sumwx2"])):
@@ -597,13 +606,14 @@ def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
     budget = int(options.get("smem_budget", 96 * 1024))
     forced = options.get("strategy", {})
+    for hp in plans:
+        # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
+        # without this every event of such a histogram is a contended global RED (c4: 8 per event)
+        hp.gcap = int(options.get("group_slots", 16)) if hp.groups else 0
     order = sorted(plans, key=lambda hp: hp.smem_bytes(options))
     used = 0
     for hp in order:
         want = forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*")))
-        if hp.groups:
-            hp.strategy = "global"
-            continue
         need = hp.smem_bytes(options)
         if want == "global":
             hp.strategy = "global"
@@ -615,7 +625,7 @@ def choose_strategies(plans, options):
             # f64 block first (8-byte aligned), u32 block after
             slots, count_u32 = hp.row_layout(options)
             hp.smem_f64_off = used
-            hp.smem_u32_off = used + hp.nbins * 8 * len(slots)
+            hp.smem_u32_off = used + hp.nrows * 8 * len(slots)
             used += (need + 15) // 16 * 16
     # Hot-window privatisation: ONE histogram that is too large for shared memory keeps a runtime-placed
     # hyper-rectangle of its bins (where most events land) in shared memory; the rest goes to global REDs.
@@ -863,13 +873,31 @@ def generate(spec, coltypes, options=None):
             ev.append("    }")
             ev.append("}")
             continue
+        if hp.skip_zero:
+            nz = ["(%s != 0.0)" % e for e in hp.terms if e is not None]
+            if nz and len(nz) == len(hp.terms):
+                conds = conds + ["(%s)" % " || ".join(nz)]
         ev.append("    if (%s) {" % (" && ".join(conds) if conds else "true"))
         ev.append("        const int bin = %s;" % idx)
         if hp.strategy == "smem":
             nslots = len(hp.row_layout(options)[0])
+            indent = "        "
+            if hp.groups:
+                ev.append("        if (slot < %d) {" % hp.gcap)
+                ev.append("            const int srowi = slot * %d + bin;" % hp.nbins)
+                indent = "            "
+            else:
+                ev.append("        const int srowi = bin;")
             if nslots:
-                ev.append("        double* const srow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)bin * %d;" % (hp.smem_f64_off, nslots))
-            ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + bin" % hp.smem_u32_off, "        "))
+                ev.append("%sdouble* const srow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)srowi * %d;" % (indent, hp.smem_f64_off, nslots))
+            ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + srowi" % hp.smem_u32_off, indent))
+            if hp.groups:
+                ev.append("        } else {")
+                ev.append("            double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
+                for t, e in enumerate(hp.terms):
+                    for col in hp.dest[t]:
+                        ev.append("            hb_red_f64(row + %d, %s);" % (col, "1.0" if e is None else e))
+                ev.append("        }")
         else:
             if hp.groups:
                 ev.append("        double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
@@ -892,7 +920,7 @@ def generate(spec, coltypes, options=None):
         if hp.strategy != "smem":
             continue
         merge.append("// merge hist %d" % hp.hid)
-        merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nbins)
+        merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nrows)
         merge.append("    double* const row = p.hist[%d] + (hb_i64)b * %d;" % (hp.hid, hp.ncol))
         nslots = len(hp.row_layout(options)[0])
         merge.append("    const double* const srow = reinterpret_cast<const double*>(hb_smem + %d) + (hb_i64)b * %d;" % (hp.smem_f64_off, nslots))
