@@ -631,7 +631,9 @@ def choose_strategies(plans, options):
     # hyper-rectangle of its bins (where most events land) in shared memory; the rest goes to global REDs.
     window = None
     if options.get("window", True):
+        # (the device marginals kernel keeps one float64 per bin of every axis in 48 KB of shared memory)
         cands = [hp for hp in plans if hp.strategy == "global" and not hp.groups and hp.index
+                 and sum(t for v, t in hp.index) * 8 <= 48 * 1024 and len(hp.index) <= 8
                  and forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) in (None, "window")]
         if cands:
             window = min(cands, key=lambda hp: hp.nbins)

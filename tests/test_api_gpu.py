@@ -1,0 +1,219 @@
+"""The unchanged histbook API on the device backend (run on the B200 with -m gpu).
+
+These read like the reference's own tests/test_hist.py and tests/test_book.py (line numbers cited) because the
+contract is that nothing above ``fill`` changes: same constructors, same ``_content`` layout, same merge
+algebra, same read side (``table``, ``project``, pickle, JSON).  histbook itself comes from ``baseline/_ref``
+(the unmodified reference, pip-installed with --target; git-ignored but shipped to the GPU box).
+"""
+import pickle
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+histbook_b200 = pytest.importorskip("histbook_b200")
+if not histbook_b200._ref.available():
+    pytest.skip("the histbook package (baseline/_ref) is not available", allow_module_level=True)
+
+from histbook import *       # noqa: E402,F401,F403
+from histbook import Book, ChannelsBook, Hist, SamplesBook, SystematicsBook, bin, cut, groupbin, groupby, intbin, profile, split  # noqa: E402
+
+
+def test_backend_is_installed():
+    assert histbook_b200.installed()
+    assert isinstance(Hist.__dict__["_content"], property)
+
+
+def test_calc_and_defs():                                    # tests/test_hist.py:43-51
+    h = Hist(bin("x + 0.1", 10, 0, 1))
+    h.fill(x=[0.4, 0.3, 0.3, 0.5, 0.4, 0.8])
+    assert h._content.tolist() == [[0], [0], [0], [0], [0], [2], [2], [1], [0], [0], [1], [0], [0]]
+    h = Hist(bin("y", 10, 0, 1), defs={"y": "x + 0.1"})
+    h.fill(x=[0.4, 0.3, 0.3, 0.5, 0.4, 0.8])
+    assert h._content.tolist() == [[0], [0], [0], [0], [0], [2], [2], [1], [0], [0], [1], [0], [0]]
+
+
+def test_nofixed():                                          # tests/test_hist.py:64-78
+    h = Hist(profile("x"))
+    h.fill(x=[3, 3, 5, 5])
+    assert h._content.tolist() == [16, 68, 4]
+    h = Hist(weight="x")
+    h.fill(x=[3, 3, 5, 5])
+    assert h._content.tolist() == [16, 68]
+    h = Hist(profile("y"), weight="x")
+    h.fill(x=[2], y=[3])
+    assert h._content.tolist() == [6, 18, 2, 4]
+
+
+def test_bin_flags():                                        # tests/test_hist.py:80-111
+    x = [0.4, 0.3, 123, 99, 0.3, numpy.nan, numpy.nan, numpy.nan, 0.5, -99, 0.4, 0.8]
+    h = Hist(bin("x", 10, 0, 1))
+    h.fill(x=x)
+    assert h._content.tolist() == [[1], [0], [0], [0], [2], [2], [1], [0], [0], [1], [0], [2], [3]]
+    h = Hist(bin("x", 10, 0, 1, underflow=False, overflow=False, nanflow=False))
+    h.fill(x=x)
+    assert h._content.tolist() == [[0], [0], [0], [2], [2], [1], [0], [0], [1], [0]]
+
+
+def test_weight_filter():                                    # tests/test_hist.py:118-152
+    h = Hist(bin("x", 10, 10, 11), weight="y")
+    h.fill(x=[10.4, 10.3, 10.3, 10.5, 10.4, 10.8], y=[0.1, 0.1, 0.1, 0.1, 0.1, 1.0])
+    assert h._content.tolist() == [[0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.2, 0.020000000000000004], [0.2, 0.020000000000000004], [0.1, 0.010000000000000002], [0.0, 0.0], [0.0, 0.0], [1.0, 1.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]]
+    h = Hist(bin("x", 10, 10, 11)).weight(2).filter("y > 0")
+    h.fill(x=[10.4, 10.3, 10.3, 10.5, 10.4, 10.8], y=[-1, -1, -1, 1, 1, 1])
+    assert h._content.tolist() == [[0, 0], [0, 0], [0, 0], [0, 0], [0, 0], [2, 4], [2, 4], [0, 0], [0, 0], [2, 4], [0, 0], [0, 0], [0, 0]]
+
+
+def test_intbin_split_cut_profile():                          # tests/test_hist.py:305-392
+    h = Hist(intbin("x", 0, 10, underflow=True, overflow=True))
+    h.fill(x=range(-5, 15))
+    assert h._content.tolist() == [[5], [1], [1], [1], [1], [1], [1], [1], [1], [1], [1], [1], [4]]
+    h = Hist(split("x", (2.5, 3.5, 5.0), closedlow=False))
+    h.fill(x=[0, 1, 2, 3, 4, 5, 6])
+    assert h._content.tolist() == [[3], [1], [2], [1], [0]]
+    h = Hist(cut("x > 3 and y % 2 == 0"), split("x", 3.5))
+    h.fill(x=[1, 2, 3, 4, 5], y=[0, 1, 2, 3, 4])
+    assert h._content.tolist() == [[[3], [1], [0]], [[0], [1], [0]]]
+    h = Hist(bin("x", 10, 10, 11), profile("y"), profile("2*y"))
+    h.fill(x=[10.4, 10.3, 10.3, 10.5, 10.4, 10.8], y=[0.1, 0.1, 0.1, 0.1, 0.1, 1.0])
+    assert h._content[9].tolist() == [1.0, 1.0, 2.0, 4.0, 1.0]
+    assert h._content[4].tolist() == [0.2, 0.020000000000000004, 0.4, 0.08000000000000002, 2.0]
+
+
+def test_groupbin_and_numeric_groupby():                      # tests/test_hist.py:409-435 (numeric keys)
+    h = Hist(groupbin("x", 10.0), bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False))
+    h.fill(x=[0, 10, 15, 20], y=[1, 2, 3, 4])
+    assert h._content[0.0].tolist() == [[1], [0], [0], [0]]
+    assert h._content[10.0].tolist() == [[0], [1], [1], [0]]
+    assert h._content[20.0].tolist() == [[0], [0], [0], [1]]
+    h.fill(x=[30.0, 0.5], y=[1.5, 4.5])                       # refill: new key appears, old ones accumulate
+    assert h._content[30.0].tolist() == [[1], [0], [0], [0]]
+    assert h._content[0.0].tolist() == [[1], [0], [0], [1]]
+    h = Hist(bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False), groupby("c"), groupbin("x", 10.0))
+    h.fill(c=[1, 1, 2, 2], x=[0, 10, 15, 20], y=[1, 2, 3, 4])
+    assert h._content[1][0.0].tolist() == [[1], [0], [0], [0]]
+    assert h._content[2][20.0].tolist() == [[0], [0], [0], [1]]
+    assert h.groupkeys(0) == set([1, 2])
+
+
+def test_pickle_and_json_roundtrip():                         # tests/test_hist.py:437-449
+    h = Hist(split("x", (1, 2, 3)), bin("y", 10, 0, 1), defs={"y": "x + 0.1"}, weight="sqrt(x)", filter="x > 2")
+    assert h == pickle.loads(pickle.dumps(h))
+    h.fill(x=[1, 2, 3])
+    assert h == pickle.loads(pickle.dumps(h))
+    assert h == Hist.fromjson(h.tojson())
+    h2 = pickle.loads(pickle.dumps(h))
+    h2.fill(x=[3, 3])                                          # host content goes back to the device and accumulates
+    assert h2._content.sum() > h._content.sum()
+
+
+def test_book_fill_and_algebra():                             # tests/test_book.py:43-142
+    b = Book()
+    b["one"] = Hist(bin("x", 2, 0, 3, underflow=False, overflow=False, nanflow=False))
+    b["two"] = Hist(split("y", 1.5, nanflow=False))
+    b.fill(x=[1, 1, 1, 2, 2], y=[1, 1, 1, 2, 2])
+    assert b["one"]._content.tolist() == [[3], [2]]
+    assert b["two"]._content.tolist() == [[3], [2]]
+
+    book1, book2 = Book(), Book()
+    book1["a"] = Hist(bin("x", 4, 0, 4), fill=[0, 0, 0])
+    book1["b"] = Hist(bin("x", 4, 0, 4), fill=[0, 1, 1])
+    book1["d"] = Hist(bin("x", 4, 0, 4), fill=[])
+    book2["a"] = Hist(bin("x", 4, 0, 4), fill=[2, 2])
+    book2["b"] = Hist(bin("x", 4, 0, 4), fill=[0, 3, 3, 3, 3])
+    book2["c"] = Hist(bin("x", 4, 0, 4), fill=[0, 1, 2, 3])
+    book = book1 + book2
+    assert book["a"][:].tolist() == [[0], [3], [0], [2], [0], [0], [0]]
+    assert book["b"][:].tolist() == [[0], [2], [2], [0], [4], [0], [0]]
+    assert book["d"][:].tolist() == [[0], [0], [0], [0], [0], [0], [0]]
+    assert book["c"][:].tolist() == [[0], [1], [1], [1], [1], [0], [0]]
+    assert book1["a"][:].tolist() == [[0], [3], [0], [0], [0], [0], [0]]      # operands untouched
+    book3 = book1 * 1.5
+    assert book3["b"][:].tolist() == [[0], [1.5], [3], [0], [0], [0], [0]]
+    book1 += book2
+    assert book1["b"][:].tolist() == [[0], [2], [2], [0], [4], [0], [0]]
+    book1 *= 2
+    assert book1["a"][:].tolist() == [[0], [6], [0], [4], [0], [0], [0]]
+    book1.fill(x=[3.5])                                       # host-modified contents are uploaded again
+    assert book1["a"][:].tolist() == [[0], [6], [0], [4], [1], [0], [0]]
+
+
+def test_views_and_copy_on_fill():                            # tests/test_book.py:160-173
+    everything = ChannelsBook(
+        mass=SamplesBook(["data", "signal", "background"],
+                         SystematicsBook(Hist(bin("x", 5, 0, 5), systematic=[0]),
+                                         Hist(bin("x + epsilon", 5, 0, 5), systematic=[1]),
+                                         Hist(bin("x - epsilon", 5, 0, 5), systematic=[-1]))),
+        truth=SamplesBook(["signal", "background"],
+                          Book(par1=Hist(bin("par1", 5, 0, 5)), par2=Hist(bin("par2", 5, 0, 5)))))
+    rs = numpy.random.RandomState(1)
+    everything.view("*/data/*").fill(x=rs.uniform(0, 5, 100000), epsilon=rs.normal(0, 0.01, 100000))
+    assert everything["mass/data/0/0"].table(recarray=False).sum() == 100000
+    assert everything["mass/signal/0/0"].table(recarray=False).sum() == 0
+
+    h = Hist(bin("x", 4, 0, 4), fill=[0.5, 1.5])
+    c = h.copyonfill()
+    assert c._content.tolist() == h._content.tolist()
+    c.fill(x=[2.5])
+    assert h._content.tolist() == [[0], [1], [1], [0], [0], [0], [0]]
+    assert c._content.tolist() == [[0], [1], [1], [1], [0], [0], [0]]
+    d = c.copy()
+    d.fill(x=[3.5])
+    assert c._content.sum() == 3 and d._content.sum() == 4
+    c.clear()
+    assert c._content is None
+
+
+def test_device_columns_pandas_and_read_side():
+    import torch
+    rs = numpy.random.RandomState(3)
+    x, y, w = rs.normal(0, 1, 200000), rs.normal(0, 1, 200000), rs.uniform(0.5, 1.5, 200000)
+    h = Hist(bin("x + y", 20, -5, 5), bin("sqrt(x**2 + y**2)", 10, 0, 5), weight="w")
+    h.fill(x=torch.from_numpy(x).cuda(), y=torch.from_numpy(y).cuda(), w=torch.from_numpy(w).cuda())
+    with histbook_b200.reference_path() as hb:
+        r = hb.Hist(hb.bin("x + y", 20, -5, 5), hb.bin("sqrt(x**2 + y**2)", 10, 0, 5), weight="w")
+        r.fill(x=x, y=y, w=w)
+        expect = r._content
+        expect_table = r.project("x + y").table(recarray=False)
+    assert numpy.allclose(h._content, expect, rtol=1e-12, atol=0)
+    assert numpy.allclose(h.project("x + y").table(recarray=False), expect_table, rtol=1e-12)
+    import pandas
+    h2 = Hist(bin("x", 10, -3, 3))
+    h2.fill(pandas.DataFrame({"x": x}))
+    h3 = Hist(bin("x", 10, -3, 3))
+    h3.fill(x=x)
+    assert numpy.array_equal(h2._content, h3._content) and h2._content.sum() == len(x)
+    assert h2.pandas().shape[0] == 13
+
+
+def test_randomised_book_against_the_reference_path():
+    rs = numpy.random.RandomState(99)
+    n = 300000
+    cols = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n), "z": rs.normal(0, 1, n), "w": rs.uniform(0.5, 1.5, n),
+            "n": rs.poisson(3, n).astype(numpy.int64)}
+    cols["x"][::1009] = numpy.nan
+
+    def make(hb):
+        b = hb.Book()
+        b["a"] = hb.Hist(hb.bin("x", 100, -5, 5))
+        b["b"] = hb.Hist(hb.bin("x*y", 50, -5, 5), hb.intbin("n", 0, 9), weight="w")
+        b["c"] = hb.Hist(hb.split("z", (-2, -1, 0, 1, 2)), hb.cut("x > y"), hb.profile("z"))
+        b["d"] = hb.Hist(hb.groupbin("n", 2), hb.bin("sqrt(x**2+y**2+z**2)", 50, 0, 5), filter="n >= 3", weight="w")
+        return b
+    ours = make(__import__("histbook"))
+    ours.fill(**cols)
+    ours.fill(**cols)
+    with histbook_b200.reference_path() as hb:
+        ref = make(hb)
+        ref.fill(**cols)
+        ref.fill(**cols)
+        expect = dict((k, ref[k]._content) for k in "abcd")
+    for k in "abc":
+        got = ours[k]._content
+        both_nan = numpy.isnan(got) & numpy.isnan(expect[k])
+        assert numpy.allclose(numpy.where(both_nan, 0, got), numpy.where(both_nan, 0, expect[k]), rtol=1e-11, atol=1e-9), k
+    assert numpy.array_equal(ours["a"]._content, expect["a"])
+    assert set(ours["d"]._content.keys()) == set(expect["d"].keys())
+    for key in expect["d"]:
+        assert numpy.allclose(ours["d"]._content[key], expect["d"][key], rtol=1e-11, atol=1e-9)

@@ -29,9 +29,22 @@ def main():
     if not variants:
         variants = [{}]
     engine.init(0)
-    case, default_n, bpe, _ = bench_cpu.WORKLOADS[workload]
-    n = n or default_n
-    spec = bench_cpu.load_case(case)["spec"]
+    if workload.startswith("hist:"):
+        # ad-hoc: tools/sweep.py 'hist:Hist(bin("x",100,-5,5), weight="w")' n=1e8 ...   (needs histbook importable)
+        import histbook_b200
+        from histbook_b200 import spec as hbspec
+        hb = histbook_b200.reference()
+        env = dict((k, getattr(hb, k)) for k in ("Hist", "bin", "intbin", "split", "cut", "profile", "groupby", "groupbin"))
+        hists = [eval(src, dict(env)) for src in workload[5:].split(";;")]
+        spec = hbspec.book_spec(hists)
+        fields = hbspec.spec_fields(spec)
+        bench_cpu.WORKLOADS[workload] = (None, 10**8, 8 * len(fields), tuple(fields))
+        n = n or 10**8
+        bpe = 8 * len(fields)
+    else:
+        case, default_n, bpe, _ = bench_cpu.WORKLOADS[workload]
+        n = n or default_n
+        spec = bench_cpu.load_case(case)["spec"]
     cols = bench.device_columns(torch, workload, n, 12345, torch.device("cuda", 0))
     for opts in variants:
         fillable._options.clear()
@@ -52,7 +65,7 @@ def main():
         ms = e0.elapsed_time(e1) / steps
         st = fillable.last_stats
         print("%s %-60s %9.3f ms  %8.2f Gev/s  %7.1f GB/s (%.1f%%)  regs=%s smem=%s grid=%s occ=%s win=%s cov=%s" % (
-            workload, json.dumps(opts), ms, n / ms * 1e-6, n * bpe / ms * 1e-6, 100 * n * bpe / ms * 1e-6 / 6551,
+            workload[:40], json.dumps(opts), ms, n / ms * 1e-6, n * bpe / ms * 1e-6, 100 * n * bpe / ms * 1e-6 / 6551,
             st.get("regs"), st.get("smem_bytes"), st.get("grid"), st.get("blocks_per_sm"), st.get("window"), st.get("window_coverage")), flush=True)
 
 
