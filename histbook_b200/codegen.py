@@ -24,6 +24,7 @@ import numpy
 from histbook_b200 import spec as hbspec
 
 THREADS = 256
+MAX_WIN = 128              # hb_template.cuh HB_MAX_WIN
 VEC = 4                    # events per thread per tile (hb_load4)
 
 MAYBECONSTANTS = {"pi": numpy.pi, "Pi": numpy.pi, "e": numpy.e, "E": numpy.e,
@@ -492,8 +493,12 @@ class HistPlan(object):
         self.smem_f64_off = None   # byte offset of the [nbins][slots] float64 rows
         self.smem_u32_off = None   # byte offset of the [nbins] u32 count block
         self.win_off = None        # "window" strategy: byte offset of the runtime-sized hot window region
+        self.win_table_off = None  # byte offset of the per-row interval table (8 bytes per row)
+        self.win_split = None      # the first `win_split` fixed axes form the row index, the rest the in-row index
         self.gcap = 0              # group histograms: slab slots [0, gcap) are privatised in shared memory
         self.skip_zero = False     # filter-derived weight: rows whose every term is exactly 0.0 are not accumulated
+        self.fx = False            # float64 terms privatised as exact 128-bit fixed point (hb_template.cuh HbFx)
+        self.fx_index = {}         # term index -> index of its scale in p.win[2 + ...]
 
     def add_term(self, expr, col):
         for t, e in enumerate(self.terms):
@@ -520,10 +525,10 @@ class HistPlan(object):
 
         Returns (slots, count_u32): ``slots`` = term index per float64 slot (-1 = padding); an unweighted
         count joins the float64 slots when that makes their number even (it is exact in float64 below 2^53)."""
-        # 128-bit CAS pairs pay off only where lanes rarely meet in one bin (the hot window of a large
-        # histogram: +7 % on c2); on small, contended tables the hand-rolled CAS.128 loop collapses
-        # (c3: 116 -> 42 Gev/s, measured), so statically privatised histograms keep 64-bit atomicAdd.
-        cas128 = (options or {}).get("cas128", self.strategy == "window")
+        # 128-bit CAS pairs (bin-major rows) were +7 % on c2 over two 64-bit atomicAdd on the same bin-major rows,
+        # but slot-major 64-bit atomicAdd beats both (c2: 127 bin-major / 153 CAS.128 / 156 slot-major Gev/s), and
+        # on small, contended tables the hand-rolled CAS.128 loop collapses (c3: 116 -> 42 Gev/s): off by default.
+        cas128 = (options or {}).get("cas128", False) and not self.fx
         slots = list(self.f64_terms)
         count_u32 = self.count_term is not None
         if cas128 and count_u32 and len(slots) % 2 == 1:
@@ -533,13 +538,38 @@ class HistPlan(object):
             slots.append(-1)
         return slots, count_u32
 
+    def strides(self, options, nrows_expr):
+        """(stride between bins, stride between the float64 slots of one bin), in doubles.  128-bit CAS pairs need
+        the two slots side by side (bin-major rows); separate 64-bit atomics are faster slot-major, where
+        consecutive instructions of a warp spread over all banks instead of every second one."""
+        opts = options or {}
+        cas128 = opts.get("cas128", False)
+        nslots = len(self.row_layout(options)[0])
+        if opts.get("soa", not cas128) and not cas128:
+            return "1", str(nrows_expr)
+        return str(nslots), "1"
+
+    @property
+    def slot_bytes(self):
+        return 16 if self.fx else 8
+
     def row_bytes(self, options=None):
         slots, count_u32 = self.row_layout(options)
-        return 8 * len(slots) + (4 if count_u32 else 0)
+        return self.slot_bytes * len(slots) + (4 if count_u32 else 0)
 
     @property
     def nrows(self):
         return self.nbins * max(self.gcap, 1)
+
+    @property
+    def win_rows(self):
+        tots = [t for v, t in self.index]
+        return int(numpy.prod(tots[:self.win_split], dtype=numpy.int64)) if self.win_split else 1
+
+    @property
+    def win_trail(self):
+        tots = [t for v, t in self.index]
+        return int(numpy.prod(tots[self.win_split:], dtype=numpy.int64))
 
     def smem_bytes(self, options=None):
         return self.nrows * self.row_bytes(options)
@@ -604,14 +634,24 @@ def plan_hist(prog, hid, h):
 
 def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
-    budget = int(options.get("smem_budget", 96 * 1024))
+    budget = int(options.get("smem_budget", (200 if options.get("fx", False) else 96) * 1024))
     forced = options.get("strategy", {})
+    nfx = 0
+    for hp in plans:
+        # exact fixed point instead of float64 CAS loops for every privatised float64 term (16 instead of 8 bytes);
+        # every such term gets a run-time scale in p.win[2 + index]
+        hp.fx = (bool(options.get("fx", False)) and not options.get("cas128", False) and len(hp.f64_terms) > 0
+                 and nfx + len(hp.f64_terms) <= MAX_WIN - 2)
+        if hp.fx:
+            for t in hp.f64_terms:
+                hp.fx_index[t] = nfx
+                nfx += 1
     for hp in plans:
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
         hp.gcap = int(options.get("group_slots", 16)) if hp.groups else 0
     order = sorted(plans, key=lambda hp: hp.smem_bytes(options))
-    used = 0
+    used = 16 if nfx else 0           # word 0: how many terms did not fit their fixed-point window (HB_FXMISS)
     for hp in order:
         want = forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*")))
         need = hp.smem_bytes(options)
@@ -625,21 +665,47 @@ def choose_strategies(plans, options):
             # f64 block first (8-byte aligned), u32 block after
             slots, count_u32 = hp.row_layout(options)
             hp.smem_f64_off = used
-            hp.smem_u32_off = used + hp.nrows * 8 * len(slots)
+            hp.smem_u32_off = used + hp.nrows * hp.slot_bytes * len(slots)
             used += (need + 15) // 16 * 16
-    # Hot-window privatisation: ONE histogram that is too large for shared memory keeps a runtime-placed
-    # hyper-rectangle of its bins (where most events land) in shared memory; the rest goes to global REDs.
+    # Hot-window privatisation: ONE histogram that is too large for shared memory keeps the bins where most
+    # events land in shared memory; the rest goes to global REDs.  The window is *ragged*: the leading fixed
+    # axes are flattened into a row index, and every row owns one contiguous interval of the (flattened)
+    # trailing axes, placed at run time (fillable.choose_ragged) from what the histogram already holds.
+    # For c2 the populated region of (x+y, r) is a V (|x+y| <= sqrt(2) r): at 6400 bins a rectangle covers
+    # 80 % of the events, per-row intervals 94.5 % (tools/window_coverage.py).
     window = None
     if options.get("window", True):
-        # (the device marginals kernel keeps one float64 per bin of every axis in 48 KB of shared memory)
-        cands = [hp for hp in plans if hp.strategy == "global" and not hp.groups and hp.index
-                 and sum(t for v, t in hp.index) * 8 <= 48 * 1024 and len(hp.index) <= 8
-                 and forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) in (None, "window")]
+        max_rows = int(options.get("win_max_rows", 4096))
+        max_bytes = int(options.get("win_max_hist_bytes", 16 << 20))
+        cands = []
+        for hp in plans:
+            if hp.strategy != "global" or hp.groups or not hp.index or hp.nbins * hp.ncol * 8 > max_bytes:
+                continue
+            if forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) not in (None, "window"):
+                continue
+            tots = [t for v, t in hp.index]
+            split = None
+            for k in range(len(tots) - 1, -1, -1):
+                rows = int(numpy.prod(tots[:k], dtype=numpy.int64)) if k else 1
+                trail = int(numpy.prod(tots[k:], dtype=numpy.int64))
+                if rows <= max_rows and trail <= 65535:
+                    split = k
+                    break
+            if split is not None:
+                hp.win_split = split
+                cands.append(hp)
         if cands:
             window = min(cands, key=lambda hp: hp.nbins)
             window.strategy = "window"
             used = (used + 15) // 16 * 16
+            window.win_table_off = used
+            used += (window.win_rows * 8 + 15) // 16 * 16
             window.win_off = used
+    for hp in plans:
+        if hp.strategy == "global":
+            hp.fx = False
+    if not any(hp.strategy in ("smem", "window") for hp in plans):
+        used = 0
     return used, window
 
 
@@ -663,6 +729,10 @@ class Kernel(object):
         self.group_aux = {}         # fill kernel: hist id -> aux slot of its group table
         self.window = None          # hot-window histogram: dict(hid, bpb, wmax, totbins, ncol, col, nf)
         self.group_goals = []       # keys kernel: [(tree key, info dict)] in aux order
+        self.fx_terms = []          # [(i, hist id, term index)] of the fixed-point terms; scale of term i in p.win[2 + i]
+        self.nfx = 0
+        self.fx_aux = None
+        self.naux = 0
 
 
 def _colarg(slot, dtype, is_scalar, loaded):
@@ -676,7 +746,7 @@ def _loadtype(dtype):
     return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
 
 
-def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, has_window=False):
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None):
     """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
     over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
     takes the scalar path), shared-memory zeroing before and block merge after."""
@@ -684,6 +754,7 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, has_w
     src.append('#include "hb_template.cuh"')
     src.append("#define HB_THREADS %d" % threads)
     src.append("#define HB_TILE (HB_THREADS * 4)")
+    src.append("#define HB_FXMISS (reinterpret_cast<hb_u32*>(hb_smem))")
     src.extend(prog.consts)
     src.append("")
     sig = ["const HbParams& p", "unsigned char* hb_smem", "const bool live"]
@@ -695,9 +766,16 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, has_w
 
     src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % minblocks)
     src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
-    if smem or has_window:
-        bound = "%d + p.win[0]" % (smem // 4) if has_window else "%d" % (smem // 4)
+    if smem or window is not None:
+        # `smem` bytes of statically privatised histograms (and the window's row table), then p.win[0] words of window
+        bound = "%d + p.win[0]" % (smem // 4) if window is not None else "%d" % (smem // 4)
         src.append("    for (int i = threadIdx.x; i < %s; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % bound)
+        if window is not None:
+            # per-row interval table of the hot window: [offset into the window | first in-row index << 16 | length]
+            src.append("    __syncthreads();")
+            src.append("    if (p.aux[%d] != nullptr)" % window["aux"])
+            src.append("        for (int i = threadIdx.x; i < %d; i += HB_THREADS)" % window["rows"])
+            src.append("            reinterpret_cast<hb_u64*>(hb_smem + %d)[i] = reinterpret_cast<const hb_u64*>(p.aux[%d])[i];" % (window["table_off"], window["aux"]))
         src.append("    __syncthreads();")
     for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
         if is_scalar:
@@ -751,14 +829,39 @@ def _group_lookup(hp, aux_slot):
     return out
 
 
-def _emit_row_adds(hp, options, rowptr, cntptr, indent):
-    """C lines adding one event's terms to the shared-memory row of its bin."""
+def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None):
+    """C lines adding one event's terms to the shared-memory row of its bin.
+
+    float64 layout: ``rowptr`` is a double* to the bin's first slot, slots ``sstride`` doubles apart.
+    Fixed-point layout (hp.fx): ``rowptr`` is a hb_u32* to limb 0 of slot 0 of the bin, ``sstride`` the number of
+    rows (limbs are that many words apart, slots four limbs apart); ``grow`` is the bin's row in the global
+    histogram, where a term that does not fit the fixed-point window is added directly."""
     slots, count_u32 = hp.row_layout(options)
-    cas128 = options.get("cas128", hp.strategy == "window")
+    cas128 = options.get("cas128", False) and not hp.fx
     out = []
 
     def val(t):
         return "1.0" if hp.terms[t] is None else hp.terms[t]
+    if hp.fx:
+        # stage k of every term before stage k+1 of any: the returning atomics overlap (hb_template.cuh)
+        for j, t in enumerate(slots):
+            out.append("%sconst double fv%d = %s;" % (indent, j, val(t)))
+            out.append("%sconst HbFx ff%d = hb_fx_decode(fv%d, p.win[%d]);" % (indent, j, j, 2 + hp.fx_index[t]))
+        for j, t in enumerate(slots):
+            out.append("%shb_u32 fc%d = hb_fx_stage0(%s + %d * %s, %s, ff%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j))
+        for j, t in enumerate(slots):
+            out.append("%sfc%d = hb_fx_stage1(%s + %d * %s, %s, ff%d, fc%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j, j))
+        for j, t in enumerate(slots):
+            out.append("%shb_fx_stage2(%s + %d * %s, %s, ff%d, fc%d);" % (indent, rowptr, 4 * j, sstride, sstride, j, j))
+        for j, t in enumerate(slots):
+            out.append("%sif (!ff%d.fits) {" % (indent, j))
+            out.append("%s    atomicAdd(HB_FXMISS, 1u);" % indent)
+            for col in hp.dest[t]:
+                out.append("%s    hb_red_f64(%s + %d, fv%d);" % (indent, grow, col, j))
+            out.append("%s}" % indent)
+        if count_u32:
+            out.append("%shb_sadd_u32(%s, 1u);" % (indent, cntptr))
+        return out
     j = 0
     while j < len(slots):
         if cas128 and j + 1 < len(slots):
@@ -768,21 +871,24 @@ def _emit_row_adds(hp, options, rowptr, cntptr, indent):
                 out.append("%shb_sadd_f64x2(%s + %d, %s, %s);" % (indent, rowptr, j, val(slots[j]), val(slots[j + 1])))
             j += 2
         else:
-            out.append("%shb_sadd_f64(%s + %d, %s);" % (indent, rowptr, j, val(slots[j])))
+            out.append("%shb_sadd_f64(%s + %d * %s, %s);" % (indent, rowptr, j, sstride, val(slots[j])))
             j += 1
     if count_u32:
         out.append("%shb_sadd_u32(%s, 1u);" % (indent, cntptr))
     return out
 
 
-def _emit_row_merge(hp, options, rowptr, cntexpr, indent):
+def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1"):
     """C lines adding one shared-memory row to the global row ``row`` (float64 REDs, zero slots skipped)."""
     slots, count_u32 = hp.row_layout(options)
     out = []
     for j, t in enumerate(slots):
         if t == -1:
             continue
-        out.append("%s{ const double v = %s[%d];" % (indent, rowptr, j))
+        if hp.fx:
+            out.append("%s{ const double v = hb_fx_read(%s + %d * %s, %s, p.win[%d]);" % (indent, rowptr, 4 * j, sstride, sstride, 2 + hp.fx_index[t]))
+        else:
+            out.append("%s{ const double v = %s[%d * %s];" % (indent, rowptr, j, sstride))
         out.append("%s  if (v != 0.0) {" % indent)
         for col in hp.dest[t]:
             out.append("%s    hb_red_f64(row + %d, v);" % (indent, col))
@@ -796,6 +902,15 @@ def _emit_row_merge(hp, options, rowptr, cntexpr, indent):
     return out
 
 
+def _rowptr(hp, options, name, base_off, index, nrows_expr, const=False):
+    """(declaration line, slot stride expr) of the shared-memory row pointer of bin ``index``."""
+    c = "const " if const else ""
+    if hp.fx:
+        return ("%shb_u32* const %s = reinterpret_cast<%shb_u32*>(hb_smem + %d) + %s;" % (c, name, c, base_off, index), str(nrows_expr))
+    bstride, sstride = hp.strides(options, nrows_expr)
+    return ("%sdouble* const %s = reinterpret_cast<%sdouble*>(hb_smem + %d) + %s * %s;" % (c, name, c, base_off, index, bstride), sstride)
+
+
 def generate(spec, coltypes, options=None):
     """The fill kernel of a spec for one set of column dtypes."""
     options = options or {}
@@ -806,18 +921,26 @@ def generate(spec, coltypes, options=None):
     smem, window = choose_strategies(plans, options)
     if len(prog.cols) > 32:
         raise UnsupportedError("more than 32 input fields in one fill")
-    threads = int(options.get("threads", THREADS))
-    minblocks = int(options.get("min_blocks", 2))
+    # resident threads per SM stay near 1024 whatever the shared-memory footprint: the fixed-point adds are chains
+    # of returning atomics and want warps to hide them
+    if smem <= 56 * 1024:
+        dthreads, dblocks = THREADS, 2
+    elif smem <= 113 * 1024:
+        dthreads, dblocks = 512, 2
+    else:
+        dthreads, dblocks = 512, 1
+    threads = int(options.get("threads", dthreads))
+    minblocks = int(options.get("min_blocks", dblocks))
     smem_cap = smem
     if window is not None:
-        # one resident block per SM that owns (almost) all of the SM's shared memory
-        # two resident blocks per SM of 512 threads, ~100 KB of shared memory each: measured best on c2
-        # (147.6 Gev/s vs 139.6 for one 1024-thread block with 200 KB) -- the shared CAS pipe and the L2 RED
-        # pipe work in parallel, so a smaller window with more traffic left to the REDs balances them.
-        threads = int(options.get("win_threads", 512))
-        minblocks = int(options.get("win_min_blocks", 2))
-        smem_cap = int(options.get("win_smem", 100 * 1024))
-        if len(window.index) * 2 + 2 > 32 or smem_cap - smem < 4096:
+        # one resident block of 1024 threads per SM that owns 200 KB of the SM's shared memory: with per-row
+        # intervals that holds 99.7 % of c2's events (12.7 k bins); measured 156 Gev/s vs 152 for two 512-thread
+        # blocks with 100 KB each (94 %) and 148 for four 256-thread blocks with 56 KB (80 %)
+        # (profiles/r01_sweeps.txt).
+        threads = int(options.get("win_threads", 1024))
+        minblocks = int(options.get("win_min_blocks", 1))
+        smem_cap = int(options.get("win_smem", 200 * 1024))
+        if smem_cap - smem < 4096:
             window.strategy, window = "global", None
             smem_cap = smem
 
@@ -846,16 +969,28 @@ def generate(spec, coltypes, options=None):
                 and sorted(hp.dest[0] + hp.dest[1]) == [0, 1])
         outside = ""
         if hp.strategy == "window":
-            # inside the hot window -> shared memory; p.win = [words, W, lo_0, n_0, lo_1, n_1, ...]
+            # inside the hot window -> shared memory.  Row table entry: x = offset of the row's interval in the
+            # window, y = (first in-row index << 16) | length; a row without interval has length 0.
             nf = len(hp.row_layout(options)[0])
+            k = hp.win_split
+            wr = "0"
+            if k:
+                wr = hp.index[0][0].c
+                for v, totbins in hp.index[1:k]:
+                    wr = "(%s) * %d + %s" % (wr, totbins, v.c)
+            wc = hp.index[k][0].c
+            for v, totbins in hp.index[k + 1:]:
+                wc = "(%s) * %d + %s" % (wc, totbins, v.c)
             ev.append("    const bool okw = %s;" % " && ".join(conds))
-            ev.append("    bool inside = okw; int wb = 0;")
-            for a, (v, totbins) in enumerate(hp.index):
-                ev.append("    { const unsigned a = (unsigned)(%s - p.win[%d]); inside = inside && (a < (unsigned)p.win[%d]); wb = wb * p.win[%d] + (int)a; }"
-                          % (v.c, 2 + 2 * a, 3 + 2 * a, 3 + 2 * a))
+            ev.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[okw ? (%s) : 0];" % (hp.win_table_off, wr))
+            ev.append("    const unsigned wa = (unsigned)((%s) - (int)(we.y >> 16));" % wc)
+            ev.append("    const bool inside = okw && wa < (we.y & 0xffffu);")
             ev.append("    if (inside) {")
-            ev.append("        double* const wrow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)wb * %d;" % (hp.win_off, nf))
-            ev.extend(_emit_row_adds(hp, options, "wrow", "reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb" % (hp.win_off, nf * 8), "        "))
+            ev.append("        const int wb = (int)(we.x + wa);")
+            decl, sstride = _rowptr(hp, options, "wrow", hp.win_off, "wb", "p.win[1]")
+            ev.append("        " + decl)
+            ev.extend(_emit_row_adds(hp, options, "wrow", "reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb" % (hp.win_off, nf * hp.slot_bytes),
+                                     "        ", sstride, grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol)))
             ev.append("    }")
             conds = ["okw", "!inside"]
         if pair:
@@ -868,10 +1003,12 @@ def generate(spec, coltypes, options=None):
             ev.append("    {")
             ev.append("        const bool okrow = %s;" % " && ".join(conds))
             ev.append("        const int bin = okrow ? (%s) : 0;" % idx)
+            # (whole warps usually have nothing outside a well-placed window: skip the exchange then)
+            vote = "if (__any_sync(0xffffffffu, okrow)) " if hp.strategy == "window" else ""
             if hp.groups:
-                ev.append("        hb_red_pair(p.hist[%d], okrow ? ((hb_i64)slot * %d + bin) : (hb_i64)-1, %s, %s);" % (hp.hid, hp.nbins, v0, v1))
+                ev.append("        %shb_red_pair(p.hist[%d], okrow ? ((hb_i64)slot * %d + bin) : (hb_i64)-1, %s, %s);" % (vote, hp.hid, hp.nbins, v0, v1))
             else:
-                ev.append("        hb_red_pair(p.hist[%d], okrow ? bin : -1, %s, %s);" % (hp.hid, v0, v1))
+                ev.append("        %shb_red_pair(p.hist[%d], okrow ? bin : -1, %s, %s);" % (vote, hp.hid, v0, v1))
             ev.append("    }")
             ev.append("}")
             continue
@@ -891,8 +1028,12 @@ def generate(spec, coltypes, options=None):
             else:
                 ev.append("        const int srowi = bin;")
             if nslots:
-                ev.append("%sdouble* const srow = reinterpret_cast<double*>(hb_smem + %d) + (hb_i64)srowi * %d;" % (indent, hp.smem_f64_off, nslots))
-            ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + srowi" % hp.smem_u32_off, indent))
+                decl, sstride = _rowptr(hp, options, "srow", hp.smem_f64_off, "srowi", hp.nrows)
+                ev.append(indent + decl)
+            else:
+                sstride = "1"
+            ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + srowi" % hp.smem_u32_off, indent, sstride,
+                                     grow="(p.hist[%d] + (hb_i64)srowi * %d)" % (hp.hid, hp.ncol)))
             if hp.groups:
                 ev.append("        } else {")
                 ev.append("            double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
@@ -925,34 +1066,47 @@ def generate(spec, coltypes, options=None):
         merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nrows)
         merge.append("    double* const row = p.hist[%d] + (hb_i64)b * %d;" % (hp.hid, hp.ncol))
         nslots = len(hp.row_layout(options)[0])
-        merge.append("    const double* const srow = reinterpret_cast<const double*>(hb_smem + %d) + (hb_i64)b * %d;" % (hp.smem_f64_off, nslots))
-        merge.extend(_emit_row_merge(hp, options, "srow", "reinterpret_cast<const hb_u32*>(hb_smem + %d)[b]" % hp.smem_u32_off, "    "))
+        decl, sstride = _rowptr(hp, options, "srow", hp.smem_f64_off, "b", hp.nrows, const=True)
+        merge.append("    " + decl)
+        merge.extend(_emit_row_merge(hp, options, "srow", "reinterpret_cast<const hb_u32*>(hb_smem + %d)[b]" % hp.smem_u32_off, "    ", sstride))
         merge.append("}")
 
     if window is not None:
         hp = window
         nf = len(hp.row_layout(options)[0])
-        merge.append("// merge the hot window of hist %d" % hp.hid)
-        merge.append("for (int wb = threadIdx.x; wb < p.win[1]; wb += HB_THREADS) {")
-        merge.append("    int rest = wb; hb_i64 bin = 0;")
-        stride = 1
-        for a in range(len(hp.index) - 1, -1, -1):
-            merge.append("    bin += (hb_i64)(p.win[%d] + rest %% p.win[%d]) * %d; rest /= p.win[%d];" % (2 + 2 * a, 3 + 2 * a, stride, 3 + 2 * a))
-            stride *= hp.index[a][1]
-        merge.append("    double* const row = p.hist[%d] + bin * %d;" % (hp.hid, hp.ncol))
-        merge.append("    const double* const wrow = reinterpret_cast<const double*>(hb_smem + %d) + (hb_i64)wb * %d;" % (hp.win_off, nf))
-        merge.extend(_emit_row_merge(hp, options, "wrow", "reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb]" % (hp.win_off, nf * 8), "    "))
+        merge.append("// merge the hot window of hist %d: one warp per table row, lanes along the row's interval" % hp.hid)
+        merge.append("for (int wr = threadIdx.x >> 5; wr < %d; wr += HB_THREADS / 32) {" % hp.win_rows)
+        merge.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[wr];" % hp.win_table_off)
+        merge.append("    for (unsigned wa = threadIdx.x & 31u; wa < (we.y & 0xffffu); wa += 32u) {")
+        merge.append("        const int wb = (int)(we.x + wa);")
+        merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
+        decl, sstride = _rowptr(hp, options, "wrow", hp.win_off, "wb", "p.win[1]", const=True)
+        merge.append("        " + decl)
+        merge.extend(_emit_row_merge(hp, options, "wrow", "reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb]" % (hp.win_off, nf * hp.slot_bytes), "        ", sstride))
+        merge.append("    }")
         merge.append("}")
 
     k = Kernel()
-    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, has_window=window is not None)
+    winfo = None
+    naux = len(group_aux)
+    if window is not None:
+        bpb = window.row_bytes(options)
+        winfo = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "rows": window.win_rows, "trail": window.win_trail,
+                 "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"], "aux": naux, "table_off": window.win_table_off}
+        naux += 1
+    k.fx_terms = [(hp.fx_index[t], hp.hid, t) for hp in plans if hp.fx for t in hp.f64_terms]
+    k.nfx = (1 + max(i for i, hid, t in k.fx_terms)) if k.fx_terms else 0
+    if k.fx_terms:
+        k.fx_aux = naux                 # aux slot of the device counter [terms that missed their fixed-point window]
+        naux += 1
+        merge.append("if (threadIdx.x == 0 && *HB_FXMISS != 0u && p.aux[%d] != nullptr)" % k.fx_aux)
+        merge.append("    atomicAdd(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), (hb_u64)*HB_FXMISS);" % k.fx_aux)
+    k.naux = naux
+    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo)
     k.cols = list(prog.cols)
     k.plans = plans
     k.smem_bytes = smem_cap
-    if window is not None:
-        bpb = window.row_bytes(options)
-        k.window = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "totbins": [t for v, t in window.index],
-                    "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"]}
+    k.window = winfo
     k.threads = threads
     k.tile = threads * VEC
     k.inexact = set(prog.inexact)
@@ -971,6 +1125,41 @@ def group_goals(spec):
                 seen.add(key)
                 out.append((key, a["goal"]))
     return out
+
+
+def generate_range(spec, coltypes, options=None):
+    """The pilot kernel of the fixed-point terms: evaluates every such term and records the largest binary
+    exponent it takes (finite values only) in aux[0][i] -- fillable._fx_scales turns that into the scale of
+    term i.  Accumulates nothing."""
+    options = options or {}
+    prog = Program(spec, coltypes)
+    plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
+    choose_strategies(plans, options)
+    terms = [(hp, t) for hp in plans if hp.fx for t in hp.f64_terms]
+    if not terms:
+        return None
+    ev = list(prog.body)
+    nfx = 1 + max(hp.fx_index[t] for hp, t in terms)
+    for hp, t in terms:
+        i = hp.fx_index[t]
+        ev.append("{ const hb_u32 e = ((hb_u32)__double2hiint(%s) >> 20) & 0x7ffu;" % hp.terms[t])
+        ev.append("  const hb_u32 m = __reduce_max_sync(0xffffffffu, (live && e != 0x7ffu) ? e : 0u);")
+        ev.append("  if ((threadIdx.x & 31u) == 0u && m > reinterpret_cast<hb_u32*>(hb_smem)[%d]) atomicMax(reinterpret_cast<hb_u32*>(hb_smem) + %d, m); }" % (i, i))
+    merge = ["for (int i = threadIdx.x; i < %d; i += HB_THREADS) {" % nfx,
+             "    const hb_u32 m = reinterpret_cast<const hb_u32*>(hb_smem)[i];",
+             "    if (m != 0u) atomicMax(reinterpret_cast<hb_u32*>(const_cast<void*>(p.aux[0])) + i, m);",
+             "}"]
+    threads = THREADS
+    k = Kernel()
+    k.smem_bytes = (nfx * 4 + 15) // 16 * 16
+    k.nfx = nfx
+    k.source = _emit_kernel(prog, ev, k.smem_bytes, merge, threads, 2)
+    k.cols = list(prog.cols)
+    k.threads = threads
+    k.tile = threads * VEC
+    k.fx_terms = [(hp.fx_index[t], hp.hid, t) for hp, t in terms]
+    k.key = hashlib.sha256(k.source.encode()).hexdigest()
+    return k
 
 
 def generate_keys(spec, coltypes, options=None):

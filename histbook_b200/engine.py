@@ -329,6 +329,19 @@ class DeviceBuffer(object):
     def ptr(self):
         return self._p.value
 
+    def read(self, dtype):
+        """The buffer's current device contents as a numpy array of ``dtype``."""
+        out = numpy.empty(self.nbytes // numpy.dtype(dtype).itemsize, dtype=dtype)
+        if out.nbytes:
+            check(lib().hb_memcpy_d2h(out.ctypes.data_as(ctypes.c_void_p), self._p, out.nbytes))
+        return out
+
+    def write(self, array):
+        array = numpy.ascontiguousarray(array)
+        assert array.nbytes <= max(self.nbytes, 8)
+        if array.nbytes:
+            check(lib().hb_memcpy_h2d(self._p, array.ctypes.data_as(ctypes.c_void_p), array.nbytes))
+
     def __del__(self):
         p, self._p = getattr(self, "_p", None), None
         if p and _lib is not None:

@@ -33,9 +33,13 @@ class Plan(object):
         self.spec = hbspec.book_spec(hists) if spec is None else spec
         self.nhists = len(self.spec["hists"])
         self.fields = hbspec.spec_fields(self.spec)
-        self.kernels = {}           # dtype signature -> (fill Kernel, Program, keys Kernel, keys Program)
+        self.kernels = {}           # dtype signature -> (fill Kernel, Program, keys Kernel, keys Program, range Kernel, range Program)
         self.generation = Plan.generation
         self.keysets = None
+        self.fx_scales = {}         # dtype signature -> fixed-point scale per term (from the pilot), see _fx_scales
+        self.fx_stat = None         # device counter: terms that missed their fixed-point window (all fills so far)
+        self.fx_seen = 0            # ... its value when last looked at
+        self.fx_last = None         # (signature, events) of the last fill that used fixed point
 
     def kernel_for(self, cols):
         if self.generation != Plan.generation:
@@ -50,72 +54,110 @@ class Plan(object):
             kprog = None
             if keys is not None:
                 kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, 0)
-            self.kernels[sig] = (kern, prog, keys, kprog)
-        return self.kernels[sig]
+            rng = rprog = None
+            if kern.fx_terms:
+                rng = codegen.generate_range(self.spec, coltypes, _options)
+                rprog = engine.Program(engine.compile_source(rng.source), rng.name, rng.threads, rng.smem_bytes)
+            self.kernels[sig] = (kern, prog, keys, kprog, rng, rprog)
+        return sig, self.kernels[sig]
 
 
 PILOT_EVENTS = 1 << 20          # events filled through the global path before the hot window is placed
+FX_MISS_REPILOT = 0.01          # re-run the fixed-point pilot when more than this fraction of a fill's events missed
+
+
+def _fx_scales(plan, sig, kern, rng, rprog, cols, length):
+    """Scale (binary exponent of the least significant bit) of every fixed-point term of ``kern``.
+
+    A pilot kernel takes the largest binary exponent each term reaches over the first PILOT_EVENTS events; the
+    128-bit field is then placed so that values up to 4x that maximum fit (hb_template.cuh: mantissa shift
+    0..50, i.e. everything within 49 binades below the pilot's maximum is added exactly, the rest goes to the
+    global histogram as float64 REDs -- correct either way, the pilot only decides which path is the fast one).
+    Cached per plan and dtype signature; dropped again when a fill reports too many misses."""
+    if plan.fx_stat is None:
+        plan.fx_stat = engine.DeviceBuffer(numpy.zeros(2, dtype=numpy.uint64))
+        plan.fx_seen = 0
+    elif plan.fx_last is not None:
+        last_sig, last_events = plan.fx_last
+        total = int(plan.fx_stat.read(numpy.uint64)[0])
+        missed, plan.fx_seen = total - plan.fx_seen, total
+        if last_events > 0 and missed > FX_MISS_REPILOT * last_events:
+            plan.fx_scales.pop(last_sig, None)
+    if sig not in plan.fx_scales:
+        maxima = engine.DeviceBuffer(numpy.zeros(max(rng.nfx, 2), dtype=numpy.uint32))
+        m = min(length, PILOT_EVENTS)
+        if m > 0:
+            engine.fill(rprog, _abi_columns(rng, cols), m, [], aux=[maxima.ptr])
+        biased = maxima.read(numpy.uint32)[:rng.nfx].astype(numpy.int64)
+        biased[biased == 0] = 1023                       # nothing seen (or only zeros): assume values near 1
+        scales = [int(b) - 1123 for b in biased]         # shift of a value with exponent e: e - max + 48
+        while len(scales) < kern.nfx:
+            scales.append(-100)
+        plan.fx_scales[sig] = scales
+    plan.fx_last = (sig, length)
+    return plan.fx_scales[sig]
+
 WINDOW_MIN_COVERAGE = 0.25      # below this (estimated) fraction of events a window is not worth its merge
 
 
-def choose_window(marginals, wmax):
-    """Place the hot window: per axis a contiguous bin range [lo, lo+n) such that prod(n) <= wmax and the
-    (independence-estimated) fraction of events inside is as large as a greedy trim can make it.
+def choose_ragged(density, wmax):
+    """Place the hot window: one contiguous interval [first, first + length) per row of ``density`` (rows =
+    flattened leading axes, columns = flattened trailing axes; values = |sum of weights| the histogram holds so
+    far) such that the intervals together have at most ``wmax`` bins and hold as much of the density as a
+    threshold rule can give: every row keeps the span between its first and last bin at or above a common
+    density threshold, the threshold being the lowest one that fits (binary search).
 
-    marginals: per-axis arrays of |sum of weights| per bin (from the histogram filled so far).
-    Returns ([(lo, n), ...], estimated coverage)."""
-    los, his = [], []
-    for m in marginals:
-        nz = numpy.flatnonzero(m)
-        if len(nz) == 0:
-            return [(0, 0)] * len(marginals), 0.0
-        los.append(int(nz[0]))
-        his.append(int(nz[-1]) + 1)
-    totals = [float(m.sum()) for m in marginals]
+    Returns (first[rows], length[rows], coverage)."""
+    density = numpy.asarray(density, dtype=numpy.float64)
+    rows, trail = density.shape
+    first = numpy.zeros(rows, dtype=numpy.int64)
+    length = numpy.zeros(rows, dtype=numpy.int64)
+    total = float(density.sum())
+    if total <= 0.0 or not numpy.isfinite(total) or wmax < 1:
+        return first, length, 0.0
+    levels = numpy.unique(density[density > 0.0])
 
-    def volume():
-        v = 1
-        for lo, hi in zip(los, his):
-            v *= hi - lo
-        return v
-    vol = volume()
-    while vol > wmax:
-        best = None
-        for k, m in enumerate(marginals):
-            nk = his[k] - los[k]
-            if nk <= 1:
-                continue
-            gain = vol // nk                       # bins saved by dropping one slice of axis k
-            for end, idx in (("lo", los[k]), ("hi", his[k] - 1)):
-                score = (m[idx] / totals[k]) / gain
-                if best is None or score < best[0]:
-                    best = (score, k, end)
-        if best is None:
-            return [(0, 0)] * len(marginals), 0.0
-        _, k, end = best
-        if end == "lo":
-            los[k] += 1
-        else:
-            his[k] -= 1
-        vol = volume()
-    coverage = 1.0
-    for k, m in enumerate(marginals):
-        coverage *= float(m[los[k]:his[k]].sum()) / totals[k]
-    return [(lo, hi - lo) for lo, hi in zip(los, his)], coverage
+    def spans(t):
+        mask = density >= t
+        has = mask.any(axis=1)
+        lo = numpy.where(has, mask.argmax(axis=1), 0)
+        hi = numpy.where(has, trail - mask[:, ::-1].argmax(axis=1), 0)
+        return lo, hi
+    a, b = 0, len(levels) - 1               # lowest threshold index whose spans fit
+    lo, hi = spans(levels[b])
+    if int((hi - lo).sum()) > wmax:
+        # even the single densest bin per row does not fit: keep the densest bins of the densest rows only
+        order = numpy.argsort(-density.max(axis=1))[:wmax]
+        first[order] = density[order].argmax(axis=1)
+        length[order] = 1
+    else:
+        while a < b:
+            mid = (a + b) // 2
+            lo, hi = spans(levels[mid])
+            if int((hi - lo).sum()) <= wmax:
+                b = mid
+            else:
+                a = mid + 1
+        lo, hi = spans(levels[b])
+        first, length = lo.astype(numpy.int64), (hi - lo).astype(numpy.int64)
+    cols = numpy.arange(trail)[None, :]
+    inside = (cols >= first[:, None]) & (cols < (first + length)[:, None])
+    return first, length, float(density[inside].sum()) / total
 
 
-def window_params(kern, window):
-    """p.win of hb_template.cuh: [u32 words to zero, bins in the window, lo_0, n_0, lo_1, n_1, ...]."""
-    info = kern.window
-    if window is None:
-        return [0, 0] + [0, 0] * len(info["totbins"])
-    w = 1
-    for lo, n in window:
-        w *= n
-    out = [(w * info["bpb"] + 3) // 4, w]
-    for lo, n in window:
-        out += [lo, n]
-    return out
+def window_table(first, length):
+    """The kernel's row table (hb_template / codegen `we`): per row one uint64 = offset of the row's interval in
+    the window (low 32 bits) | first in-row index << 48 | length << 32.  Returns (table, bins in the window)."""
+    first = numpy.asarray(first, dtype=numpy.uint64)
+    length = numpy.asarray(length, dtype=numpy.uint64)
+    offset = numpy.concatenate([[0], numpy.cumsum(length)[:-1]]).astype(numpy.uint64)
+    table = offset | (length << numpy.uint64(32)) | (first << numpy.uint64(48))
+    return table, int(length.sum())
+
+
+def window_params(kern, bins):
+    """p.win of hb_template.cuh: [u32 words of window to zero, bins in the window]."""
+    return [(bins * kern.window["bpb"] + 3) // 4, bins]
 
 
 def _abi_columns(kern, cols):
@@ -133,7 +175,7 @@ def fill_hists(plan, hists, arrays, timed=False):
     """One pass over ``arrays`` filling every histogram in ``hists`` (deduplicated, in plan order)."""
     with _lock:
         cols, length = columns.bind_all(plan.fields, arrays)
-        kern, prog, keys, kprog = plan.kernel_for(cols)
+        sig, (kern, prog, keys, kprog, rng, rprog) = plan.kernel_for(cols)
 
         # group axes: which keys does this fill hold?  (numpy.unique in calc/__init__.py:150,178,182)
         discovered = {}
@@ -177,31 +219,49 @@ def fill_hists(plan, hists, arrays, timed=False):
         if length > 0:
             abi = _abi_columns(kern, cols)
             arenas = [st.arena for st in stores]
+            aux = list(aux) + [0] * (kern.naux - len(aux))
+            fx = []
+            if kern.fx_terms:
+                fx = _fx_scales(plan, sig, kern, rng, rprog, cols, length)
+                aux[kern.fx_aux] = plan.fx_stat.ptr
             if kern.window is None:
-                stats = engine.fill(prog, abi, length, arenas, aux=aux, timed=timed)
+                stats = engine.fill(prog, abi, length, arenas, aux=aux, win=[0, 0] + fx, timed=timed)
             else:
                 # hot-window privatisation: place the window from what the histogram already holds; a histogram
                 # that is still empty first gets a pilot slice of this fill through the global path.
-                wst = stores[kern.window["hid"]]
+                info = kern.window
+                wst = stores[info["hid"]]
                 done = 0
                 extra = 0.0
-                if wst.window is None:
+                aux[info["aux"]] = 0                      # the row table (null = no window)
+                if wst.window is None or wst.window_key != (info["rows"], info["trail"], info["wmax"]):
                     if not wst.nonempty:
                         done = min(length, max(kern.tile, PILOT_EVENTS // kern.tile * kern.tile))
-                        pilot = engine.fill(prog, abi, done, arenas, aux=aux, win=window_params(kern, None), timed=timed)
+                        pilot = engine.fill(prog, abi, done, arenas, aux=aux, win=[0, 0] + fx, timed=timed)
                         extra = pilot["ms_kernel"]
-                    marg = wst.arena.marginals(kern.window["totbins"], kern.window["ncol"], kern.window["col"])
-                    window, coverage = choose_window(marg, kern.window["wmax"])
-                    wst.window = window if coverage >= WINDOW_MIN_COVERAGE else False
+                    content = wst.arena.read(0, info["rows"] * info["trail"] * info["ncol"])
+                    density = numpy.abs(content.reshape(info["rows"], info["trail"], info["ncol"])[:, :, info["col"]])
+                    density[~numpy.isfinite(density)] = 0.0
+                    first, nlen, coverage = choose_ragged(density, info["wmax"])
+                    wst.window_key = (info["rows"], info["trail"], info["wmax"])
                     wst.window_coverage = coverage
-                win = window_params(kern, wst.window or None)
+                    if coverage >= WINDOW_MIN_COVERAGE:
+                        table, bins = window_table(first, nlen)
+                        wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum())}
+                    else:
+                        wst.window = False
+                if wst.window:
+                    aux[info["aux"]] = wst.window["table"].ptr
+                    win = window_params(kern, wst.window["bins"]) + fx
+                else:
+                    win = [0, 0] + fx
                 stats = {"events": length, "launches": 1 if done else 0, "ms_kernel": extra}
                 if length > done:
                     main = engine.fill(prog, abi, length - done, arenas, aux=aux, win=win, timed=timed, offset=done)
                     main["launches"] += stats["launches"]
                     main["ms_kernel"] += extra
                     stats = main
-                stats["window"] = list(wst.window) if wst.window else None
+                stats["window"] = {"bins": wst.window["bins"], "rows": wst.window["rows"]} if wst.window else None
                 stats["window_coverage"] = wst.window_coverage
         for st in stores:
             st.mark_filled()

@@ -87,7 +87,8 @@ class Store(object):
         self.table = None                             # engine.DeviceBuffer with the lookup table of the last fill
         self.table_version = None
         # hot-window privatisation (fillable.choose_window): None = not placed yet, False = not worth it
-        self.window = None
+        self.window = None            # {"table": DeviceBuffer, "bins", "rows"}
+        self.window_key = None        # (rows, trail, wmax) of the kernel the window was placed for
         self.window_coverage = None
         self.nonempty = False                         # the device copy holds at least one fill / uploaded content
 

@@ -42,7 +42,7 @@ extern "C" {
 #define HB_MAX_COLS 32
 #define HB_MAX_HISTS 256
 #define HB_MAX_AUX 64
-#define HB_MAX_WIN 32
+#define HB_MAX_WIN 128     /* run-time integer parameters of a launch (window geometry, fixed-point scales) */
 
 /* column dtypes (numpy names) */
 enum hb_dtype {

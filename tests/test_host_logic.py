@@ -131,24 +131,36 @@ def test_group_table_layout_roundtrip():
 
 
 def test_hot_window_placement():
-    from histbook_b200.fillable import choose_window, window_params
+    from histbook_b200.fillable import choose_ragged, window_table, window_params
     rs = numpy.random.RandomState(3)
     x, y = rs.normal(0, 1, 200000), rs.normal(0, 1, 200000)
     i0 = numpy.clip(numpy.floor((x + y + 5) * 20).astype(int) + 1, 0, 201)
     i1 = numpy.clip(numpy.floor(numpy.sqrt(x * x + y * y) * 40).astype(int) + 1, 0, 201)
     h = numpy.zeros((203, 203))
     numpy.add.at(h, (i0, i1), 1)
-    win, cov = choose_window([h.sum(1), h.sum(0)], 12800)
-    (l0, n0), (l1, n1) = win
-    assert n0 * n1 <= 12800 and cov > 0.9
-    assert h[l0:l0 + n0, l1:l1 + n1].sum() / h.sum() > 0.9
+    first, length, cov = choose_ragged(h, 6400)
+    assert length.sum() <= 6400 and cov > 0.9            # a rectangle of 6400 bins holds ~0.80 of these events
+    inside = sum(h[r, first[r]:first[r] + length[r]].sum() for r in range(203))
+    assert abs(inside / h.sum() - cov) < 1e-12
+    # the table the kernel reads: low word = offset of the row's interval, high word = first << 16 | length
+    table, bins = window_table(first, length)
+    assert bins == length.sum() and table.dtype == numpy.uint64
+    assert numpy.array_equal(table & numpy.uint64(0xffffffff), numpy.concatenate([[0], numpy.cumsum(length)[:-1]]).astype(numpy.uint64))
+    assert numpy.array_equal((table >> numpy.uint64(32)) & numpy.uint64(0xffff), length.astype(numpy.uint64))
+    assert numpy.array_equal(table >> numpy.uint64(48), first.astype(numpy.uint64))
     # nothing filled yet -> no window
-    assert choose_window([numpy.zeros(5), numpy.zeros(7)], 100) == ([(0, 0), (0, 0)], 0.0)
-    # everything fits -> whole populated range
-    win, cov = choose_window([numpy.array([0, 1.0, 2, 0]), numpy.array([3.0, 0, 1])], 100)
-    assert win == [(1, 2), (0, 3)] and cov == 1.0
+    first, length, cov = choose_ragged(numpy.zeros((5, 7)), 100)
+    assert length.sum() == 0 and cov == 0.0
+    # everything fits -> the populated span of every row
+    first, length, cov = choose_ragged(numpy.array([[0, 1.0, 2, 0], [3.0, 0, 1, 0], [0, 0, 0, 0]]), 100)
+    assert first.tolist() == [1, 0, 0] and length.tolist() == [2, 3, 0] and cov == 1.0
+    # budget smaller than the number of populated rows -> single bins of the densest rows
+    first, length, cov = choose_ragged(numpy.array([[0, 1.0, 2, 0], [3.0, 0, 1, 0], [0, 0, 0, 9.0]]), 2)
+    assert length.tolist() == [0, 1, 1] and first.tolist()[1:] == [0, 3]
+    # a 1-d histogram is one row
+    first, length, cov = choose_ragged(numpy.array([[0, 1.0, 5, 7, 2, 0.5]]), 3)
+    assert first.tolist() == [2] and length.tolist() == [3]
 
     class K(object):
-        window = {"bpb": 16, "totbins": [203, 203]}
-    assert window_params(K, [(41, 120), (4, 106)]) == [120 * 106 * 4, 120 * 106, 41, 120, 4, 106]
-    assert window_params(K, None) == [0, 0, 0, 0, 0, 0]
+        window = {"bpb": 16}
+    assert window_params(K, 1000) == [4000, 1000]

@@ -49,6 +49,54 @@ __device__ __forceinline__ int bin1d(double v, double low, double scale, int nb)
     return i;
 }
 
+// Exact fixed-point add of a double into an L-limb (32 L bits, two's complement, SoA limbs `stride` words apart)
+// accumulator whose least significant bit weighs 2^s.  Returns false (nothing added) when v does not fit exactly.
+template <int L>
+__device__ __forceinline__ bool fx_add(u32* limb0, int stride, double v, int s) {
+    const u32 hi = (u32)__double2hiint(v), lo = (u32)__double2loint(v);
+    const int e = (int)((hi >> 20) & 0x7ffu);
+    const int sh = e - 1075 - s;
+    if (e == 0) return (hi << 1 | lo) == 0u;                       // +-0 adds nothing; subnormals do not fit
+    if (sh < 0 || sh > 32 * L - 25 - 53 || e == 0x7ff) return false;
+    const bool neg = (hi >> 31) != 0u;
+    const u32 mh = (hi & 0xfffffu) | 0x100000u;
+    const int w = (L > 3) ? (sh >> 5) : 0, b = sh & 31;
+    // (mh:lo) << b as three 32-bit pieces
+    const u32 q0 = lo << b;
+    const u32 q1 = __funnelshift_l(lo, mh, b);
+    const u32 q2 = __funnelshift_l(mh, 0u, b);
+    u32* p = limb0 + w * stride;
+    u32 c = 0u;
+    if (q0) { const u32 x = neg ? 0u - q0 : q0; const u32 o = atomicAdd(p, x); const u32 n = o + x; c = neg ? (n > o) : (n < o); }
+    const u64 a21 = (((u64)q2 << 32) | q1) + c;
+    const u32 a1 = (u32)a21;
+    u32 a2 = (u32)(a21 >> 32);
+    if (a1) { const u32 x = neg ? 0u - a1 : a1; const u32 o = atomicAdd(p + stride, x); const u32 n = o + x; a2 += (neg ? (n > o) : (n < o)) ? 1u : 0u; }
+    if (L > 3) {
+        if (a2) {
+            const u32 x = neg ? 0u - a2 : a2;
+            if (w == 0) { const u32 o = atomicAdd(p + 2 * stride, x); const u32 n = o + x; if (neg ? (n > o) : (n < o)) atomicAdd(p + 3 * stride, neg ? 0xffffffffu : 1u); }
+            else atomicAdd(p + 2 * stride, x);
+        }
+    } else {
+        if (a2) atomicAdd(p + 2 * stride, neg ? 0u - a2 : a2);
+    }
+    return true;
+}
+// signed L-limb fixed point (lsb 2^s) -> double, rounded once
+template <int L>
+__device__ __forceinline__ double fx_read(const u32* limb0, int stride, int s) {
+    u32 l[4] = {0u, 0u, 0u, 0u};
+    for (int j = 0; j < L; ++j) l[j] = limb0[j * stride];
+    const bool neg = (l[L - 1] >> 31) != 0u;
+    if (neg) { u32 c = 1u; for (int j = 0; j < L; ++j) { const u32 t = ~l[j] + c; c = (c && t == 0u) ? 1u : 0u; l[j] = t; } }
+    // magnitude = sum l[j] 2^(32 j): exact in two doubles when done high to low with error-free pieces
+    double acc = 0.0;
+    for (int j = L - 1; j >= 0; --j) acc = acc * 4294967296.0 + (double)l[j];   // NOTE: rounds per step (prototype only)
+    acc = ldexp(acc, s);
+    return neg ? -acc : acc;
+}
+
 enum Mode {
     READ_ONLY = 0,        // sum of x: the streaming ceiling
     C1_SMEM_U32,          // 103 bins, shared u32 atomicAdd per event
@@ -62,12 +110,14 @@ enum Mode {
     C3_GLOBAL_RED,        // same terms as global REDs into an 80 KB L2-resident table
     C5_GLOBAL_RED,        // 203^3 x 2 f64 (134 MB), two REDs per event
     C5_INDEX_ONLY,
+    C3_SMEM_FX3,          // c3 terms in 96-bit fixed point: three native u32 shared atomics per term (+ f64 RED fallback)
+    C3_SMEM_FX4,          // same, 128-bit field with a sliding 3-limb window
     NMODES
 };
 static const char* kNames[NMODES] = {"read_only", "c1_smem_u32", "c1_smem_u32_match", "c1_tpriv_u8", "c1_global_red",
                                      "c2_global_red", "c2_global_red_pair", "c2_index_only", "c3_smem_f64", "c3_global_red",
-                                     "c5_global_red", "c5_index_only"};
-static const int kBytesPerEvent[NMODES] = {8, 8, 8, 8, 8, 24, 24, 24, 16, 16, 32, 32};
+                                     "c5_global_red", "c5_index_only", "c3_smem_fx3", "c3_smem_fx4"};
+static const int kBytesPerEvent[NMODES] = {8, 8, 8, 8, 8, 24, 24, 24, 16, 16, 32, 32, 16, 16};
 
 #define THREADS 256
 #define TILE (THREADS * 4)
@@ -83,6 +133,8 @@ __global__ void __launch_bounds__(THREADS, 2) k(const double* __restrict__ x, co
     if (MODE == C1_SMEM_U32 || MODE == C1_SMEM_U32_MATCH) zero_words = 104;
     if (MODE == C1_TPRIV_U8) zero_words = 26 * THREADS;
     if (MODE == C3_SMEM_F64) zero_words = NB3 * 3 * 2 + NB3;
+    if (MODE == C3_SMEM_FX3) zero_words = NB3 * 3 * 3 + NB3;
+    if (MODE == C3_SMEM_FX4) zero_words = NB3 * 3 * 4 + NB3;
     for (int i = threadIdx.x; i < zero_words; i += THREADS) s32[i] = 0u;
     __syncthreads();
     double acc = 0.0;
@@ -141,6 +193,19 @@ __global__ void __launch_bounds__(THREADS, 2) k(const double* __restrict__ x, co
                     red_f64(row, y1); red_f64(row + 1, y2); red_f64(row + 2, y2); red_f64(row + 3, y4); red_f64(row + 4, 1.0);
                 }
             }
+            if (MODE == C3_SMEM_FX3 || MODE == C3_SMEM_FX4) {
+                const int L = (MODE == C3_SMEM_FX3) ? 3 : 4;
+                int b0 = bin1d(vx[e], -5.0, 100.0, 1000);
+                int b = b0 * 2 + (0.0 < vx[e] ? 1 : 0);
+                double y1 = vy[e], y2 = y1 * y1, y4 = y2 * y2;
+                // scales: |y| < 2^3, y^2 < 2^6, y^4 < 2^12 plus two guard bits
+                const int top = 32 * L - 25;
+                double* row = out + (i64)b * 5;
+                if (!fx_add<(MODE == C3_SMEM_FX3) ? 3 : 4>(s32 + b, NB3, y1, 3 + 2 - top)) red_f64(row, y1);
+                if (!fx_add<(MODE == C3_SMEM_FX3) ? 3 : 4>(s32 + L * NB3 + b, NB3, y2, 6 + 2 - top)) { red_f64(row + 1, y2); red_f64(row + 2, y2); }
+                if (!fx_add<(MODE == C3_SMEM_FX3) ? 3 : 4>(s32 + 2 * L * NB3 + b, NB3, y4, 12 + 2 - top)) red_f64(row + 3, y4);
+                atomicAdd(&s32[3 * L * NB3 + b], 1u);
+            }
             if (MODE == C5_GLOBAL_RED || MODE == C5_INDEX_ONLY) {
                 int b0 = bin1d(vx[e], -5.0, 20.0, 200), b1 = bin1d(vy[e], -5.0, 20.0, 200), b2 = bin1d(vz[e], -5.0, 20.0, 200);
                 i64 idx = (((i64)b0 * 203 + b1) * 203 + b2) * 2;
@@ -174,6 +239,21 @@ __global__ void __launch_bounds__(THREADS, 2) k(const double* __restrict__ x, co
             for (int q = 0; q < 4; ++q) { u32 c = (v >> (8 * q)) & 0xffu; if (c) red_f64(out + wd * 4 + q, (double)c); }
         }
     }
+    if (MODE == C3_SMEM_FX3 || MODE == C3_SMEM_FX4) {
+        const int L = (MODE == C3_SMEM_FX3) ? 3 : 4;
+        const int top = 32 * L - 25;
+        for (int b = threadIdx.x; b < NB3; b += THREADS) {
+            double* row = out + (i64)b * 5;
+            double a = fx_read<(MODE == C3_SMEM_FX3) ? 3 : 4>(s32 + b, NB3, 3 + 2 - top);
+            double c = fx_read<(MODE == C3_SMEM_FX3) ? 3 : 4>(s32 + L * NB3 + b, NB3, 6 + 2 - top);
+            double d = fx_read<(MODE == C3_SMEM_FX3) ? 3 : 4>(s32 + 2 * L * NB3 + b, NB3, 12 + 2 - top);
+            u32 cnt = s32[3 * L * NB3 + b];
+            if (a != 0.0) red_f64(row, a);
+            if (c != 0.0) { red_f64(row + 1, c); red_f64(row + 2, c); }
+            if (d != 0.0) red_f64(row + 3, d);
+            if (cnt) red_f64(row + 4, (double)cnt);
+        }
+    }
     if (MODE == C3_SMEM_F64) {
         for (int b = threadIdx.x; b < NB3; b += THREADS) {
             double* row = out + (i64)b * 5;
@@ -192,6 +272,8 @@ static void run(const double* x, const double* y, const double* z, const double*
     if (MODE == C1_SMEM_U32 || MODE == C1_SMEM_U32_MATCH) smem = 104 * 4;
     if (MODE == C1_TPRIV_U8) smem = 26 * THREADS * 4;
     if (MODE == C3_SMEM_F64) smem = (size_t)(1003 * 2) * (3 * 8 + 4);
+    if (MODE == C3_SMEM_FX3) smem = (size_t)(1003 * 2) * (3 * 12 + 4);
+    if (MODE == C3_SMEM_FX4) smem = (size_t)(1003 * 2) * (3 * 16 + 4);
     CK(cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<MODE>, THREADS, smem));
@@ -246,6 +328,8 @@ int main(int argc, char** argv) {
     run<C2_GLOBAL_RED_PAIR>(x, y, z, w, n, out, out_bytes, sms);
     run<C3_SMEM_F64>(x, y, z, w, n, out, out_bytes, sms);
     run<C3_GLOBAL_RED>(x, y, z, w, n, out, out_bytes, sms);
+    run<C3_SMEM_FX3>(x, y, z, w, n, out, out_bytes, sms);
+    run<C3_SMEM_FX4>(x, y, z, w, n, out, out_bytes, sms);
     run<C5_INDEX_ONLY>(x, y, z, w, n, out, out_bytes, sms);
     run<C5_GLOBAL_RED>(x, y, z, w, n, out, out_bytes, sms);
     return 0;
