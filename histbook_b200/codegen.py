@@ -746,7 +746,7 @@ def _loadtype(dtype):
     return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
 
 
-def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None):
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False):
     """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
     over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
     takes the scalar path), shared-memory zeroing before and block merge after."""
@@ -781,29 +781,68 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
         if is_scalar:
             src.append("    const %s s%d = hb_scalar<%s>(p.scal[%d]);" % (_loadtype(dtype), slot, _loadtype(dtype), slot))
     src.append("    const hb_i64 ntiles = (p.n + HB_TILE - 1) / HB_TILE;")
-    src.append("    for (hb_i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {")
-    src.append("        const hb_i64 first = tile * HB_TILE;")
-    src.append("        if (p.vec_ok && first + HB_TILE <= p.n) {")
-    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
-        if not is_scalar:
-            src.append("            %s v%d[4]; hb_load4<%s>(p.cols[%d], first, threadIdx.x, HB_THREADS, v%d);" % (_loadtype(dtype), slot, _loadtype(dtype), slot, slot))
-    src.append("#pragma unroll")
-    src.append("            for (int k = 0; k < 4; ++k) {")
-    src.append("                hb_event(p, hb_smem, true%s);" % "".join(
-        ", " + _colarg(slot, dtype, is_scalar, "v%d[k]" % slot) for slot, (name, dtype, is_scalar) in enumerate(prog.cols)))
-    src.append("            }")
-    src.append("        } else {")
-    src.append("            // tail / unaligned input: scalar loads; every lane still calls hb_event (warp-cooperative accumulates)")
-    src.append("            for (int k = 0; k < 4; ++k) {")
-    src.append("                const hb_i64 i = first + (hb_i64)k * HB_THREADS + threadIdx.x;")
-    src.append("                const bool live = i < p.n;")
-    src.append("                const hb_i64 j = live ? i : 0;")
-    src.append("                hb_event(p, hb_smem, live%s);" % "".join(
-        ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], j)" % (_loadtype(dtype), slot))
-        for slot, (name, dtype, is_scalar) in enumerate(prog.cols)))
-    src.append("            }")
-    src.append("        }")
-    src.append("    }")
+    vcols = [(slot, dtype) for slot, (name, dtype, is_scalar) in enumerate(prog.cols) if not is_scalar]
+
+    def loads(suffix, first, indent):
+        return ["%shb_load4<%s>(p.cols[%d], %s, threadIdx.x, HB_THREADS, v%d%s);" % (indent, _loadtype(dtype), slot, first, slot, suffix)
+                for slot, dtype in vcols]
+
+    def events(suffix, indent):
+        out = ["#pragma unroll", "%sfor (int k = 0; k < 4; ++k) {" % indent]
+        out.append("%s    hb_event(p, hb_smem, true%s);" % (indent, "".join(
+            ", " + _colarg(slot, dtype, is_scalar, "v%d%s[k]" % (slot, suffix)) for slot, (name, dtype, is_scalar) in enumerate(prog.cols))))
+        out.append("%s}" % indent)
+        return out
+
+    def tail(indent):
+        out = ["%s// tail / unaligned input: scalar loads; every lane still calls hb_event (warp-cooperative accumulates)" % indent,
+               "%sfor (int k = 0; k < 4; ++k) {" % indent,
+               "%s    const hb_i64 i = first + (hb_i64)k * HB_THREADS + threadIdx.x;" % indent,
+               "%s    const bool live = i < p.n;" % indent,
+               "%s    const hb_i64 j = live ? i : 0;" % indent,
+               "%s    hb_event(p, hb_smem, live%s);" % (indent, "".join(
+                   ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], j)" % (_loadtype(dtype), slot))
+                   for slot, (name, dtype, is_scalar) in enumerate(prog.cols))),
+               "%s}" % indent]
+        return out
+
+    if prefetch and vcols:
+        # register double buffer: the next tile's loads are in flight while this tile's events are accumulated
+        for slot, dtype in vcols:
+            src.append("    %s v%d[4], v%dn[4];" % (_loadtype(dtype), slot, slot))
+        src.append("    hb_i64 tile = blockIdx.x;")
+        src.append("    bool full = p.vec_ok && tile < ntiles && tile * HB_TILE + HB_TILE <= p.n;")
+        src.append("    if (full) {")
+        src.extend(loads("", "tile * HB_TILE", "        "))
+        src.append("    }")
+        src.append("    for (; tile < ntiles; tile += gridDim.x) {")
+        src.append("        const hb_i64 first = tile * HB_TILE;")
+        src.append("        const hb_i64 next = tile + gridDim.x;")
+        src.append("        const bool nfull = p.vec_ok && next < ntiles && next * HB_TILE + HB_TILE <= p.n;")
+        src.append("        if (nfull) {")
+        src.extend(loads("n", "next * HB_TILE", "            "))
+        src.append("        }")
+        src.append("        if (full) {")
+        src.extend(events("", "            "))
+        src.append("        } else {")
+        src.extend(tail("            "))
+        src.append("        }")
+        src.append("        full = nfull;")
+        src.append("#pragma unroll")
+        src.append("        for (int k = 0; k < 4; ++k) { %s }" % " ".join("v%d[k] = v%dn[k];" % (slot, slot) for slot, dtype in vcols))
+        src.append("    }")
+    else:
+        src.append("    for (hb_i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {")
+        src.append("        const hb_i64 first = tile * HB_TILE;")
+        src.append("        if (p.vec_ok && first + HB_TILE <= p.n) {")
+        for slot, dtype in vcols:
+            src.append("            %s v%d[4];" % (_loadtype(dtype), slot))
+        src.extend(loads("", "first", "            "))
+        src.extend(events("", "            "))
+        src.append("        } else {")
+        src.extend(tail("            "))
+        src.append("        }")
+        src.append("    }")
     if merge_lines:
         src.append("    __syncthreads();")
         src.extend("    " + line for line in merge_lines)
@@ -848,11 +887,11 @@ def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None):
             out.append("%sconst double fv%d = %s;" % (indent, j, val(t)))
             out.append("%sconst HbFx ff%d = hb_fx_decode(fv%d, p.win[%d]);" % (indent, j, j, 2 + hp.fx_index[t]))
         for j, t in enumerate(slots):
-            out.append("%shb_u32 fc%d = hb_fx_stage0(%s + %d * %s, %s, ff%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j))
+            out.append("%sconst hb_u32 fc%d = hb_fx_stage0(%s + %d * %s, %s, ff%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j))
         for j, t in enumerate(slots):
-            out.append("%sfc%d = hb_fx_stage1(%s + %d * %s, %s, ff%d, fc%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j, j))
+            out.append("%sconst hb_u64 fd%d = hb_fx_stage1(%s + %d * %s, %s, ff%d, fc%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j, j))
         for j, t in enumerate(slots):
-            out.append("%shb_fx_stage2(%s + %d * %s, %s, ff%d, fc%d);" % (indent, rowptr, 4 * j, sstride, sstride, j, j))
+            out.append("%shb_fx_stage2(%s + %d * %s, %s, ff%d, fd%d);" % (indent, rowptr, 4 * j, sstride, sstride, j, j))
         for j, t in enumerate(slots):
             out.append("%sif (!ff%d.fits) {" % (indent, j))
             out.append("%s    atomicAdd(HB_FXMISS, 1u);" % indent)
@@ -886,7 +925,7 @@ def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1"):
         if t == -1:
             continue
         if hp.fx:
-            out.append("%s{ const double v = hb_fx_read(%s + %d * %s, %s, p.win[%d]);" % (indent, rowptr, 4 * j, sstride, sstride, 2 + hp.fx_index[t]))
+            out.append("%s{ const double v = hb_fx_read(%s + %d * %s, %s, p.win[%d] - 1075);" % (indent, rowptr, 4 * j, sstride, sstride, 2 + hp.fx_index[t]))
         else:
             out.append("%s{ const double v = %s[%d * %s];" % (indent, rowptr, j, sstride))
         out.append("%s  if (v != 0.0) {" % indent)
@@ -923,7 +962,12 @@ def generate(spec, coltypes, options=None):
         raise UnsupportedError("more than 32 input fields in one fill")
     # resident threads per SM stay near 1024 whatever the shared-memory footprint: the fixed-point adds are chains
     # of returning atomics and want warps to hide them
-    if smem <= 56 * 1024:
+    if smem <= 8 * 1024 and not any(hp.groups for hp in plans):
+        # tiny tables (c1: 103 bins): the block merge -- every block REDs every non-zero bin into the same few
+        # global addresses -- is what costs; 1024-thread blocks quarter the number of blocks
+        # (c1 at 1e8 events: 751 -> 818 Gev/s, profiles/r01_sweeps.txt)
+        dthreads, dblocks = 1024, 1
+    elif smem <= 56 * 1024:
         dthreads, dblocks = THREADS, 2
     elif smem <= 113 * 1024:
         dthreads, dblocks = 512, 2
@@ -1102,7 +1146,7 @@ def generate(spec, coltypes, options=None):
         merge.append("if (threadIdx.x == 0 && *HB_FXMISS != 0u && p.aux[%d] != nullptr)" % k.fx_aux)
         merge.append("    atomicAdd(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), (hb_u64)*HB_FXMISS);" % k.fx_aux)
     k.naux = naux
-    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo)
+    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)))
     k.cols = list(prog.cols)
     k.plans = plans
     k.smem_bytes = smem_cap

@@ -12,7 +12,11 @@ import numpy
 from histbook_b200 import codegen, columns, engine, spec as hbspec
 from histbook_b200.store import GroupInfo, Store
 
-_options = {}
+import json
+import os
+
+# kernel-generation options; HB_OPTIONS='{"fx": true}' presets them for a whole process (tests, tuning)
+_options = dict(json.loads(os.environ.get("HB_OPTIONS", "") or "{}"))
 _lock = threading.RLock()
 last_stats = {}
 
@@ -90,9 +94,10 @@ def _fx_scales(plan, sig, kern, rng, rprog, cols, length):
             engine.fill(rprog, _abi_columns(rng, cols), m, [], aux=[maxima.ptr])
         biased = maxima.read(numpy.uint32)[:rng.nfx].astype(numpy.int64)
         biased[biased == 0] = 1023                       # nothing seen (or only zeros): assume values near 1
-        scales = [int(b) - 1123 for b in biased]         # shift of a value with exponent e: e - max + 48
+        # what the kernel gets is k = 1075 + s: a value with biased exponent e is shifted by e - k = e - max + 48
+        scales = [int(b) - 48 for b in biased]
         while len(scales) < kern.nfx:
-            scales.append(-100)
+            scales.append(1023 - 48)
         plan.fx_scales[sig] = scales
     plan.fx_last = (sig, length)
     return plan.fx_scales[sig]
