@@ -27,6 +27,20 @@ import numpy                                        # noqa: E402
 import bench_cpu                                    # noqa: E402
 
 
+def ncu_traffic(workload, n):
+    """dram bytes per launch of the fill kernel from this round's `ncu --set full` capture (profiles/traffic.json),
+    or None when no capture exists for this workload at this size."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            entry = json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None, None
+    if not entry or int(entry["events"]) != int(n):
+        return None, None
+    return int(entry["dram_bytes_per_launch"]), entry.get("source")
+
+
 def peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -247,6 +261,7 @@ def run_gpu(args):
 
     if rank == 0:
         stats = main_stats
+        traffic, traffic_src = ncu_traffic(workload, n)
         line = {
             "metric": "fill events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -259,7 +274,10 @@ def run_gpu(args):
                                   "blocks_per_sm": stats.get("blocks_per_sm"), "hot_window": stats.get("window"),
                                   "hot_window_coverage_est": stats.get("window_coverage")}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": hbm_src},
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": n * bytes_per_event,
+                         "kernel": "hb_fill_kernel (generated per book; the only kernel in the timed region)",
+                         "peak_source": hbm_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if extras:

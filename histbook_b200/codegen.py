@@ -634,13 +634,14 @@ def plan_hist(prog, hid, h):
 
 def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
-    budget = int(options.get("smem_budget", (200 if options.get("fx", False) else 96) * 1024))
+    budget = int(options.get("smem_budget", (200 if (options.get("fx", False) or options.get("deterministic", False)) else 96) * 1024))
     forced = options.get("strategy", {})
     nfx = 0
     for hp in plans:
         # exact fixed point instead of float64 CAS loops for every privatised float64 term (16 instead of 8 bytes);
         # every such term gets a run-time scale in p.win[2 + index]
-        hp.fx = (bool(options.get("fx", False)) and not options.get("cas128", False) and len(hp.f64_terms) > 0
+        hp.fx = (bool(options.get("fx", False) or options.get("deterministic", False)) and not options.get("cas128", False)
+                 and len(hp.f64_terms) > 0
                  and nfx + len(hp.f64_terms) <= MAX_WIN - 2)
         if hp.fx:
             for t in hp.f64_terms:
@@ -701,10 +702,13 @@ def choose_strategies(plans, options):
             window.win_table_off = used
             used += (window.win_rows * 8 + 15) // 16 * 16
             window.win_off = used
+    det = bool(options.get("deterministic", False))
     for hp in plans:
-        if hp.strategy == "global":
+        if hp.strategy == "global" and not det:      # (deterministic mode: global histograms add to exact accumulators too)
             hp.fx = False
-    if not any(hp.strategy in ("smem", "window") for hp in plans):
+        if det and len(hp.f64_terms) > 0 and not hp.fx:
+            raise UnsupportedError("deterministic mode: more than {0} float64 terms in one fill".format(MAX_WIN - 2))
+    if not any(hp.strategy in ("smem", "window") for hp in plans) and not any(hp.fx for hp in plans):
         used = 0
     return used, window
 
@@ -733,6 +737,8 @@ class Kernel(object):
         self.nfx = 0
         self.fx_aux = None
         self.naux = 0
+        self.deterministic = False
+        self.exact = {}
 
 
 def _colarg(slot, dtype, is_scalar, loaded):
@@ -868,7 +874,7 @@ def _group_lookup(hp, aux_slot):
     return out
 
 
-def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None):
+def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None, gexact=None):
     """C lines adding one event's terms to the shared-memory row of its bin.
 
     float64 layout: ``rowptr`` is a double* to the bin's first slot, slots ``sstride`` doubles apart.
@@ -892,8 +898,14 @@ def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None):
             out.append("%sconst hb_u64 fd%d = hb_fx_stage1(%s + %d * %s, %s, ff%d, fc%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j, j))
         for j, t in enumerate(slots):
             out.append("%shb_fx_stage2(%s + %d * %s, %s, ff%d, fd%d);" % (indent, rowptr, 4 * j, sstride, sstride, j, j))
+        det = bool(options.get("deterministic", False))
         for j, t in enumerate(slots):
-            out.append("%sif (!ff%d.fits) {" % (indent, j))
+            if det:
+                # does not fit the shared-memory field: the lower global window takes it, exactly
+                out.append("%sif (!ff%d.fits && !hb_fxg_add1(%s + %d, fv%d, p.win[%d] - HB_FXG_LOWER)) {" % (
+                    indent, j, gexact, 6 * j + 3, j, 2 + hp.fx_index[t]))
+            else:
+                out.append("%sif (!ff%d.fits) {" % (indent, j))
             out.append("%s    atomicAdd(HB_FXMISS, 1u);" % indent)
             for col in hp.dest[t]:
                 out.append("%s    hb_red_f64(%s + %d, fv%d);" % (indent, grow, col, j))
@@ -917,12 +929,22 @@ def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None):
     return out
 
 
-def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1"):
-    """C lines adding one shared-memory row to the global row ``row`` (float64 REDs, zero slots skipped)."""
+def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1", rowidx=None):
+    """C lines adding one shared-memory row to the global row ``row`` (float64 REDs, zero slots skipped); in
+    deterministic mode the fixed-point limbs go to the exact accumulators of global row ``rowidx`` as integers."""
     slots, count_u32 = hp.row_layout(options)
+    det = bool(options.get("deterministic", False)) and hp.fx
     out = []
+    if det:
+        out.append("%shb_u64* const grow = p.fxg[%d] + (hb_i64)(%s) * %d;" % (indent, hp.hid, rowidx, 6 * len(slots)))
     for j, t in enumerate(slots):
         if t == -1:
+            continue
+        if det:
+            acc = "%s + %d * %s" % (rowptr, 4 * j, sstride)
+            out.append("%s{ const hb_u64 ml = ((hb_u64)(%s)[%s] << 32) | (%s)[0], mh = ((hb_u64)(%s)[3 * %s] << 32) | (%s)[2 * %s];" % (
+                indent, acc, sstride, acc, acc, sstride, acc, sstride))
+            out.append("%s  hb_fxg_add128(grow + %d, ml, mh, (hb_u64)((hb_i64)mh >> 63)); }" % (indent, 6 * j))
             continue
         if hp.fx:
             out.append("%s{ const double v = hb_fx_read(%s + %d * %s, %s, p.win[%d] - 1075);" % (indent, rowptr, 4 * j, sstride, sstride, 2 + hp.fx_index[t]))
@@ -941,6 +963,36 @@ def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1"):
     return out
 
 
+def _emit_global_adds(hp, options, rowidx, indent):
+    """C lines adding one event's terms to the histogram in global memory: float64 REDs, or -- deterministic mode --
+    integer adds to the exact accumulators p.fxg (a term that does not fit them is still a float64 RED, counted)."""
+    out = []
+    det = bool(options.get("deterministic", False))
+    out.append("%sdouble* const row = p.hist[%d] + (hb_i64)(%s) * %d;" % (indent, hp.hid, rowidx, hp.ncol))
+    if det and hp.fx:
+        ns = len(hp.f64_terms)
+        out.append("%shb_u64* const grow = p.fxg[%d] + (hb_i64)(%s) * %d;" % (indent, hp.hid, rowidx, 6 * ns))
+    for t, e in enumerate(hp.terms):
+        if e is not None and det and hp.fx:
+            j = hp.f64_terms.index(t)
+            out.append("%s{ const double v = %s;" % (indent, e))
+            out.append("%s  if (!hb_fxg_add(grow + %d, v, p.win[%d])) {" % (indent, 6 * j, 2 + hp.fx_index[t]))
+            out.append("%s    atomicAdd(HB_FXMISS, 1u);" % indent)
+            for col in hp.dest[t]:
+                out.append("%s    hb_red_f64(row + %d, v);" % (indent, col))
+            out.append("%s  } }" % indent)
+            continue
+        val = "1.0" if e is None else e
+        if len(hp.dest[t]) > 1:
+            out.append("%s{ const double v = %s;" % (indent, val))
+            for col in hp.dest[t]:
+                out.append("%s  hb_red_f64(row + %d, v);" % (indent, col))
+            out.append("%s}" % indent)
+        else:
+            out.append("%shb_red_f64(row + %d, %s);" % (indent, hp.dest[t][0], val))
+    return out
+
+
 def _rowptr(hp, options, name, base_off, index, nrows_expr, const=False):
     """(declaration line, slot stride expr) of the shared-memory row pointer of bin ``index``."""
     c = "const " if const else ""
@@ -955,8 +1007,8 @@ def generate(spec, coltypes, options=None):
     options = options or {}
     prog = Program(spec, coltypes)
     plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
-    if len(plans) > 256:
-        raise UnsupportedError("more than 256 histograms in one fill")
+    if len(plans) > 128:
+        raise UnsupportedError("more than 128 histograms in one fill")
     smem, window = choose_strategies(plans, options)
     if len(prog.cols) > 32:
         raise UnsupportedError("more than 32 input fields in one fill")
@@ -1009,7 +1061,8 @@ def generate(spec, coltypes, options=None):
             ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
             conds = ["okg", "slot >= 0"] + conds
         conds = ["live"] + conds
-        pair = (hp.strategy in ("global", "window") and options.get("pair_red", True) and hp.ncol == 2 and len(hp.terms) == 2
+        pair = (hp.strategy in ("global", "window") and options.get("pair_red", True) and not options.get("deterministic", False)
+                and hp.ncol == 2 and len(hp.terms) == 2
                 and sorted(hp.dest[0] + hp.dest[1]) == [0, 1])
         outside = ""
         if hp.strategy == "window":
@@ -1034,7 +1087,8 @@ def generate(spec, coltypes, options=None):
             decl, sstride = _rowptr(hp, options, "wrow", hp.win_off, "wb", "p.win[1]")
             ev.append("        " + decl)
             ev.extend(_emit_row_adds(hp, options, "wrow", "reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb" % (hp.win_off, nf * hp.slot_bytes),
-                                     "        ", sstride, grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol)))
+                                     "        ", sstride, grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol),
+                                     gexact="(p.fxg[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, 6 * len(hp.f64_terms))))
             ev.append("    }")
             conds = ["okw", "!inside"]
         if pair:
@@ -1077,28 +1131,14 @@ def generate(spec, coltypes, options=None):
             else:
                 sstride = "1"
             ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + srowi" % hp.smem_u32_off, indent, sstride,
-                                     grow="(p.hist[%d] + (hb_i64)srowi * %d)" % (hp.hid, hp.ncol)))
+                                     grow="(p.hist[%d] + (hb_i64)srowi * %d)" % (hp.hid, hp.ncol),
+                                     gexact="(p.fxg[%d] + (hb_i64)srowi * %d)" % (hp.hid, 6 * len(hp.f64_terms))))
             if hp.groups:
                 ev.append("        } else {")
-                ev.append("            double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
-                for t, e in enumerate(hp.terms):
-                    for col in hp.dest[t]:
-                        ev.append("            hb_red_f64(row + %d, %s);" % (col, "1.0" if e is None else e))
+                ev.extend(_emit_global_adds(hp, options, "(hb_i64)slot * %d + bin" % hp.nbins, "            "))
                 ev.append("        }")
         else:
-            if hp.groups:
-                ev.append("        double* const row = p.hist[%d] + ((hb_i64)slot * %d + bin) * %d;" % (hp.hid, hp.nbins, hp.ncol))
-            else:
-                ev.append("        double* const row = p.hist[%d] + (hb_i64)bin * %d;" % (hp.hid, hp.ncol))
-            for t, e in enumerate(hp.terms):
-                val = "1.0" if e is None else e
-                if len(hp.dest[t]) > 1:
-                    ev.append("        { const double v = %s;" % val)
-                    for col in hp.dest[t]:
-                        ev.append("          hb_red_f64(row + %d, v);" % col)
-                    ev.append("        }")
-                else:
-                    ev.append("        hb_red_f64(row + %d, %s);" % (hp.dest[t][0], val))
+            ev.extend(_emit_global_adds(hp, options, ("(hb_i64)slot * %d + bin" % hp.nbins) if hp.groups else "bin", "        "))
         ev.append("    }")
         ev.append("}")
 
@@ -1112,7 +1152,7 @@ def generate(spec, coltypes, options=None):
         nslots = len(hp.row_layout(options)[0])
         decl, sstride = _rowptr(hp, options, "srow", hp.smem_f64_off, "b", hp.nrows, const=True)
         merge.append("    " + decl)
-        merge.extend(_emit_row_merge(hp, options, "srow", "reinterpret_cast<const hb_u32*>(hb_smem + %d)[b]" % hp.smem_u32_off, "    ", sstride))
+        merge.extend(_emit_row_merge(hp, options, "srow", "reinterpret_cast<const hb_u32*>(hb_smem + %d)[b]" % hp.smem_u32_off, "    ", sstride, rowidx="b"))
         merge.append("}")
 
     if window is not None:
@@ -1126,7 +1166,8 @@ def generate(spec, coltypes, options=None):
         merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
         decl, sstride = _rowptr(hp, options, "wrow", hp.win_off, "wb", "p.win[1]", const=True)
         merge.append("        " + decl)
-        merge.extend(_emit_row_merge(hp, options, "wrow", "reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb]" % (hp.win_off, nf * hp.slot_bytes), "        ", sstride))
+        merge.extend(_emit_row_merge(hp, options, "wrow", "reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb]" % (hp.win_off, nf * hp.slot_bytes), "        ", sstride,
+                                     rowidx="(hb_i64)wr * %d + (we.y >> 16) + wa" % hp.win_trail))
         merge.append("    }")
         merge.append("}")
 
@@ -1146,6 +1187,13 @@ def generate(spec, coltypes, options=None):
         merge.append("if (threadIdx.x == 0 && *HB_FXMISS != 0u && p.aux[%d] != nullptr)" % k.fx_aux)
         merge.append("    atomicAdd(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), (hb_u64)*HB_FXMISS);" % k.fx_aux)
     k.naux = naux
+    k.deterministic = bool(options.get("deterministic", False))
+    # deterministic mode: per histogram [(scale index, destination column mask)] of its float64 slots, in slot order
+    k.exact = {}
+    if k.deterministic:
+        for hp in plans:
+            if hp.fx:
+                k.exact[hp.hid] = [(hp.fx_index[t], sum(1 << c for c in hp.dest[t])) for t in hp.f64_terms]
     k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)))
     k.cols = list(prog.cols)
     k.plans = plans

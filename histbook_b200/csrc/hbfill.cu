@@ -517,6 +517,12 @@ static int launch(hb_program* prog, const HbParams& params, int grid) {
 extern "C" int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
                        int nhists, hb_arena* const* hists, int naux, const void* const* aux,
                        int nwin, const int32_t* win, int flags, hb_stats* stats) {
+    return hb_fill_exact(prog, ncols, cols, n, nhists, hists, nullptr, naux, aux, nwin, win, flags, stats);
+}
+
+extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
+                             int nhists, hb_arena* const* hists, hb_arena* const* exact, int naux, const void* const* aux,
+                             int nwin, const int32_t* win, int flags, hb_stats* stats) {
     int rc = ensure_device();
     if (rc) return rc;
     if (!prog || ncols < 0 || ncols > HB_MAX_COLS || nhists < 0 || nhists > HB_MAX_HISTS || naux < 0 || naux > HB_MAX_AUX || n < 0)
@@ -537,6 +543,7 @@ extern "C" int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64
     for (int h = 0; h < nhists; ++h) {
         if (!hists[h]) return fail(HB_ERR_ARG, "null arena");
         base.hist[h] = hists[h]->ptr;
+        base.fxg[h] = (exact && exact[h]) ? reinterpret_cast<hb_u64*>(exact[h]->ptr) : nullptr;
     }
     for (int a = 0; a < naux; ++a) base.aux[a] = aux[a];
     if (nwin < 0 || nwin > HB_MAX_WIN) return fail(HB_ERR_ARG, "too many window parameters");
@@ -617,6 +624,54 @@ extern "C" int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64
         cudaEventDestroy(t1);
     }
     if (stats) *stats = st;
+    return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic mode: exact accumulators -> float64 contents
+
+#define HB_FX_MAXSLOTS 32
+struct HbFinalize {
+    int k[HB_FX_MAXSLOTS];
+    unsigned long long mask[HB_FX_MAXSLOTS];
+};
+
+__global__ void hb_fx_finalize_kernel(double* __restrict__ content, hb_u64* __restrict__ g, int64_t nrows, int ncol, int nslots,
+                                      const HbFinalize f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrows * nslots; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / nslots;
+        const int j = (int)(i - row * nslots);
+        hb_u64* const acc = g + (int64_t)HB_FXG_SLOT * i;
+        hb_u64 any = 0ull;
+        for (int w = 0; w < HB_FXG_SLOT; ++w) any |= acc[w];
+        if (any == 0ull) continue;
+        const double v = hb_fxg_value(acc, f.k[j] - 1075);
+        for (int w = 0; w < HB_FXG_SLOT; ++w) acc[w] = 0ull;
+        unsigned long long m = f.mask[j];
+        for (int c = 0; m != 0ull; ++c, m >>= 1)
+            if (m & 1ull) content[row * ncol + c] += v;     // one writer per (row, column): no two slots feed the same column
+    }
+}
+
+extern "C" int hb_fx_finalize(hb_arena* content, hb_arena* exact, int64_t nrows, int ncol, int nslots,
+                              const int32_t* k, const uint64_t* dest_mask) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!content || !exact || !k || !dest_mask || nrows < 0 || ncol < 1 || ncol > 64 || nslots < 1 || nslots > HB_FX_MAXSLOTS)
+        return fail(HB_ERR_ARG, "bad hb_fx_finalize arguments");
+    if (nrows * ncol > content->n || nrows * nslots * HB_FXG_SLOT > exact->n) return fail(HB_ERR_ARG, "hb_fx_finalize: arenas too small");
+    HbFinalize f;
+    memset(&f, 0, sizeof(f));
+    unsigned long long seen = 0ull;
+    for (int j = 0; j < nslots; ++j) {
+        f.k[j] = k[j];
+        f.mask[j] = dest_mask[j];
+        if (seen & dest_mask[j]) return fail(HB_ERR_ARG, "hb_fx_finalize: two slots feed one column");
+        seen |= dest_mask[j];
+    }
+    if (nrows == 0) return HB_OK;
+    hb_fx_finalize_kernel<<<grid_for(nrows * nslots), 256, 0, g_stream>>>(content->ptr, reinterpret_cast<hb_u64*>(exact->ptr), nrows, ncol, nslots, f);
+    CUDA_TRY(cudaGetLastError());
     return HB_OK;
 }
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libhbfill.so")
 TEMPLATE_PATH = os.path.join(_HERE, "csrc", "hb_template.cuh")
 
 HB_FILL_TIMED = 1
-MAX_COLS, MAX_HISTS, MAX_AUX = 32, 256, 64
+MAX_COLS, MAX_HISTS, MAX_AUX = 32, 128, 64
 
 
 class EngineError(RuntimeError):
@@ -65,6 +65,8 @@ SYMBOLS = {
     "hb_arena_ptr": (_P, [_P]),
     "hb_arena_size": (_I64, [_P]),
     "hb_fill": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
+    "hb_fill_exact": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
+    "hb_fx_finalize": (_I, [_P, _P, _I64, _I, _I, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64)]),
     "hb_arena_marginals": (_I, [_P, _I, ctypes.POINTER(_I64), _I, _I, _P]),
     "hb_keyset_create": (_I, [_I, _PP]),
     "hb_keyset_destroy": (_I, [_P]),
@@ -353,9 +355,18 @@ class DeviceBuffer(object):
 _ITEMSIZE = [8, 4, 8, 4, 2, 1, 8, 4, 2, 1, 1]
 
 
-def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0):
+def fx_finalize(content, exact, nrows, ncol, ks, masks):
+    """Round the exact accumulators of one histogram into its float64 content and zero them (deterministic mode)."""
+    n = len(ks)
+    karr = (ctypes.c_int32 * n)(*[int(x) for x in ks])
+    marr = (ctypes.c_uint64 * n)(*[int(x) for x in masks])
+    check(lib().hb_fx_finalize(content._h, exact._h, int(nrows), int(ncol), n, karr, marr))
+
+
+def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exact=None):
     """columns: list of (ptr:int, dtype_code, location 0 host / 1 device) or ("scalar", dtype_code, bits).
-    ``offset``/``n`` select the event range [offset, offset + n) of every column."""
+    ``offset``/``n`` select the event range [offset, offset + n) of every column.  ``exact``: per histogram an
+    Arena of 128-bit accumulators or None (deterministic mode)."""
     init()
     ncols = len(columns)
     cols = (hb_column * max(ncols, 1))()
@@ -369,7 +380,12 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0):
     auxp = (ctypes.c_void_p * max(len(aux), 1))(*[ctypes.c_void_p(int(x)) for x in aux])
     winp = (ctypes.c_int32 * max(len(win), 1))(*[int(x) for x in win])
     stats = hb_stats()
-    check(lib().hb_fill(program._h, ncols, cols, int(n), len(arenas), hist, len(aux), auxp, len(win), winp,
-                        HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
+    if exact is None:
+        check(lib().hb_fill(program._h, ncols, cols, int(n), len(arenas), hist, len(aux), auxp, len(win), winp,
+                            HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
+    else:
+        ex = (ctypes.c_void_p * max(len(arenas), 1))(*[(a._h if a is not None else None) for a in exact])
+        check(lib().hb_fill_exact(program._h, ncols, cols, int(n), len(arenas), hist, ex, len(aux), auxp, len(win), winp,
+                                  HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
     return {"events": stats.events, "h2d_bytes": stats.h2d_bytes, "launches": stats.launches, "grid": stats.grid,
             "blocks_per_sm": stats.blocks_per_sm, "ms_kernel": stats.ms_kernel}

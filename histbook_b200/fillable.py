@@ -229,8 +229,30 @@ def fill_hists(plan, hists, arrays, timed=False):
             if kern.fx_terms:
                 fx = _fx_scales(plan, sig, kern, rng, rprog, cols, length)
                 aux[kern.fx_aux] = plan.fx_stat.ptr
+            exact = None
+            if kern.deterministic and kern.exact:
+                # deterministic mode: two zeroed 192-bit accumulators (upper / lower exponent window) per (row, float64 slot) next to every histogram
+                exact = []
+                for hid, st in enumerate(stores):
+                    slots = kern.exact.get(hid)
+                    if not slots:
+                        exact.append(None)
+                        continue
+                    need = (st.arena.size // st.shape[-1]) * len(slots) * 6
+                    if st.exact is None or st.exact.size != need:
+                        st.exact = engine.Arena(need)
+                    exact.append(st.exact)
+
+            def finalize():
+                if exact is not None:
+                    for hid, st in enumerate(stores):
+                        slots = kern.exact.get(hid)
+                        if slots:
+                            engine.fx_finalize(st.arena, st.exact, st.arena.size // st.shape[-1], st.shape[-1],
+                                               [fx[i] for i, mask in slots], [mask for i, mask in slots])
             if kern.window is None:
-                stats = engine.fill(prog, abi, length, arenas, aux=aux, win=[0, 0] + fx, timed=timed)
+                stats = engine.fill(prog, abi, length, arenas, aux=aux, win=[0, 0] + fx, timed=timed, exact=exact)
+                finalize()
             else:
                 # hot-window privatisation: place the window from what the histogram already holds; a histogram
                 # that is still empty first gets a pilot slice of this fill through the global path.
@@ -242,7 +264,8 @@ def fill_hists(plan, hists, arrays, timed=False):
                 if wst.window is None or wst.window_key != (info["rows"], info["trail"], info["wmax"]):
                     if not wst.nonempty:
                         done = min(length, max(kern.tile, PILOT_EVENTS // kern.tile * kern.tile))
-                        pilot = engine.fill(prog, abi, done, arenas, aux=aux, win=[0, 0] + fx, timed=timed)
+                        pilot = engine.fill(prog, abi, done, arenas, aux=aux, win=[0, 0] + fx, timed=timed, exact=exact)
+                        finalize()
                         extra = pilot["ms_kernel"]
                     content = wst.arena.read(0, info["rows"] * info["trail"] * info["ncol"])
                     density = numpy.abs(content.reshape(info["rows"], info["trail"], info["ncol"])[:, :, info["col"]])
@@ -262,7 +285,8 @@ def fill_hists(plan, hists, arrays, timed=False):
                     win = [0, 0] + fx
                 stats = {"events": length, "launches": 1 if done else 0, "ms_kernel": extra}
                 if length > done:
-                    main = engine.fill(prog, abi, length - done, arenas, aux=aux, win=win, timed=timed, offset=done)
+                    main = engine.fill(prog, abi, length - done, arenas, aux=aux, win=win, timed=timed, offset=done, exact=exact)
+                    finalize()
                     main["launches"] += stats["launches"]
                     main["ms_kernel"] += extra
                     stats = main
@@ -270,6 +294,9 @@ def fill_hists(plan, hists, arrays, timed=False):
                 stats["window_coverage"] = wst.window_coverage
         for st in stores:
             st.mark_filled()
+        if kern.fx_terms and _options.get("fx_stats", False):
+            stats["fx_missed_total"] = int(plan.fx_stat.read(numpy.uint64)[0])
+        stats["deterministic"] = kern.deterministic
         stats["regs"] = prog.regs
         stats["smem_bytes"] = kern.smem_bytes
         stats["keys_launches"] = 1 if (keys is not None and length > 0) else 0

@@ -90,6 +90,7 @@ class Store(object):
         self.window = None            # {"table": DeviceBuffer, "bins", "rows"}
         self.window_key = None        # (rows, trail, wmax) of the kernel the window was placed for
         self.window_coverage = None
+        self.exact = None             # deterministic mode: engine.Arena of 128-bit accumulators (zero between fills)
         self.nonempty = False                         # the device copy holds at least one fill / uploaded content
 
     # ------------------------------------------------------------------ host view

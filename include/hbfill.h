@@ -40,7 +40,7 @@ extern "C" {
 #define HB_ERR_OVERFLOW 4   /* a device-side table is full (key sets) */
 
 #define HB_MAX_COLS 32
-#define HB_MAX_HISTS 256
+#define HB_MAX_HISTS 128
 #define HB_MAX_AUX 64
 #define HB_MAX_WIN 128     /* run-time integer parameters of a launch (window geometry, fixed-point scales) */
 
@@ -116,6 +116,20 @@ int64_t hb_arena_size(const hb_arena* a);
 int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
             int nhists, hb_arena* const* hists, int naux, const void* const* aux,
             int nwin, const int32_t* win, int flags, hb_stats* stats);
+
+/* Deterministic mode.  hb_fill_exact is hb_fill with, per histogram, a second arena (`exact[h]`, may be NULL) that
+ * holds two 192-bit fixed-point accumulators (upper and lower exponent window, 2 x 3 64-bit words) per (row, float64 slot): kernels generated with the
+ * "deterministic" option add every float64 term there with integer atomics instead of float64 REDs.
+ * hb_fx_finalize then rounds each accumulator to float64 once, adds it to the columns named by dest_mask[slot]
+ * (bit c = column c) of `content`, and zeroes it.  k[slot] = 1075 + binary exponent of the accumulator's least
+ * significant bit (the same run-time integer the fill kernel received).  Stands in for the per-column
+ * numpy.add.at of Hist._postfill (histbook/hist.py:439-456), whose sequential float64 sum it replaces by the
+ * correctly rounded exact sum. */
+int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
+                  int nhists, hb_arena* const* hists, hb_arena* const* exact, int naux, const void* const* aux,
+                  int nwin, const int32_t* win, int flags, hb_stats* stats);
+int hb_fx_finalize(hb_arena* content, hb_arena* exact, int64_t nrows, int ncol, int nslots,
+                   const int32_t* k, const uint64_t* dest_mask);
 
 /* Per-axis marginals of |content[..., col]| of an N-d histogram (shape = fixed-axis bins..., ncol), computed on
  * the device; host_out receives shape[0] + ... + shape[ndim-1] doubles.  Used to place the hot window that the

@@ -370,6 +370,29 @@ def _new_content(h, level):
     return {}
 
 
+_EXACT = [False]
+
+
+def _add_at(target, idx, values):
+    """numpy.add.at (hist.py:439-456): sequential float64 adds in input order -- or, with ``exact`` set by
+    fill(..., exact=True) (tests of the deterministic mode only), the correctly rounded exact sum of each bin's
+    terms (math.fsum) added to the bin once."""
+    if not _EXACT[0]:
+        numpy.add.at(target, idx, values)
+        return
+    idx = numpy.asarray(idx)
+    values = numpy.broadcast_to(numpy.asarray(values, dtype=numpy.float64), idx.shape)
+    order = numpy.argsort(idx, kind="stable")
+    sidx, svals = idx[order], values[order]
+    starts = numpy.flatnonzero(numpy.concatenate([[True], sidx[1:] != sidx[:-1]])) if len(sidx) else []
+    ends = list(starts[1:]) + [len(sidx)] if len(sidx) else []
+    for a, b in zip(starts, ends):
+        chunk = svals[a:b]
+        with numpy.errstate(all="ignore"):
+            total = math.fsum(chunk) if numpy.all(numpy.isfinite(chunk)) else float(numpy.sum(chunk))
+        target[sidx[a]] += total
+
+
 def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length, absolute=False):
     """hist.py:429-456 (fillblock).  ``absolute`` (tests only) accumulates |term| instead of term: the
     per-bin sum of magnitudes that the float tolerance is stated against."""
@@ -384,14 +407,14 @@ def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length, abs
             if mask is not numpy.ma.nomask:
                 weight = weight[~mask]
                 weight2 = weight2[~mask]
-        numpy.add.at(flat[:, p["sumwx"]], indexes.compressed(), A(sumx * weight))
-        numpy.add.at(flat[:, p["sumwx2"]], indexes.compressed(), A(sumx2 * weight))
+        _add_at(flat[:, p["sumwx"]], indexes.compressed(), A(sumx * weight))
+        _add_at(flat[:, p["sumwx2"]], indexes.compressed(), A(sumx2 * weight))
 
     if weight2 is None:
         if indexes is None:
             flat[:, h["sumw"]] += A((1 if length is None else length) * weight)
         else:
-            numpy.add.at(flat[:, h["sumw"]], indexes.compressed(), A(weight))
+            _add_at(flat[:, h["sumw"]], indexes.compressed(), A(weight))
     else:
         if indexes is None:
             indexes = numpy.ma.zeros(len(weight), dtype=INDEXTYPE)
@@ -399,8 +422,8 @@ def _fill_block(h, content, indexes, sumxs, sumx2s, weight, weight2, length, abs
         if mask is not numpy.ma.nomask:
             weight = weight[~mask]
             weight2 = weight2[~mask]
-        numpy.add.at(flat[:, h["sumw"]], indexes.compressed(), A(weight))
-        numpy.add.at(flat[:, h["sumw2"]], indexes.compressed(), A(weight2))
+        _add_at(flat[:, h["sumw"]], indexes.compressed(), A(weight))
+        _add_at(flat[:, h["sumw2"]], indexes.compressed(), A(weight2))
 
 
 def _fill_dict(h, groups, level, content, indexes, sumxs, sumx2s, weight, weight2, allsel, length, absolute=False):
@@ -476,12 +499,22 @@ def _postfill(h, interp, content, length, absolute=False):
     _fill_dict(h, groups, 0, content, indexes, sumxs, sumx2s, weight, weight2, None, length, absolute)
 
 
-def fill(spec, arrays, contents=None, absolute=False):
+def fill(spec, arrays, contents=None, absolute=False, exact=False):
     """One ``Book.fill`` (book.py:540-586) / ``Hist.fill`` (hist.py:337-379) over ``arrays``.
 
     ``contents`` is the list of previous per-hist contents (``None`` entries = never
-    filled); it is updated in place where possible and returned.
+    filled); it is updated in place where possible and returned.  ``exact`` (not the reference's behaviour; the
+    yardstick of the device's deterministic mode): every bin receives the correctly rounded exact sum of this
+    fill's terms instead of their sequential float64 sum.
     """
+    _EXACT[0] = bool(exact)
+    try:
+        return _fill(spec, arrays, contents, absolute)
+    finally:
+        _EXACT[0] = False
+
+
+def _fill(spec, arrays, contents, absolute):
     hists = spec["hists"]
     if contents is None:
         contents = [None] * len(hists)
