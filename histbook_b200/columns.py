@@ -11,6 +11,50 @@ import numpy
 from histbook_b200.codegen import DTYPE_CODE, MAYBECONSTANTS, UnsupportedError
 
 
+class StringCodes(object):
+    """Dictionary encoding of one string-valued ``groupby`` field (histbook_groupby accepts strings:
+    histbook/calc/__init__.py:149-154, tests/test_hist.py:394-407).  The device only ever sees int64 codes; the
+    code of a string never changes, so codes from different fills (and contents uploaded from host dicts) agree."""
+
+    def __init__(self):
+        self.code_of = {}
+        self.strings = []
+
+    def code(self, key):
+        key = str(key) if not isinstance(key, bytes) else key
+        c = self.code_of.get(key)
+        if c is None:
+            c = self.code_of[key] = len(self.strings)
+            self.strings.append(key)
+        return c
+
+    def encode(self, values):
+        """array-like of str / bytes -> int64 codes (numpy.unique once, then a table lookup)."""
+        arr = numpy.asarray(values)
+        if arr.ndim != 1:
+            raise UnsupportedError("only one-dimensional string arrays can be filled")
+        if arr.dtype.kind == "O":
+            arr = arr.astype(str)
+        uniques, inverse = numpy.unique(arr, return_inverse=True)
+        table = numpy.array([self.code(u.item() if hasattr(u, "item") else u) for u in uniques], dtype=numpy.int64)
+        return table[inverse] if len(uniques) else numpy.zeros(0, dtype=numpy.int64)
+
+    def decode(self, code):
+        s = self.strings[int(code)]
+        return numpy.bytes_(s) if isinstance(s, bytes) else numpy.str_(s)
+
+
+def is_stringlike(value):
+    """A fill argument that numpy would turn into a string array (list of str, '<U' / 'S' / object-of-str arrays)."""
+    if isinstance(value, numpy.ndarray):
+        if value.dtype.kind in "US":
+            return True
+        return value.dtype.kind == "O" and value.ndim == 1 and len(value) > 0 and isinstance(value[0], (str, bytes))
+    if isinstance(value, (list, tuple)) and len(value) > 0:
+        return isinstance(value[0], (str, bytes))
+    return False
+
+
 class Column(object):
     __slots__ = ("name", "dtype", "is_scalar", "ptr", "location", "length", "scalar_bits", "keepalive")
 

@@ -112,8 +112,10 @@ def _allreduce_store(st, group):
     # group axes: agree on the union of key tuples, re-lay the slab out in that order, then reduce
     world = dist.get_world_size(group)
     gathered = [None] * world
-    dist.all_gather_object(gathered, list(st.tuples.keys()), group=group)
-    order = union_keys(gathered)
+    # (string group keys are dictionary codes local to a rank: they travel as the strings themselves)
+    wire = [tuple(g.to_wire(p) for g, p in zip(st.groups, tup)) for tup in st.tuples.keys()]
+    dist.all_gather_object(gathered, wire, group=group)
+    order = [tuple(g.from_wire(w) for g, w in zip(st.groups, tup)) for tup in union_keys(gathered)]
     host = st.arena.read(0, len(st.tuples) * st.blocksize).reshape(len(st.tuples), st.blocksize) if st.tuples else numpy.zeros((0, st.blocksize))
     slab = numpy.zeros((max(len(order), 1), st.blocksize))
     for slot, tup in enumerate(order):

@@ -40,6 +40,14 @@ class Plan(object):
         self.kernels = {}           # dtype signature -> (fill Kernel, Program, keys Kernel, keys Program, range Kernel, range Program)
         self.generation = Plan.generation
         self.keysets = None
+        # fields that are the direct argument of a groupby axis may hold strings: dictionary-encoded on the host
+        self.groupby_fields = {}    # field name -> tree key of the groupby goal
+        for h in self.spec["hists"]:
+            for a in h["group"]:
+                g = a["goal"]
+                if a["kind"] == "groupby" and g[0] == "call" and g[1] == "histbook.groupby" and g[2][0] == "name":
+                    self.groupby_fields[g[2][1]] = hbspec.tree_key(g)
+        self.string_codes = {}      # field name -> columns.StringCodes (created at the first string-valued fill)
         self.fx_scales = {}         # dtype signature -> fixed-point scale per term (from the pilot), see _fx_scales
         self.fx_stat = None         # device counter: terms that missed their fixed-point window (all fills so far)
         self.fx_seen = 0            # ... its value when last looked at
@@ -179,6 +187,7 @@ def _store_of(hist):
 def fill_hists(plan, hists, arrays, timed=False):
     """One pass over ``arrays`` filling every histogram in ``hists`` (deduplicated, in plan order)."""
     with _lock:
+        arrays = _encode_strings(plan, arrays)
         cols, length = columns.bind_all(plan.fields, arrays)
         sig, (kern, prog, keys, kprog, rng, rprog) = plan.kernel_for(cols)
 
@@ -210,7 +219,11 @@ def fill_hists(plan, hists, arrays, timed=False):
                 for a in hspec["group"]:
                     goalkey = hbspec.tree_key(a["goal"])
                     patterns, info = discovered[goalkey]
-                    infos.append(GroupInfo(a["kind"], a["keeporder"], info["kind"] == "f", info["dtype"], info["nanflow"], goalkey))
+                    codes = None
+                    for field, gk in plan.groupby_fields.items():
+                        if gk == goalkey and field in plan.string_codes:
+                            codes = plan.string_codes[field]
+                    infos.append(GroupInfo(a["kind"], a["keeporder"], info["kind"] == "f", info["dtype"], info["nanflow"], goalkey, codes))
                     fill_keys.append([int(x) for x in patterns])
                 st.groups = infos
                 st.to_device()
@@ -303,6 +316,33 @@ def fill_hists(plan, hists, arrays, timed=False):
         last_stats.clear()
         last_stats.update(stats)
         return length
+
+
+class _Overlay(object):
+    """``arrays`` with a few fields replaced (dict-like: __getitem__ raising KeyError is all bind_all needs)."""
+
+    def __init__(self, base, replaced):
+        self.base, self.replaced = base, replaced
+
+    def __getitem__(self, name):
+        if name in self.replaced:
+            return self.replaced[name]
+        return self.base[name]
+
+
+def _encode_strings(plan, arrays):
+    """String-valued groupby fields -> int64 codes (histbook_groupby on strings, calc/__init__.py:149-154)."""
+    replaced = {}
+    for field in plan.groupby_fields:
+        try:
+            value = arrays[field]
+        except KeyError:
+            continue
+        if columns.is_stringlike(value):
+            replaced[field] = plan.string_codes.setdefault(field, columns.StringCodes()).encode(value)
+        elif field in plan.string_codes:
+            raise codegen.UnsupportedError("field {0!r} was filled with strings before; a group axis cannot mix string and numeric keys".format(field))
+    return _Overlay(arrays, replaced) if replaced else arrays
 
 
 def _clone_store(st):

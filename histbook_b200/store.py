@@ -24,9 +24,10 @@ KEY_EMPTY = 0xFFF0DEADBEEFCAFE
 
 class GroupInfo(object):
     """Static description of one group axis of a histogram."""
-    __slots__ = ("kind", "keeporder", "floatkey", "dtype", "nanflow", "goalkey")
+    __slots__ = ("kind", "keeporder", "floatkey", "dtype", "nanflow", "goalkey", "codes")
 
-    def __init__(self, kind, keeporder, floatkey, dtype, nanflow, goalkey):
+    def __init__(self, kind, keeporder, floatkey, dtype, nanflow, goalkey, codes=None):
+        self.codes = codes            # columns.StringCodes when the axis groups by a string field (patterns are codes)
         self.kind = kind              # "groupby" | "groupbin"
         self.keeporder = keeporder
         self.floatkey = floatkey      # True: pattern is float64 bits; False: int64 bits
@@ -36,6 +37,8 @@ class GroupInfo(object):
 
     def key_object(self, pattern):
         """64-bit pattern -> the dict key the reference would use (calc/__init__.py:150-154,170-187)."""
+        if self.codes is not None:
+            return self.codes.decode(pattern)
         if self.floatkey:
             if pattern == KEY_NAN:
                 return "NaN" if self.kind == "groupbin" else self.dtype.type(numpy.nan)
@@ -46,6 +49,10 @@ class GroupInfo(object):
 
     def pattern(self, key):
         """dict key -> 64-bit pattern (inverse of key_object)."""
+        if self.codes is not None:
+            if not isinstance(key, (str, bytes)):
+                raise UnsupportedError("a group axis cannot mix string and numeric keys")
+            return self.codes.code(key)
         if isinstance(key, str):
             if key == "NaN" and self.floatkey:
                 return KEY_NAN
@@ -59,8 +66,17 @@ class GroupInfo(object):
             return int(numpy.array([v]).view(numpy.uint64)[0])
         return int(numpy.array([int(key)], dtype=numpy.int64).view(numpy.uint64)[0])
 
+    def to_wire(self, pattern):
+        """What identifies this key on another rank (string codes are rank-local)."""
+        return ("s", self.codes.strings[int(pattern)]) if self.codes is not None else int(pattern)
+
+    def from_wire(self, wire):
+        return self.codes.code(wire[1]) if self.codes is not None else int(wire)
+
     def sort_patterns(self, patterns):
         """Order numpy.unique would give the keys of one fill: ascending by value, NaN last."""
+        if self.codes is not None:
+            return [int(p) for p in sorted(patterns, key=lambda p: self.codes.strings[int(p)])]
         arr = numpy.array(sorted(patterns), dtype=numpy.uint64)
         if self.floatkey:
             vals = arr.view(numpy.float64)

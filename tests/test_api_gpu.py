@@ -97,6 +97,59 @@ def test_groupbin_and_numeric_groupby():                      # tests/test_hist.
     assert h.groupkeys(0) == set([1, 2])
 
 
+def test_groupby_strings():                                   # tests/test_hist.py:394-407,422-435 (string keys, verbatim)
+    h = Hist(groupby("c"), bin("x", 3, 1.0, 4.0, underflow=False, overflow=False, nanflow=False))
+    h.fill(c=["one", "two", "three", "two", "one", "one", "one"], x=[1, 2, 3, 2, 1, 1, 3])
+    assert h._content["one"].tolist() == [[3], [0], [1]]
+    assert h._content["two"].tolist() == [[0], [2], [0]]
+    assert h._content["three"].tolist() == [[0], [0], [1]]
+    assert list(h._content.keys()) == ["one", "three", "two"]                    # numpy.unique order
+    h.fill(c=numpy.array(["two", "zero"]), x=[3.5, 1.5])                          # refill: codes stay, a new key appears
+    assert h._content["two"].tolist() == [[0], [2], [1]]
+    assert h._content["zero"].tolist() == [[1], [0], [0]]
+    assert h._content["one"].tolist() == [[3], [0], [1]]
+
+    h = Hist(groupby("c1"), groupby("c2"), bin("x", 1, 1.0, 2.0, underflow=False, overflow=False, nanflow=False))
+    h.fill(c1=["one", "two", "one", "two"], c2=["uno", "uno", "dos", "dos"], x=[1, 1, 1, 1])
+    assert h._content["one"]["uno"].tolist() == [[1]]
+    assert h._content["two"]["uno"].tolist() == [[1]]
+    assert h._content["one"]["dos"].tolist() == [[1]]
+    assert h._content["two"]["dos"].tolist() == [[1]]
+
+    h = Hist(bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False), groupby("c"), groupbin("x", 10.0))
+    h.fill(c=["one", "one", "two", "two"], x=[0, 10, 15, 20], y=[1, 2, 3, 4])
+    assert h._content["one"][0.0].tolist() == [[1], [0], [0], [0]]
+    assert h._content["one"][10.0].tolist() == [[0], [1], [0], [0]]
+    assert h._content["two"][10.0].tolist() == [[0], [0], [1], [0]]
+    assert h._content["two"][20.0].tolist() == [[0], [0], [0], [1]]
+
+    h = Hist(groupbin("x", 10.0), bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False), groupby("c"))
+    h.fill(c=["one", "one", "two", "two"], x=[0, 10, 15, 20], y=[1, 2, 3, 4])
+    assert h._content[0.0]["one"].tolist() == [[1], [0], [0], [0]]
+    assert h._content[10.0]["one"].tolist() == [[0], [1], [0], [0]]
+    assert h._content[10.0]["two"].tolist() == [[0], [0], [1], [0]]
+    assert h._content[20.0]["two"].tolist() == [[0], [0], [0], [1]]
+
+    # against the reference path on random data, and through + (host dicts with string keys go back to the device)
+    rs = numpy.random.RandomState(7)
+    names = numpy.array(["ttbar", "wjets", "zjets", "qcd", "data"])
+    c = names[rs.randint(0, 5, 20000)]
+    x = rs.normal(0, 1, 20000)
+    w = rs.uniform(0.5, 1.5, 20000)
+    h = Hist(groupby("c"), bin("x", 20, -3, 3), weight="w")
+    h.fill(c=c, x=x, w=w)
+    with histbook_b200.reference_path() as hb:
+        r = hb.Hist(hb.groupby("c"), hb.bin("x", 20, -3, 3), weight="w")
+        r.fill(c=c, x=x, w=w)
+        expected = dict((str(k), v.copy()) for k, v in r._content.items())
+    assert sorted(str(k) for k in h._content.keys()) == sorted(expected)
+    for k, v in h._content.items():
+        assert numpy.allclose(v, expected[str(k)], rtol=1e-12, atol=0)
+    both = h + h
+    both.fill(c=c[:100], x=x[:100], w=w[:100])
+    assert numpy.all(both._content["qcd"][:, 0] >= 2 * h._content["qcd"][:, 0])
+
+
 def test_pickle_and_json_roundtrip():                         # tests/test_hist.py:437-449
     h = Hist(split("x", (1, 2, 3)), bin("y", 10, 0, 1), defs={"y": "x + 0.1"}, weight="sqrt(x)", filter="x > 2")
     assert h == pickle.loads(pickle.dumps(h))

@@ -164,3 +164,21 @@ def test_hot_window_placement():
     class K(object):
         window = {"bpb": 16}
     assert window_params(K, 1000) == [4000, 1000]
+
+
+def test_string_codes():
+    from histbook_b200.columns import StringCodes, is_stringlike
+    from histbook_b200.store import GroupInfo
+    sc = StringCodes()
+    a = sc.encode(["one", "two", "three", "two", "one"])
+    assert a.dtype == numpy.int64 and a[0] == a[4] and a[1] == a[3] and len(set(a.tolist())) == 3
+    b = sc.encode(numpy.array(["two", "zero"]))
+    assert b[0] == a[1] and b[1] not in a.tolist()                  # codes are stable across fills
+    assert str(sc.decode(a[2])) == "three"
+    assert is_stringlike(["x"]) and is_stringlike(numpy.array(["x"])) and not is_stringlike([1.0]) and not is_stringlike(numpy.zeros(3))
+    g = GroupInfo("groupby", False, False, "int64", True, None, codes=sc)
+    assert g.key_object(g.pattern("two")) == "two"
+    assert [str(g.key_object(p)) for p in g.sort_patterns([g.pattern(k) for k in ("two", "one", "zero", "three")])] == ["one", "three", "two", "zero"]
+    assert g.from_wire(g.to_wire(g.pattern("zero"))) == g.pattern("zero")
+    with pytest.raises(Exception):
+        g.pattern(3)
