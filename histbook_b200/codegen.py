@@ -491,13 +491,12 @@ class HistPlan(object):
         self.dest = []           # per term: list of destination columns
         self.strategy = "global"
         self.smem_f64_off = None   # byte offset of the [nbins][slots] float64 rows
-        self.smem_u32_off = None   # byte offset of the [nbins] u32 count block
         self.win_off = None        # "window" strategy: byte offset of the runtime-sized hot window region
         self.win_table_off = None  # byte offset of the per-row interval table (8 bytes per row)
         self.win_split = None      # the first `win_split` fixed axes form the row index, the rest the in-row index
         self.gcap = 0              # group histograms: slab slots [0, gcap) are privatised in shared memory
         self.skip_zero = False     # filter-derived weight: rows whose every term is exactly 0.0 are not accumulated
-        self.fx = False            # float64 terms privatised as exact 128-bit fixed point (hb_template.cuh HbFx)
+        self.fx_set = set()        # float64 terms kept as exact 128-bit fixed point (hb_template.cuh HbFx) instead of float64
         self.fx_index = {}         # term index -> index of its scale in p.win[2 + ...]
 
     def add_term(self, expr, col):
@@ -519,43 +518,25 @@ class HistPlan(object):
                 return t
         return None
 
+    # Shared-memory layout of a privatised histogram (or of its hot window), slot-major: for every float64 term one
+    # block of `nrows` float64 values (updated with atomicAdd(double) = LDS.64 + ATOMS.CAST.SPIN.64) or -- terms in
+    # `fx_set` -- four blocks of `nrows` u32 limbs (exact fixed point, native ATOMS.ADD); then `nrows` native u32
+    # counters for an unweighted count.  Slot-major because consecutive instructions of a warp then spread over all
+    # banks (c2: 127 Gev/s bin-major, 153 with hand-rolled 128-bit CAS pairs on bin-major rows, 156 slot-major).
     def row_layout(self, options=None):
-        """Shared-memory row of one bin: float64 slots (bin-major, so that two neighbouring slots can be
-        updated by ONE 128-bit CAS) and, separately, a native u32 counter.
+        """(term index per float64 slot, whether a u32 count block follows)."""
+        return list(self.f64_terms), self.count_term is not None
 
-        Returns (slots, count_u32): ``slots`` = term index per float64 slot (-1 = padding); an unweighted
-        count joins the float64 slots when that makes their number even (it is exact in float64 below 2^53)."""
-        # 128-bit CAS pairs (bin-major rows) were +7 % on c2 over two 64-bit atomicAdd on the same bin-major rows,
-        # but slot-major 64-bit atomicAdd beats both (c2: 127 bin-major / 153 CAS.128 / 156 slot-major Gev/s), and
-        # on small, contended tables the hand-rolled CAS.128 loop collapses (c3: 116 -> 42 Gev/s): off by default.
-        cas128 = (options or {}).get("cas128", False) and not self.fx
-        slots = list(self.f64_terms)
-        count_u32 = self.count_term is not None
-        if cas128 and count_u32 and len(slots) % 2 == 1:
-            slots.append(self.count_term)
-            count_u32 = False
-        if cas128 and len(slots) >= 2 and len(slots) % 2 == 1:
-            slots.append(-1)
-        return slots, count_u32
-
-    def strides(self, options, nrows_expr):
-        """(stride between bins, stride between the float64 slots of one bin), in doubles.  128-bit CAS pairs need
-        the two slots side by side (bin-major rows); separate 64-bit atomics are faster slot-major, where
-        consecutive instructions of a warp spread over all banks instead of every second one."""
-        opts = options or {}
-        cas128 = opts.get("cas128", False)
-        nslots = len(self.row_layout(options)[0])
-        if opts.get("soa", not cas128) and not cas128:
-            return "1", str(nrows_expr)
-        return str(nslots), "1"
+    def slot_units(self):
+        """Size of every float64 slot in 8-byte units per row: 1 (float64) or 2 (four u32 limbs)."""
+        return [2 if t in self.fx_set else 1 for t in self.f64_terms]
 
     @property
-    def slot_bytes(self):
-        return 16 if self.fx else 8
+    def fx(self):
+        return len(self.fx_set) > 0
 
     def row_bytes(self, options=None):
-        slots, count_u32 = self.row_layout(options)
-        return self.slot_bytes * len(slots) + (4 if count_u32 else 0)
+        return 8 * sum(self.slot_units()) + (4 if self.count_term is not None else 0)
 
     @property
     def nrows(self):
@@ -634,19 +615,27 @@ def plan_hist(prog, hid, h):
 
 def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
-    budget = int(options.get("smem_budget", (200 if (options.get("fx", False) or options.get("deterministic", False)) else 96) * 1024))
+    budget = int(options.get("smem_budget", (200 if (options.get("fx", False) is True or options.get("deterministic", False)) else 96) * 1024))
     forced = options.get("strategy", {})
+    # Which float64 terms are accumulated as exact fixed point (16 bytes per bin, native u32 atomics, ~55 instructions)
+    # rather than with float64 CAS loops (8 bytes, ~10 instructions, but ~3x the shared-memory wavefronts):
+    #   fx = False  none;  True  all of them (always so in deterministic mode);
+    #   "mix"       every second term of a histogram -- the CAS path saturates the LSU wavefront pipe with the issue
+    #               slots 20-40 % busy, the fixed-point path is issue-bound: mixing them loads both.
+    mode = True if options.get("deterministic", False) else options.get("fx", False)
     nfx = 0
     for hp in plans:
-        # exact fixed point instead of float64 CAS loops for every privatised float64 term (16 instead of 8 bytes);
-        # every such term gets a run-time scale in p.win[2 + index]
-        hp.fx = (bool(options.get("fx", False) or options.get("deterministic", False)) and not options.get("cas128", False)
-                 and len(hp.f64_terms) > 0
-                 and nfx + len(hp.f64_terms) <= MAX_WIN - 2)
-        if hp.fx:
-            for t in hp.f64_terms:
-                hp.fx_index[t] = nfx
-                nfx += 1
+        terms = list(hp.f64_terms)
+        if mode == "mix":
+            terms = terms[1::2]
+        elif not mode:
+            terms = []
+        if nfx + len(terms) > MAX_WIN - 2:
+            terms = []
+        hp.fx_set = set(terms)
+        for t in terms:
+            hp.fx_index[t] = nfx
+            nfx += 1
     for hp in plans:
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
@@ -663,10 +652,7 @@ def choose_strategies(plans, options):
         else:
             hp.strategy = "global"
         if hp.strategy == "smem":
-            # f64 block first (8-byte aligned), u32 block after
-            slots, count_u32 = hp.row_layout(options)
             hp.smem_f64_off = used
-            hp.smem_u32_off = used + hp.nrows * hp.slot_bytes * len(slots)
             used += (need + 15) // 16 * 16
     # Hot-window privatisation: ONE histogram that is too large for shared memory keeps the bins where most
     # events land in shared memory; the rest goes to global REDs.  The window is *ragged*: the leading fixed
@@ -705,7 +691,7 @@ def choose_strategies(plans, options):
     det = bool(options.get("deterministic", False))
     for hp in plans:
         if hp.strategy == "global" and not det:      # (deterministic mode: global histograms add to exact accumulators too)
-            hp.fx = False
+            hp.fx_set = set()
         if det and len(hp.f64_terms) > 0 and not hp.fx:
             raise UnsupportedError("deterministic mode: more than {0} float64 terms in one fill".format(MAX_WIN - 2))
     if not any(hp.strategy in ("smem", "window") for hp in plans) and not any(hp.fx for hp in plans):
@@ -874,63 +860,64 @@ def _group_lookup(hp, aux_slot):
     return out
 
 
-def _emit_row_adds(hp, options, rowptr, cntptr, indent, sstride="1", grow=None, gexact=None):
-    """C lines adding one event's terms to the shared-memory row of its bin.
+def _slot_ptr(hp, region, j, bidx, nrows, const=False):
+    """(C type, C expression) of the pointer to bin ``bidx`` of float64 slot ``j`` (j = number of slots: the u32 count
+    block) of a histogram whose shared-memory region starts at byte ``region`` and has ``nrows`` rows (int or C expr)."""
+    units = hp.slot_units()
+    before = 8 * sum(units[:j])
+    fx = j < len(units) and hp.f64_terms[j] in hp.fx_set
+    ctype_ = "double" if (j < len(units) and not fx) else "hb_u32"
+    if isinstance(nrows, int):
+        base = "hb_smem + %d" % (region + before * nrows)
+    else:
+        base = "hb_smem + %d + %d * %s" % (region, before, nrows)
+    c = "const " if const else ""
+    return ctype_, "(reinterpret_cast<%s%s*>(%s) + %s)" % (c, ctype_, base, bidx)
 
-    float64 layout: ``rowptr`` is a double* to the bin's first slot, slots ``sstride`` doubles apart.
-    Fixed-point layout (hp.fx): ``rowptr`` is a hb_u32* to limb 0 of slot 0 of the bin, ``sstride`` the number of
-    rows (limbs are that many words apart, slots four limbs apart); ``grow`` is the bin's row in the global
-    histogram, where a term that does not fit the fixed-point window is added directly."""
+
+def _emit_row_adds(hp, options, region, bidx, nrows, indent, grow=None, gexact=None):
+    """C lines adding one event's terms to the shared-memory row ``bidx`` of a histogram (region start ``region``,
+    ``nrows`` rows).  ``grow`` = the bin's row in the global histogram, ``gexact`` = its exact accumulators
+    (deterministic mode): where a term goes that does not fit its fixed-point window."""
     slots, count_u32 = hp.row_layout(options)
-    cas128 = options.get("cas128", False) and not hp.fx
+    det = bool(options.get("deterministic", False))
     out = []
 
     def val(t):
         return "1.0" if hp.terms[t] is None else hp.terms[t]
-    if hp.fx:
-        # stage k of every term before stage k+1 of any: the returning atomics overlap (hb_template.cuh)
-        for j, t in enumerate(slots):
-            out.append("%sconst double fv%d = %s;" % (indent, j, val(t)))
-            out.append("%sconst HbFx ff%d = hb_fx_decode(fv%d, p.win[%d]);" % (indent, j, j, 2 + hp.fx_index[t]))
-        for j, t in enumerate(slots):
-            out.append("%sconst hb_u32 fc%d = hb_fx_stage0(%s + %d * %s, %s, ff%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j))
-        for j, t in enumerate(slots):
-            out.append("%sconst hb_u64 fd%d = hb_fx_stage1(%s + %d * %s, %s, ff%d, fc%d);" % (indent, j, rowptr, 4 * j, sstride, sstride, j, j))
-        for j, t in enumerate(slots):
-            out.append("%shb_fx_stage2(%s + %d * %s, %s, ff%d, fd%d);" % (indent, rowptr, 4 * j, sstride, sstride, j, j))
-        det = bool(options.get("deterministic", False))
-        for j, t in enumerate(slots):
-            if det:
-                # does not fit the shared-memory field: the lower global window takes it, exactly
-                out.append("%sif (!ff%d.fits && !hb_fxg_add1(%s + %d, fv%d, p.win[%d] - HB_FXG_LOWER)) {" % (
-                    indent, j, gexact, 6 * j + 3, j, 2 + hp.fx_index[t]))
-            else:
-                out.append("%sif (!ff%d.fits) {" % (indent, j))
-            out.append("%s    atomicAdd(HB_FXMISS, 1u);" % indent)
-            for col in hp.dest[t]:
-                out.append("%s    hb_red_f64(%s + %d, fv%d);" % (indent, grow, col, j))
-            out.append("%s}" % indent)
-        if count_u32:
-            out.append("%shb_sadd_u32(%s, 1u);" % (indent, cntptr))
-        return out
-    j = 0
-    while j < len(slots):
-        if cas128 and j + 1 < len(slots):
-            if slots[j + 1] == -1:
-                out.append("%shb_sadd_f64(%s + %d, %s);" % (indent, rowptr, j, val(slots[j])))
-            else:
-                out.append("%shb_sadd_f64x2(%s + %d, %s, %s);" % (indent, rowptr, j, val(slots[j]), val(slots[j + 1])))
-            j += 2
-        else:
-            out.append("%shb_sadd_f64(%s + %d * %s, %s);" % (indent, rowptr, j, sstride, val(slots[j])))
-            j += 1
+    fxs = [(j, t) for j, t in enumerate(slots) if t in hp.fx_set]
+    # fixed point: stage k of every term before stage k+1 of any, so that the returning atomics overlap
+    for j, t in fxs:
+        out.append("%sconst double fv%d = %s;" % (indent, j, val(t)))
+        out.append("%sconst HbFx ff%d = hb_fx_decode(fv%d, p.win[%d]);" % (indent, j, j, 2 + hp.fx_index[t]))
+        out.append("%shb_u32* const fa%d = %s;" % (indent, j, _slot_ptr(hp, region, j, bidx, nrows)[1]))
+    for j, t in fxs:
+        out.append("%sconst hb_u32 fc%d = hb_fx_stage0(fa%d, %s, ff%d);" % (indent, j, j, nrows, j))
+    for j, t in enumerate(slots):
+        if t not in hp.fx_set:
+            out.append("%shb_sadd_f64(%s, %s);" % (indent, _slot_ptr(hp, region, j, bidx, nrows)[1], val(t)))
+    for j, t in fxs:
+        out.append("%sconst hb_u64 fd%d = hb_fx_stage1(fa%d, %s, ff%d, fc%d);" % (indent, j, j, nrows, j, j))
     if count_u32:
-        out.append("%shb_sadd_u32(%s, 1u);" % (indent, cntptr))
+        out.append("%shb_sadd_u32(%s, 1u);" % (indent, _slot_ptr(hp, region, len(slots), bidx, nrows)[1]))
+    for j, t in fxs:
+        out.append("%shb_fx_stage2(fa%d, %s, ff%d, fd%d);" % (indent, j, nrows, j, j))
+    for j, t in fxs:
+        if det:
+            # does not fit the shared-memory field: the lower global window takes it, exactly
+            out.append("%sif (!ff%d.fits && !hb_fxg_add1(%s + %d, fv%d, p.win[%d] - HB_FXG_LOWER)) {" % (
+                indent, j, gexact, 6 * j + 3, j, 2 + hp.fx_index[t]))
+        else:
+            out.append("%sif (!ff%d.fits) {" % (indent, j))
+        out.append("%s    atomicAdd(HB_FXMISS, 1u);" % indent)
+        for col in hp.dest[t]:
+            out.append("%s    hb_red_f64(%s + %d, fv%d);" % (indent, grow, col, j))
+        out.append("%s}" % indent)
     return out
 
 
-def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1", rowidx=None):
-    """C lines adding one shared-memory row to the global row ``row`` (float64 REDs, zero slots skipped); in
+def _emit_row_merge(hp, options, region, bidx, nrows, indent, rowidx=None):
+    """C lines adding shared-memory row ``bidx`` to the global row ``row`` (float64 REDs, zero slots skipped); in
     deterministic mode the fixed-point limbs go to the exact accumulators of global row ``rowidx`` as integers."""
     slots, count_u32 = hp.row_layout(options)
     det = bool(options.get("deterministic", False)) and hp.fx
@@ -938,24 +925,22 @@ def _emit_row_merge(hp, options, rowptr, cntexpr, indent, sstride="1", rowidx=No
     if det:
         out.append("%shb_u64* const grow = p.fxg[%d] + (hb_i64)(%s) * %d;" % (indent, hp.hid, rowidx, 6 * len(slots)))
     for j, t in enumerate(slots):
-        if t == -1:
-            continue
-        if det:
-            acc = "%s + %d * %s" % (rowptr, 4 * j, sstride)
-            out.append("%s{ const hb_u64 ml = ((hb_u64)(%s)[%s] << 32) | (%s)[0], mh = ((hb_u64)(%s)[3 * %s] << 32) | (%s)[2 * %s];" % (
-                indent, acc, sstride, acc, acc, sstride, acc, sstride))
+        ptr = _slot_ptr(hp, region, j, bidx, nrows, const=True)[1]
+        if t in hp.fx_set and det:
+            out.append("%s{ const hb_u32* const fa = %s;" % (indent, ptr))
+            out.append("%s  const hb_u64 ml = ((hb_u64)fa[%s] << 32) | fa[0], mh = ((hb_u64)fa[3 * %s] << 32) | fa[2 * %s];" % (indent, nrows, nrows, nrows))
             out.append("%s  hb_fxg_add128(grow + %d, ml, mh, (hb_u64)((hb_i64)mh >> 63)); }" % (indent, 6 * j))
             continue
-        if hp.fx:
-            out.append("%s{ const double v = hb_fx_read(%s + %d * %s, %s, p.win[%d] - 1075);" % (indent, rowptr, 4 * j, sstride, sstride, 2 + hp.fx_index[t]))
+        if t in hp.fx_set:
+            out.append("%s{ const double v = hb_fx_read(%s, %s, p.win[%d] - 1075);" % (indent, ptr, nrows, 2 + hp.fx_index[t]))
         else:
-            out.append("%s{ const double v = %s[%d * %s];" % (indent, rowptr, j, sstride))
+            out.append("%s{ const double v = *%s;" % (indent, ptr))
         out.append("%s  if (v != 0.0) {" % indent)
         for col in hp.dest[t]:
             out.append("%s    hb_red_f64(row + %d, v);" % (indent, col))
         out.append("%s  } }" % indent)
     if count_u32:
-        out.append("%s{ const hb_u32 c = %s;" % (indent, cntexpr))
+        out.append("%s{ const hb_u32 c = *%s;" % (indent, _slot_ptr(hp, region, len(slots), bidx, nrows, const=True)[1]))
         out.append("%s  if (c != 0u) { const double v = (double)c;" % indent)
         for col in hp.dest[hp.count_term]:
             out.append("%s    hb_red_f64(row + %d, v);" % (indent, col))
@@ -991,15 +976,6 @@ def _emit_global_adds(hp, options, rowidx, indent):
         else:
             out.append("%shb_red_f64(row + %d, %s);" % (indent, hp.dest[t][0], val))
     return out
-
-
-def _rowptr(hp, options, name, base_off, index, nrows_expr, const=False):
-    """(declaration line, slot stride expr) of the shared-memory row pointer of bin ``index``."""
-    c = "const " if const else ""
-    if hp.fx:
-        return ("%shb_u32* const %s = reinterpret_cast<%shb_u32*>(hb_smem + %d) + %s;" % (c, name, c, base_off, index), str(nrows_expr))
-    bstride, sstride = hp.strides(options, nrows_expr)
-    return ("%sdouble* const %s = reinterpret_cast<%sdouble*>(hb_smem + %d) + %s * %s;" % (c, name, c, base_off, index, bstride), sstride)
 
 
 def generate(spec, coltypes, options=None):
@@ -1084,10 +1060,8 @@ def generate(spec, coltypes, options=None):
             ev.append("    const bool inside = okw && wa < (we.y & 0xffffu);")
             ev.append("    if (inside) {")
             ev.append("        const int wb = (int)(we.x + wa);")
-            decl, sstride = _rowptr(hp, options, "wrow", hp.win_off, "wb", "p.win[1]")
-            ev.append("        " + decl)
-            ev.extend(_emit_row_adds(hp, options, "wrow", "reinterpret_cast<hb_u32*>(hb_smem + %d + p.win[1] * %d) + wb" % (hp.win_off, nf * hp.slot_bytes),
-                                     "        ", sstride, grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol),
+            ev.extend(_emit_row_adds(hp, options, hp.win_off, "wb", "p.win[1]", "        ",
+                                     grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol),
                                      gexact="(p.fxg[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, 6 * len(hp.f64_terms))))
             ev.append("    }")
             conds = ["okw", "!inside"]
@@ -1125,12 +1099,7 @@ def generate(spec, coltypes, options=None):
                 indent = "            "
             else:
                 ev.append("        const int srowi = bin;")
-            if nslots:
-                decl, sstride = _rowptr(hp, options, "srow", hp.smem_f64_off, "srowi", hp.nrows)
-                ev.append(indent + decl)
-            else:
-                sstride = "1"
-            ev.extend(_emit_row_adds(hp, options, "srow", "reinterpret_cast<hb_u32*>(hb_smem + %d) + srowi" % hp.smem_u32_off, indent, sstride,
+            ev.extend(_emit_row_adds(hp, options, hp.smem_f64_off, "srowi", hp.nrows, indent,
                                      grow="(p.hist[%d] + (hb_i64)srowi * %d)" % (hp.hid, hp.ncol),
                                      gexact="(p.fxg[%d] + (hb_i64)srowi * %d)" % (hp.hid, 6 * len(hp.f64_terms))))
             if hp.groups:
@@ -1149,10 +1118,7 @@ def generate(spec, coltypes, options=None):
         merge.append("// merge hist %d" % hp.hid)
         merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nrows)
         merge.append("    double* const row = p.hist[%d] + (hb_i64)b * %d;" % (hp.hid, hp.ncol))
-        nslots = len(hp.row_layout(options)[0])
-        decl, sstride = _rowptr(hp, options, "srow", hp.smem_f64_off, "b", hp.nrows, const=True)
-        merge.append("    " + decl)
-        merge.extend(_emit_row_merge(hp, options, "srow", "reinterpret_cast<const hb_u32*>(hb_smem + %d)[b]" % hp.smem_u32_off, "    ", sstride, rowidx="b"))
+        merge.extend(_emit_row_merge(hp, options, hp.smem_f64_off, "b", hp.nrows, "    ", rowidx="b"))
         merge.append("}")
 
     if window is not None:
@@ -1164,9 +1130,7 @@ def generate(spec, coltypes, options=None):
         merge.append("    for (unsigned wa = threadIdx.x & 31u; wa < (we.y & 0xffffu); wa += 32u) {")
         merge.append("        const int wb = (int)(we.x + wa);")
         merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
-        decl, sstride = _rowptr(hp, options, "wrow", hp.win_off, "wb", "p.win[1]", const=True)
-        merge.append("        " + decl)
-        merge.extend(_emit_row_merge(hp, options, "wrow", "reinterpret_cast<const hb_u32*>(hb_smem + %d + p.win[1] * %d)[wb]" % (hp.win_off, nf * hp.slot_bytes), "        ", sstride,
+        merge.extend(_emit_row_merge(hp, options, hp.win_off, "wb", "p.win[1]", "        ",
                                      rowidx="(hb_i64)wr * %d + (we.y >> 16) + wa" % hp.win_trail))
         merge.append("    }")
         merge.append("}")
@@ -1179,7 +1143,7 @@ def generate(spec, coltypes, options=None):
         winfo = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "rows": window.win_rows, "trail": window.win_trail,
                  "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"], "aux": naux, "table_off": window.win_table_off}
         naux += 1
-    k.fx_terms = [(hp.fx_index[t], hp.hid, t) for hp in plans if hp.fx for t in hp.f64_terms]
+    k.fx_terms = [(hp.fx_index[t], hp.hid, t) for hp in plans for t in hp.f64_terms if t in hp.fx_set]
     k.nfx = (1 + max(i for i, hid, t in k.fx_terms)) if k.fx_terms else 0
     if k.fx_terms:
         k.fx_aux = naux                 # aux slot of the device counter [terms that missed their fixed-point window]
@@ -1227,7 +1191,7 @@ def generate_range(spec, coltypes, options=None):
     prog = Program(spec, coltypes)
     plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
     choose_strategies(plans, options)
-    terms = [(hp, t) for hp in plans if hp.fx for t in hp.f64_terms]
+    terms = [(hp, t) for hp in plans for t in hp.f64_terms if t in hp.fx_set]
     if not terms:
         return None
     ev = list(prog.body)
