@@ -128,6 +128,35 @@ def _hist_copyonfill(self):
     return out
 
 
+def _hist_project(self, *axis):
+    """``Hist.project`` (histbook/proj.py:227-296).  When the bins live on the device and the histogram has no group
+    axes, the sum over the dropped axes runs there (hb_arena_project) and the result stays on the device -- a
+    projection of c5's 134 MB never crosses PCIe.  Everything else takes the reference's own path on a host copy."""
+    hb = _ref.load()
+    st = self.__dict__.get("_hb")
+    if st is None or st.groups or len(self._group) > 0 or st.host_valid or not st.dev_valid or st.arena is None:
+        return _originals["Hist.project"](self, *axis)
+    allaxis = self._group + self._fixed
+    axis = [x if isinstance(x, hb.axis.Axis) else self.axis[x] for x in axis]
+    for x in axis:
+        if x not in allaxis:
+            raise IndexError("no such axis: {0}".format(x))
+    if len(self._fixed) == 0 or len(self._fixed) > 8:
+        return _originals["Hist.project"](self, *axis)
+    keep = [x in axis for x in self._fixed]
+    outaxis = [x for x in allaxis if x in axis] + [x for x in self._profile]
+    out = self.__class__(*outaxis, weight=self._weightoriginal, filter=self._filteroriginal, defs=dict(self._defs),
+                         attachment=dict(self._attachment))
+    from histbook_b200.store import Store
+    shape = tuple(self._shape)
+    new = Store(out._shape, [], None)
+    assert tuple(out._shape) == tuple(t for t, k in zip(shape[:-1], keep) if k) + (shape[-1],)
+    new.arena = st.arena.project(shape[:-1], shape[-1], keep)
+    new.host, new.host_valid, new.dev_valid, new.nonempty = None, False, True, True
+    out.__dict__["_hb"] = new
+    return out
+
+
 # ----------------------------------------------------------------------------- install / uninstall
 
 def install():
@@ -140,13 +169,14 @@ def install():
     _originals.update({
         "Hist.fill": Hist.__dict__["fill"], "Book.fill": Book.__dict__["fill"],
         "Hist.copy": Hist.__dict__["copy"], "Hist.copyonfill": Hist.__dict__["copyonfill"],
-        "Hist.cleared": Hist.__dict__["cleared"],
+        "Hist.cleared": Hist.__dict__["cleared"], "Hist.project": hb.proj.Projectable.__dict__["project"],
     })
     Hist._content = property(_content_get, _content_set)
     Hist.fill = _hist_fill
     Book.fill = _book_fill
     Hist.copy = _hist_copy
     Hist.copyonfill = _hist_copyonfill
+    Hist.project = _hist_project
     _installed = True
 
 
@@ -163,6 +193,7 @@ def uninstall():
     Book.fill = _originals["Book.fill"]
     Hist.copy = _originals["Hist.copy"]
     Hist.copyonfill = _originals["Hist.copyonfill"]
+    del Hist.project                      # falls back to the inherited Projectable.project
     _installed = False
 
 

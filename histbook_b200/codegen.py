@@ -990,7 +990,7 @@ def generate(spec, coltypes, options=None):
         raise UnsupportedError("more than 32 input fields in one fill")
     # resident threads per SM stay near 1024 whatever the shared-memory footprint: the fixed-point adds are chains
     # of returning atomics and want warps to hide them
-    if smem <= 8 * 1024 and not any(hp.groups for hp in plans):
+    if 0 < smem <= 8 * 1024 and not any(hp.groups for hp in plans):
         # tiny tables (c1: 103 bins): the block merge -- every block REDs every non-zero bin into the same few
         # global addresses -- is what costs; 1024-thread blocks quarter the number of blocks
         # (c1 at 1e8 events: 751 -> 818 Gev/s, profiles/r01_sweeps.txt)

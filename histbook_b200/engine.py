@@ -62,6 +62,7 @@ SYMBOLS = {
     "hb_arena_write": (_I, [_P, _I64, _I64, _P]),
     "hb_arena_axpy": (_I, [_P, _P, ctypes.c_double]),
     "hb_arena_scale": (_I, [_P, ctypes.c_double]),
+    "hb_arena_project": (_I, [_P, _I, ctypes.POINTER(_I64), _I, ctypes.POINTER(ctypes.c_int32), _PP]),
     "hb_arena_ptr": (_P, [_P]),
     "hb_arena_size": (_I64, [_P]),
     "hb_fill": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
@@ -266,6 +267,15 @@ class Arena(object):
 
     def scale(self, alpha):
         check(lib().hb_arena_scale(self._h, float(alpha)))
+
+    def project(self, shape, ncol, keep):
+        """Sum over the fixed axes with keep[k] false (Hist.project on the device); returns a new Arena."""
+        shape = [int(x) for x in shape]
+        arr = (ctypes.c_int64 * len(shape))(*shape)
+        karr = (ctypes.c_int32 * len(shape))(*[1 if k else 0 for k in keep])
+        out = ctypes.c_void_p()
+        check(lib().hb_arena_project(self._h, len(shape), arr, int(ncol), karr, ctypes.byref(out)))
+        return Arena(_handle=out)
 
     def marginals(self, shape, ncol, col):
         """Per-axis marginals of |content[..., col]| (list of arrays), computed on the device."""

@@ -106,6 +106,10 @@ int hb_arena_read(const hb_arena* a, int64_t offset, int64_t count, double* host
 int hb_arena_write(hb_arena* a, int64_t offset, int64_t count, const double* host_in);
 int hb_arena_axpy(hb_arena* dst, const hb_arena* src, double alpha);   /* dst += alpha * src */
 int hb_arena_scale(hb_arena* dst, double alpha);                       /* dst *= alpha */
+/* Hist.project (histbook/proj.py:227-296) on the device: sum the content over the fixed axes with keep[k] == 0.
+ * `shape` = bins per fixed axis (ndim <= 8), ncol = size of the last (column) dimension, which is always kept.
+ * *out is a new arena of prod(kept shape) * ncol doubles. */
+int hb_arena_project(const hb_arena* src, int ndim, const int64_t* shape, int ncol, const int32_t* keep, hb_arena** out);
 void* hb_arena_ptr(const hb_arena* a);                   /* device pointer (for NCCL / DLPack wrapping) */
 int64_t hb_arena_size(const hb_arena* a);
 
@@ -146,7 +150,7 @@ void* hb_keyset_ptr(const hb_keyset* ks);                /* device table, passed
 int hb_keyset_read(const hb_keyset* ks, uint64_t* keys_out, int max_keys, int* nkeys, int* overflowed);
 
 /* utilities ---------------------------------------------------------------------------------------------- */
-int hb_flush_l2(void);                                   /* overwrite a buffer larger than L2 (benchmark hygiene) */
+int hb_flush_l2(void);                                   /* overwrite a buffer larger than L2, then stream another one through it (benchmark hygiene) */
 int hb_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
 int hb_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
 int hb_device_malloc(size_t bytes, void** out);

@@ -150,6 +150,41 @@ def test_groupby_strings():                                   # tests/test_hist.
     assert numpy.all(both._content["qcd"][:, 0] >= 2 * h._content["qcd"][:, 0])
 
 
+def test_project_on_the_device():                             # histbook/proj.py:227-296
+    rs = numpy.random.RandomState(11)
+    n = 200000
+    x, y, z, w = rs.normal(0, 1, n), rs.normal(0, 1, n), rs.normal(0, 1, n), rs.uniform(0.5, 1.5, n)
+    h = Hist(bin("x", 20, -3, 3), bin("y", 15, -3, 3), split("z", (-1, 0, 1)), weight="w")
+    h.fill(x=x, y=y, z=z, w=w)
+    full = histbook_b200.peek(h).copy()                        # (23, 18, 6, 2)
+    for keep, axes in ((("x",), (1, 2)), (("y", "z"), (0,)), ((0, 2), (1,)), ((), (0, 1, 2)), (("x", "y", "z"), ())):
+        p = h.project(*keep)
+        st = p.__dict__["_hb"]
+        assert st.dev_valid and not st.host_valid              # computed and kept on the device
+        exp = numpy.sum(full, axes)
+        bound = numpy.sum(numpy.abs(full), axes)
+        got = p._content
+        assert got.shape == exp.shape == tuple(p._shape)
+        assert numpy.all(numpy.abs(got - exp) <= 1e-12 * bound)
+    # the projection is an ordinary histogram: it can be filled further and tabulated
+    p = h.project("x")
+    p.fill(x=x[:1000], w=w[:1000])
+    assert abs(p._content[:, 0].sum() - (w.sum() + w[:1000].sum())) <= 1e-9
+    # unweighted counts stay exact; profile columns are carried along
+    c = Hist(bin("x", 50, -3, 3), cut("y > 0"), profile("z"))
+    c.fill(x=x, y=y, z=z)
+    q = c.project("x")
+    assert q.__dict__["_hb"].dev_valid and not q.__dict__["_hb"].host_valid
+    ref = histbook_b200.peek(c).sum(axis=1)
+    assert numpy.array_equal(q._content[:, 2], ref[:, 2]) and q._content[:, 2].sum() == n
+    assert numpy.allclose(q._content[:, :2], ref[:, :2], rtol=1e-12, atol=1e-12)
+    assert len(q.table()) == 53
+    # with group axes the reference's own (host) path is taken
+    g = Hist(groupby("c"), bin("x", 5, -3, 3), bin("y", 4, -3, 3))
+    g.fill(c=rs.randint(0, 3, 1000), x=x[:1000], y=y[:1000])
+    assert sum(v.sum() for v in g.project("c", "x")._content.values()) == 1000
+
+
 def test_pickle_and_json_roundtrip():                         # tests/test_hist.py:437-449
     h = Hist(split("x", (1, 2, 3)), bin("y", 10, 0, 1), defs={"y": "x + 0.1"}, weight="sqrt(x)", filter="x > 2")
     assert h == pickle.loads(pickle.dumps(h))
