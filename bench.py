@@ -287,9 +287,35 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def api_target(workload, spec):
+    """What a user would call: the histbook Hist (or Book) of the workload with the device backend installed
+    (``import histbook_b200``) -- or, where the histbook package itself is not importable, the spec-level driver that
+    Hist.fill / Book.fill delegate to.  Returns (fill(host_columns), read_result() -> bytes read, description)."""
+    from histbook_b200 import _ref, fillable
+    if _ref.available():
+        import histbook_b200
+        histbook_b200.install()
+        hb = _ref.load()
+        env = dict((n, getattr(hb, n)) for n in ("Hist", "Book", "bin", "intbin", "split", "cut", "profile", "groupby", "groupbin"))
+        hists = [eval(src, dict(env)) for src in bench_cpu.load_case(bench_cpu.WORKLOADS[workload][0])["hists"]]
+        target = hists[0] if len(hists) == 1 else hb.Book(dict(("h%03d" % i, h) for i, h in enumerate(hists)))
+
+        def read():
+            total = 0
+            for h in hists:
+                c = h._content                      # device -> host copy, as proj/export/vega would trigger
+                total += c.nbytes if isinstance(c, numpy.ndarray) else sum(v.nbytes for v in c.values())
+            return total
+        return (lambda cols: target.fill(**cols)), read, "histbook %s.fill(**host numpy columns) + ._content (backend installed by `import histbook_b200`)" % type(target).__name__
+    filler = fillable.SpecFill(spec)
+
+    def read():
+        return sum(c.nbytes for c in filler.contents() if isinstance(c, numpy.ndarray))
+    return filler.fill, read, "SpecFill.fill(host numpy columns) + contents()"
+
+
 def run_e2e(torch, dist, workload, spec, n, rank, world, device, args):
     """Same metric through the user-facing call with host buffers: Hist.fill(x=<numpy>, ...) then read hist content."""
-    from histbook_b200 import fillable
     host = {}
     h2d = 0
     src = device_columns(torch, workload, n, 777 + rank, device)
@@ -300,7 +326,7 @@ def run_e2e(torch, dist, workload, spec, n, rank, world, device, args):
         h2d += pinned.numel() * pinned.element_size()
     del src
     torch.cuda.empty_cache()
-    filler = fillable.SpecFill(spec)
+    fill, read, api = api_target(workload, spec)
     steps = max(1, min(args.steps, 3))
     d2h = 0
     for it in range(1 + steps):
@@ -309,9 +335,8 @@ def run_e2e(torch, dist, workload, spec, n, rank, world, device, args):
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-        filler.fill(host)
-        out = filler.contents()                     # device -> host read of the step's result
-        d2h = sum(c.nbytes for c in out if isinstance(c, numpy.ndarray))
+        fill(host)
+        d2h = read()                                # device -> host read of the step's result
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     if world > 1:
@@ -319,7 +344,8 @@ def run_e2e(torch, dist, workload, spec, n, rank, world, device, args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     return {"value": world * n * steps / sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "events_per_gpu_per_step": n, "api": "SpecFill.fill(host numpy columns) + contents()"}
+            "steps": steps, "events_per_gpu_per_step": n, "api": api,
+            "h2d_gbs_per_gpu": h2d * steps / sec / 1e9, "bound": "PCIe host->device copy of the columns"}
 
 
 def run_extra(torch, dist, workload, device, hbm):
