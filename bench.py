@@ -194,7 +194,7 @@ def run_gpu(args):
 
     workload = args.workload
     case_name, default_n, bytes_per_event, _ = bench_cpu.WORKLOADS[workload]
-    n = int(args.events) if args.events else default_n          # per GPU (weak scaling: every rank gets the full workload size)
+    n = int(float(args.events)) if args.events else default_n          # per GPU (weak scaling: every rank gets the full workload size)
     spec = bench_cpu.load_case(case_name)["spec"]
     cols = device_columns(torch, workload, n, 12345 + rank, device)
     filler = fillable.SpecFill(spec)
@@ -236,7 +236,7 @@ def run_gpu(args):
     # ---- end to end through the public API with HOST (pinned) buffers: H2D of every column + D2H of the result per step
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, dist, workload, spec, n if args.e2e_events is None else int(args.e2e_events), rank, world, device, args)
+        e2e = run_e2e(torch, dist, workload, spec, n if args.e2e_events is None else int(float(args.e2e_events)), rank, world, device, args)
 
     extras = {}
     if rank == 0 and world == 1 and args.extras:
