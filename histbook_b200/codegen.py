@@ -893,9 +893,10 @@ def _emit_row_adds(hp, options, region, bidx, nrows, indent, grow=None, gexact=N
         out.append("%shb_u32* const fa%d = %s;" % (indent, j, _slot_ptr(hp, region, j, bidx, nrows)[1]))
     for j, t in fxs:
         out.append("%sconst hb_u32 fc%d = hb_fx_stage0(fa%d, %s, ff%d);" % (indent, j, j, nrows, j))
+XX
     for j, t in enumerate(slots):
         if t not in hp.fx_set:
-            out.append("%shb_sadd_f64(%s, %s);" % (indent, _slot_ptr(hp, region, j, bidx, nrows)[1], val(t)))
+            out.append("%s%s(%s, %s);" % (indent, add, _slot_ptr(hp, region, j, bidx, nrows)[1], val(t)))
     for j, t in fxs:
         out.append("%sconst hb_u64 fd%d = hb_fx_stage1(fa%d, %s, ff%d, fc%d);" % (indent, j, j, nrows, j, j))
     if count_u32:
