@@ -893,7 +893,9 @@ def _emit_row_adds(hp, options, region, bidx, nrows, indent, grow=None, gexact=N
         out.append("%shb_u32* const fa%d = %s;" % (indent, j, _slot_ptr(hp, region, j, bidx, nrows)[1]))
     for j, t in fxs:
         out.append("%sconst hb_u32 fc%d = hb_fx_stage0(fa%d, %s, ff%d);" % (indent, j, j, nrows, j))
-XX
+    # float64 slots: CAS loop (atomicAdd); "exch" = take / put back with ATOMS.EXCH.64 + STS.64 -- fewer wavefronts on
+    # paper, slower in every measurement (c2 129 vs 156 Gev/s, c3 88 vs 116, c4 collapses: lanes that meet the marker spin)
+    add = "hb_sadd_f64_exch" if options.get("f64_atomic", "cas") == "exch" else "hb_sadd_f64"
     for j, t in enumerate(slots):
         if t not in hp.fx_set:
             out.append("%s%s(%s, %s);" % (indent, add, _slot_ptr(hp, region, j, bidx, nrows)[1], val(t)))
