@@ -149,9 +149,11 @@ def measure(torch, dist, filler, cols, steps, warmup, world, merge):
     """warmup + timed steps; device time by CUDA events on the launch stream, max over ranks."""
     from histbook_b200 import fillable
     launches = 0
+    finish = getattr(merge, "finish", lambda: None)
     for _ in range(warmup):
         filler.fill(cols)
         merge()
+    finish()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -162,6 +164,7 @@ def measure(torch, dist, filler, cols, steps, warmup, world, merge):
         filler.fill(cols)
         launches += fillable.last_stats.get("launches", 0) + fillable.last_stats.get("keys_launches", 0)
         merge()
+    finish()                                       # every step's merge has completed before the clock stops
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -201,21 +204,50 @@ def run_gpu(args):
     filler.fill(dict((k, v[:4096]) for k, v in cols.items()))     # compile + first touch (excluded)
     filler.clear()
 
-    # rank merge = Hist.__add__ over ranks: all-reduce for small contents, reduce-scatter for large ones
-    merged = {}
+    # rank merge = Hist.__add__ over ranks: all-reduce for small contents, reduce-scatter for large ones.
+    # One merge per step.  The fill stream only snapshots the bins (device copy, in order with the kernels); the
+    # collective runs on a side stream and overlaps the next step's fill; two snapshot buffers alternate, and
+    # merge.finish() joins the side stream before the timed region ends.
+    merged, snaps, freed = {}, {}, {}
+    side = torch.cuda.Stream(device=device) if world > 1 else None
+    counter = [0]
 
     def merge():
         if world == 1:
             return
+        parity = counter[0] & 1
+        counter[0] += 1
+        cur = torch.cuda.current_stream()
+        if parity in freed:
+            cur.wait_event(freed[parity])               # the collective that read this snapshot two steps ago is done
+        items = []
         for i, arena in enumerate(filler.arenas()):
             t = arena.as_tensor()
-            if t.numel() * 8 >= (8 << 20) and t.numel() % world == 0:
-                out = merged.setdefault(i, torch.empty(t.numel() // world, device=device, dtype=torch.float64))
-                dist.reduce_scatter_tensor(out, t)
-            else:
-                out = merged.setdefault(i, torch.empty_like(t))
-                out.copy_(t)
-                dist.all_reduce(out)
+            snap = snaps.get((i, parity))
+            if snap is None or snap.numel() != t.numel():
+                snap = snaps[(i, parity)] = torch.empty_like(t)
+            snap.copy_(t)
+            items.append((i, snap))
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            for i, snap in items:
+                if snap.numel() * 8 >= (8 << 20) and snap.numel() % world == 0:
+                    out = merged.get(i)
+                    if out is None or out.numel() != snap.numel() // world:
+                        out = merged[i] = torch.empty(snap.numel() // world, device=device, dtype=torch.float64)
+                    dist.reduce_scatter_tensor(out, snap)
+                else:
+                    dist.all_reduce(snap)
+            done = torch.cuda.Event()
+            done.record(side)
+            freed[parity] = done
+
+    def finish():
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+    merge.finish = finish
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -269,7 +301,7 @@ def run_gpu(args):
             "config": {"workload": "%s: %s" % (workload, bench_cpu.DESCRIPTION[workload]), "events_per_gpu_per_step": n,
                        "bytes_per_event": bytes_per_event, "l2": "inputs (%.1f GB per GPU) larger than L2" % (n * bytes_per_event / 1e9)
                        if n * bytes_per_event > 256e6 else "L2 flushed between steps is NOT done; inputs fit L2",
-                       "rank_merge": "none (1 GPU)" if world == 1 else "NCCL all-reduce / reduce-scatter of the bin contents every step",
+                       "rank_merge": "none (1 GPU)" if world == 1 else "NCCL all-reduce / reduce-scatter of the bin contents every step, on a side stream overlapping the next step's fill; all merges complete inside the timed region",
                        "kernel": {"regs": stats.get("regs"), "smem_bytes": stats.get("smem_bytes"), "grid": stats.get("grid"),
                                   "blocks_per_sm": stats.get("blocks_per_sm"), "hot_window": stats.get("window"),
                                   "hot_window_coverage_est": stats.get("window_coverage")}},
