@@ -615,36 +615,50 @@ def plan_hist(prog, hid, h):
 
 def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
-    budget = int(options.get("smem_budget", (200 if (options.get("fx", False) is True or options.get("deterministic", False)) else 96) * 1024))
+    det = bool(options.get("deterministic", False))
     forced = options.get("strategy", {})
-    # Which float64 terms are accumulated as exact fixed point (16 bytes per bin, native u32 atomics, ~55 instructions)
-    # rather than with float64 CAS loops (8 bytes, ~10 instructions, but ~3x the shared-memory wavefronts):
-    #   fx = False  none;  True  all of them (always so in deterministic mode);
-    #   "mix"       every second term of a histogram -- the CAS path saturates the LSU wavefront pipe with the issue
-    #               slots 20-40 % busy, the fixed-point path is issue-bound: mixing them loads both.
-    mode = True if options.get("deterministic", False) else options.get("fx", False)
-    nfx = 0
-    for hp in plans:
-        terms = list(hp.f64_terms)
-        if mode == "mix":
-            terms = terms[1::2]
-        elif not mode:
-            terms = []
-        if nfx + len(terms) > MAX_WIN - 2:
-            terms = []
-        hp.fx_set = set(terms)
-        for t in terms:
-            hp.fx_index[t] = nfx
-            nfx += 1
+    # Which float64 terms are accumulated as exact fixed point (16 bytes per bin, native u32 atomics, ~55 instructions,
+    # no retries) rather than with float64 CAS loops (8 bytes, ~10 instructions, but several times the shared-memory
+    # wavefronts, and one more attempt for every other lane of the warp that is in the same bin):
+    #   fx = False  none;  True  all (always so in deterministic mode);  "mix"  every second term;  [slots]  explicit;
+    #   "auto" (default), statically privatised histograms of small books only:
+    #          tables up to 1024 rows: all terms   (Hist(bin("x",100), weight="w"): 55 -> 198 Gev/s),
+    #          larger ones: all but the first      (c3: 116 -> 152 Gev/s; 53x53 weighted: 154 -> 183; all: 167),
+    #          hot windows: all but the first as well, but only in the "dense" variant of the kernel, which the fill
+    #          driver picks when the smaller window still holds 95 % of the events (c2: 156 -> 171 Gev/s although the
+    #          window shrinks from 12.7 k to 8.5 k bins; all terms: the window halves and the gain is gone).
+    #          The CAS path saturates the LSU wavefront pipe with the issue slots 20-40 % busy, the fixed-point path is
+    #          issue-bound: on larger tables a mix loads both pipes.  Measurements: profiles/r01_sweeps.txt.
+    mode = True if det else options.get("fx", "auto")
+    budget = int(options.get("smem_budget", (200 if (mode is True) else 96) * 1024))
     for hp in plans:
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
         hp.gcap = int(options.get("group_slots", 16)) if hp.groups else 0
+    for hp in plans:
+        terms = list(hp.f64_terms)
+        if mode == "mix":
+            terms = terms[1::2]
+        elif mode == "auto":
+            terms = terms if hp.nrows <= 1024 else terms[1:]
+        elif isinstance(mode, (list, tuple)):          # explicit slot numbers (tuning)
+            terms = [t for j, t in enumerate(terms) if j in mode]
+        elif not mode:
+            terms = []
+        hp.fx_set = set(terms)
+    total = sum(len(hp.fx_set) for hp in plans)
+    if (mode == "auto" and total > int(options.get("fx_auto_max_terms", 8))) or (mode is not True and total > MAX_WIN - 2):
+        # big books (c4: 40 float64 terms): the fixed-point code costs more registers and instructions than it saves
+        for hp in plans:
+            hp.fx_set = set()
     order = sorted(plans, key=lambda hp: hp.smem_bytes(options))
-    used = 16 if nfx else 0           # word 0: how many terms did not fit their fixed-point window (HB_FXMISS)
+    used = 16 if any(hp.fx_set for hp in plans) else 0     # word 0: how many terms missed their fixed-point window (HB_FXMISS)
     for hp in order:
         want = forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*")))
         need = hp.smem_bytes(options)
+        if mode == "auto" and hp.fx_set and (want == "smem" or want is None) and used + need > budget:
+            hp.fx_set = set()                          # fits as float64 only
+            need = hp.smem_bytes(options)
         if want == "global":
             hp.strategy = "global"
         elif (want == "smem" or want is None) and used + need <= budget:
@@ -688,12 +702,21 @@ def choose_strategies(plans, options):
             window.win_table_off = used
             used += (window.win_rows * 8 + 15) // 16 * 16
             window.win_off = used
-    det = bool(options.get("deterministic", False))
+    nfx = 0
     for hp in plans:
         if hp.strategy == "global" and not det:      # (deterministic mode: global histograms add to exact accumulators too)
             hp.fx_set = set()
-        if det and len(hp.f64_terms) > 0 and not hp.fx:
-            raise UnsupportedError("deterministic mode: more than {0} float64 terms in one fill".format(MAX_WIN - 2))
+        if hp.strategy == "window" and mode == "auto":
+            # two variants, chosen at fill time from the coverage the window reaches (fillable.fill_hists)
+            hp.fx_set = set(hp.f64_terms[1:]) if options.get("win_dense", False) else set()
+        if det and len(hp.f64_terms) > 0 and len(hp.fx_set) != len(hp.f64_terms):
+            raise UnsupportedError("deterministic mode: every float64 term must be fixed point")
+        for t in hp.f64_terms:
+            if t in hp.fx_set:
+                hp.fx_index[t] = nfx                 # its run-time scale lives in p.win[2 + index]
+                nfx += 1
+    if nfx > MAX_WIN - 2:
+        raise UnsupportedError("more than {0} fixed-point terms in one fill".format(MAX_WIN - 2))
     if not any(hp.strategy in ("smem", "window") for hp in plans) and not any(hp.fx for hp in plans):
         used = 0
     return used, window
@@ -998,7 +1021,7 @@ def generate(spec, coltypes, options=None):
         # global addresses -- is what costs; 1024-thread blocks quarter the number of blocks
         # (c1 at 1e8 events: 751 -> 818 Gev/s, profiles/r01_sweeps.txt)
         dthreads, dblocks = 1024, 1
-    elif smem <= 56 * 1024:
+    elif smem <= 37 * 1024:
         dthreads, dblocks = THREADS, 2
     elif smem <= 113 * 1024:
         dthreads, dblocks = 512, 2
@@ -1008,13 +1031,13 @@ def generate(spec, coltypes, options=None):
     minblocks = int(options.get("min_blocks", dblocks))
     smem_cap = smem
     if window is not None:
-        # one resident block of 1024 threads per SM that owns 200 KB of the SM's shared memory: with per-row
-        # intervals that holds 99.7 % of c2's events (12.7 k bins); measured 156 Gev/s vs 152 for two 512-thread
-        # blocks with 100 KB each (94 %) and 148 for four 256-thread blocks with 56 KB (80 %)
-        # (profiles/r01_sweeps.txt).
+        # one resident block of 1024 threads per SM that owns 226 of the SM's 227 KB of shared memory: with per-row
+        # intervals and float64 rows that holds 99.9 % of c2's events (14.3 k bins); measured (float64 CAS variant, 200 KB)
+        # 156 Gev/s vs 152 for two 512-thread blocks with 100 KB each (94 %) and 148 for four 256-thread blocks with
+        # 56 KB (80 %); the dense variant gains another 1 % from 200 -> 226 KB (profiles/r01_sweeps.txt).
         threads = int(options.get("win_threads", 1024))
         minblocks = int(options.get("win_min_blocks", 1))
-        smem_cap = int(options.get("win_smem", 200 * 1024))
+        smem_cap = int(options.get("win_smem", 226 * 1024))
         if smem_cap - smem < 4096:
             window.strategy, window = "global", None
             smem_cap = smem
@@ -1040,7 +1063,10 @@ def generate(spec, coltypes, options=None):
             ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
             conds = ["okg", "slot >= 0"] + conds
         conds = ["live"] + conds
-        pair = (hp.strategy in ("global", "window") and options.get("pair_red", True) and not options.get("deterministic", False)
+        # (lane pairing is for histograms whose every event is a global RED; the few lanes that fall outside a hot
+        # window are cheaper as two predicated REDs each than as a warp-wide exchange -- unless asked for: win_pair)
+        pair = ((hp.strategy == "global" or (hp.strategy == "window" and options.get("win_pair", not options.get("win_dense", False))))
+                and options.get("pair_red", True) and not options.get("deterministic", False)
                 and hp.ncol == 2 and len(hp.terms) == 2
                 and sorted(hp.dest[0] + hp.dest[1]) == [0, 1])
         outside = ""
