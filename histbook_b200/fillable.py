@@ -49,6 +49,7 @@ class Plan(object):
                     self.groupby_fields[g[2][1]] = hbspec.tree_key(g)
         self.string_codes = {}      # field name -> columns.StringCodes (created at the first string-valued fill)
         self.fx_scales = {}         # dtype signature -> fixed-point scale per term (from the pilot), see _fx_scales
+        self.fx_sample = {}         # dtype signature -> events the pilot of fx_scales[signature] looked at
         self.fx_stat = None         # device counter: terms that missed their fixed-point window (all fills so far)
         self.fx_seen = 0            # ... its value when last looked at
         self.fx_last = None         # (signature, events, fills) since the miss counter was last looked at
@@ -104,9 +105,15 @@ def _fx_scales(plan, sig, kern, rng, rprog, cols, length):
             if events > 0 and missed > FX_MISS_REPILOT * events:
                 plan.fx_scales.pop(last_sig, None)
             plan.fx_last = None
+    # (a pilot that saw only a sliver of data -- a first fill of a few thousand events -- is repeated once a fill
+    #  brings four times as much, until it has seen PILOT_EVENTS)
+    sample = plan.fx_sample.get(sig, 0)
+    if sig in plan.fx_scales and sample < PILOT_EVENTS and min(length, PILOT_EVENTS) >= 4 * max(sample, 1):
+        plan.fx_scales.pop(sig)
     if sig not in plan.fx_scales:
         maxima = engine.DeviceBuffer(numpy.zeros(max(rng.nfx, 2), dtype=numpy.uint32))
         m = min(length, PILOT_EVENTS)
+        plan.fx_sample[sig] = m
         if m > 0:
             engine.fill(rprog, _abi_columns(rng, cols), m, [], aux=[maxima.ptr])
         biased = maxima.read(numpy.uint32)[:rng.nfx].astype(numpy.int64)
