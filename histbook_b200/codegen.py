@@ -613,6 +613,13 @@ def plan_hist(prog, hid, h):
     return hp
 
 
+def _unroll(plans, options):
+    """How the four events a thread owns per tile are laid out in code: 4 = vector loads + four inlined copies of the event
+    function; 1 = vector loads, one copy in a loop; 0 = one copy, one coalesced scalar load per column and event (big
+    books: c4's 64 histograms are 600 KB of SASS and 110 registers when unrolled, 200 KB and 60 registers this way)."""
+    return int(options.get("unroll", 0 if len(plans) > 16 else 4))
+
+
 def choose_strategies(plans, options):
     """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
     det = bool(options.get("deterministic", False))
@@ -630,7 +637,9 @@ def choose_strategies(plans, options):
     #          The CAS path saturates the LSU wavefront pipe with the issue slots 20-40 % busy, the fixed-point path is
     #          issue-bound: on larger tables a mix loads both pipes.  Measurements: profiles/r01_sweeps.txt.
     mode = True if det else options.get("fx", "auto")
-    budget = int(options.get("smem_budget", (200 if (mode is True) else 96) * 1024))
+    # (statically privatised tables share 96 KB so that two blocks fit an SM; all-fixed-point kernels and big books run one
+    #  1024-thread block per SM and may take 200 KB)
+    budget = int(options.get("smem_budget", (200 if (mode is True or _unroll(plans, options) == 0) else 96) * 1024))
     for hp in plans:
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
@@ -647,8 +656,11 @@ def choose_strategies(plans, options):
             terms = []
         hp.fx_set = set(terms)
     total = sum(len(hp.fx_set) for hp in plans)
-    if (mode == "auto" and total > int(options.get("fx_auto_max_terms", 8))) or (mode is not True and total > MAX_WIN - 2):
-        # big books (c4: 40 float64 terms): the fixed-point code costs more registers and instructions than it saves
+    big = _unroll(plans, options) == 0
+    if (mode == "auto" and total > int(options.get("fx_auto_max_terms", MAX_WIN - 2 if big else 8))) or (mode is not True and total > MAX_WIN - 2):
+        # middle-sized books: the fixed-point code costs more registers and instructions than it saves while the
+        # event function is unrolled four times; big books run one event at a time (see _unroll) and take it again
+        # (c4, 40 float64 terms on 50..100-bin axes: 5.2 -> 5.9 Gev/s from the single copy, 6.4 with fixed point)
         for hp in plans:
             hp.fx_set = set()
     order = sorted(plans, key=lambda hp: hp.smem_bytes(options))
@@ -761,7 +773,7 @@ def _loadtype(dtype):
     return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
 
 
-def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False):
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False, unroll=4):
     """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
     over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
     takes the scalar path), shared-memory zeroing before and block merge after."""
@@ -803,6 +815,21 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
                 for slot, dtype in vcols]
 
     def events(suffix, indent):
+        if unroll == 1:
+            # big books: one copy of the event code instead of four (c4: 600 KB of SASS thrash the instruction
+            # cache); the four loaded values are picked with selects so that they stay in registers
+            out = ["#pragma unroll 1", "%sfor (int k = 0; k < 4; ++k) {" % indent]
+            args = []
+            for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+                if is_scalar:
+                    args.append(_colarg(slot, dtype, is_scalar, None))
+                else:
+                    v = "v%d%s" % (slot, suffix)
+                    out.append("%s    const %s e%d = k == 0 ? %s[0] : (k == 1 ? %s[1] : (k == 2 ? %s[2] : %s[3]));" % (indent, _loadtype(dtype), slot, v, v, v, v))
+                    args.append(_colarg(slot, dtype, is_scalar, "e%d" % slot))
+            out.append("%s    hb_event(p, hb_smem, true%s);" % (indent, "".join(", " + a for a in args)))
+            out.append("%s}" % indent)
+            return out
         out = ["#pragma unroll", "%sfor (int k = 0; k < 4; ++k) {" % indent]
         out.append("%s    hb_event(p, hb_smem, true%s);" % (indent, "".join(
             ", " + _colarg(slot, dtype, is_scalar, "v%d%s[k]" % (slot, suffix)) for slot, (name, dtype, is_scalar) in enumerate(prog.cols))))
@@ -845,6 +872,13 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
         src.append("        full = nfull;")
         src.append("#pragma unroll")
         src.append("        for (int k = 0; k < 4; ++k) { %s }" % " ".join("v%d[k] = v%dn[k];" % (slot, slot) for slot, dtype in vcols))
+        src.append("    }")
+    elif unroll == 0:
+        # very big books: ONE copy of the event code, one 8-byte (or narrower) coalesced load per column and event --
+        # the 4-event vectors alone would hold 8 registers per column through the whole event function
+        src.append("    for (hb_i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {")
+        src.append("        const hb_i64 first = tile * HB_TILE;")
+        src.extend(x.replace("for (int k = 0; k < 4; ++k) {", "_Pragma(\"unroll 1\") for (int k = 0; k < 4; ++k) {") for x in tail("        "))
         src.append("    }")
     else:
         src.append("    for (hb_i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {")
@@ -1025,6 +1059,8 @@ def generate(spec, coltypes, options=None):
         dthreads, dblocks = THREADS, 2
     elif smem <= 113 * 1024:
         dthreads, dblocks = 512, 2
+    elif _unroll(plans, options) == 0:
+        dthreads, dblocks = 1024, 1           # the one-event-at-a-time code of big books stays within 64 registers
     else:
         dthreads, dblocks = 512, 1
     threads = int(options.get("threads", dthreads))
@@ -1187,7 +1223,8 @@ def generate(spec, coltypes, options=None):
         for hp in plans:
             if hp.fx:
                 k.exact[hp.hid] = [(hp.fx_index[t], sum(1 << c for c in hp.dest[t])) for t in hp.f64_terms]
-    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)))
+    unroll = _unroll(plans, options)
+    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll)
     k.cols = list(prog.cols)
     k.plans = plans
     k.smem_bytes = smem_cap
