@@ -130,3 +130,45 @@ def test_fast_fixed_point_option_matches_the_oracle():
     bound = fill_oracle.fill(spec, arrays, absolute=True)
     for g, r, b in zip(_flat(got), _flat(ref), _flat(bound)):
         assert numpy.all(numpy.abs(g - r) <= 1e-12 * b)
+
+
+def test_fixed_point_pilot_follows_the_data():
+    """Default options on a small weighted table (all terms fixed point).  The pilot of the first, tiny fill sees weights
+    near 1; later fills bring weights a million times larger (outside the field's headroom: they are added as float64
+    REDs and counted) -- every fill must still match the oracle, and the pilot is repeated once it has seen enough."""
+    from histbook_b200 import fillable
+    spec = golden_util.load()["bin_weight"]["spec"] if "bin_weight" in golden_util.load() else None
+    if spec is None:
+        spec = [c for n, c in golden_util.load().items() if c["spec"]["hists"][0]["weight"] and len(c["spec"]["hists"]) == 1
+                and not c["spec"]["hists"][0]["group"] and "w" in c["spec"]["hists"][0]["weight"]][0]["spec"]
+    from histbook_b200 import spec as hbspec
+    fields = hbspec.spec_fields(spec)
+    rs = numpy.random.RandomState(5)
+
+    def cols(n, scale):
+        out = {}
+        for f in fields:
+            out[f] = rs.uniform(0.0, 4.0, n) * (scale if f in ("w", "weight", "y") else 1.0)
+        return out
+    fills = [cols(3000, 1.0), cols(5000, 1.0e6), cols(300000, 1.0e6), cols(300000, 1.0e6)]
+    saved = dict(fillable._options)
+    try:
+        fillable.set_options(fx_stats=True)
+        sf = fillable.SpecFill(spec)
+        exp = bound = None
+        missed = []
+        for arrays in fills:
+            sf.fill(arrays)
+            missed.append(fillable.last_stats.get("fx_missed_total", 0))
+            exp = fill_oracle.fill(spec, arrays, exp)
+            bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+            for g, r, b in zip(_flat(sf.contents()), _flat(exp), _flat(bound)):
+                assert numpy.all(numpy.abs(g - r) <= 1e-12 * b)
+    finally:
+        fillable._options.clear()
+        fillable._options.update(saved)
+        fillable.set_options()
+    assert any(v[0].fx_terms for v in sf.plan.kernels.values())
+    # fill 2 still runs on the first pilot's scales: its large weights are REDs, counted; fill 3 brings 100x the data the
+    # pilot had seen, the pilot is repeated, and from then on everything fits
+    assert missed[0] == 0 and missed[1] > 0 and missed[2] == missed[1] and missed[3] == missed[1]

@@ -182,3 +182,31 @@ def test_string_codes():
     assert g.from_wire(g.to_wire(g.pattern("zero"))) == g.pattern("zero")
     with pytest.raises(Exception):
         g.pattern(3)
+
+
+def test_accumulation_kinds_chosen_for_the_baseline_configs():
+    """fx="auto" (codegen.choose_strategies): which float64 terms become exact fixed point, which stay float64 CAS."""
+    import golden_util
+    from histbook_b200 import codegen, spec as hbspec
+
+    def gen(name, **options):
+        spec = golden_util.load()[name]["spec"]
+        coltypes = dict((n, (numpy.dtype("int64" if n == "n" else "float64"), False)) for n in hbspec.spec_fields(spec))
+        return codegen.generate(spec, coltypes, options)
+    k = gen("c1")
+    assert [hp.strategy for hp in k.plans] == ["smem"] and not k.fx_terms and k.threads == 1024
+    k = gen("c3")                                   # 2006 rows: all but the first term, 2 blocks of 512 threads
+    assert [hp.strategy for hp in k.plans] == ["smem"] and len(k.fx_terms) == 2 and k.threads == 512 and k.smem_bytes < 113 * 1024
+    assert len(gen("c3", fx=False).fx_terms) == 0 and len(gen("c3", fx=True).fx_terms) == 3
+    k = gen("c2")                                   # hot window, sparse variant: float64 CAS, paired REDs behind a vote
+    assert k.plans[0].strategy == "window" and not k.fx_terms and "__any_sync" in k.source and "hb_red_pair" in k.source
+    d = gen("c2", win_dense=True)                   # dense variant: sum(w^2) in fixed point, plain REDs outside
+    assert len(d.fx_terms) == 1 and "hb_red_pair(" not in d.source.split("hb_event")[1] and d.window["wmax"] < k.window["wmax"]
+    assert d.window["bpb"] == 24 and k.window["bpb"] == 16
+    k = gen("c5")                                   # 134 MB: global paired REDs only, no window
+    assert [hp.strategy for hp in k.plans] == ["global"] and k.window is None and k.smem_bytes == 0
+    k = gen("c4")                                   # big book: one copy of the event code, everything privatised, all fixed point
+    assert all(hp.strategy == "smem" for hp in k.plans) and len(k.fx_terms) == 48 and k.threads == 1024
+    assert k.source.count("hb_event(p, hb_smem") == 1
+    k = gen("c2", deterministic=True)
+    assert k.deterministic and len(k.fx_terms) == 2 and "hb_fxg_add128" in k.source and "hb_red_pair(" not in k.source.split("hb_event")[1]
