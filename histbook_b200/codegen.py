@@ -150,6 +150,7 @@ class Program(object):
         self.counter = 0
         self.consts = []        # __constant__ array definitions (split edges)
         self.inexact = set()    # library functions used that are not bit-identical to numpy
+        self.nonneg = set()     # SSA names known to be >= +0 or NaN (squares, absolute values): the fixed-point add skips the sign path
 
     # ------------------------------------------------------------------ helpers
     def new(self, prefix="t"):
@@ -221,7 +222,11 @@ class Program(object):
             a, b, out = _resolve(ufunc, args)
             if fcn == "numpy.subtract" and out == numpy.bool_:
                 raise TypeError("numpy boolean subtract, the `-` operator, is not supported")
-            return self.emit(out, "%s<%s>(%s, %s)" % (helper, ctype(out), self.cast(args[0], a), self.cast(args[1], b)))
+            res = self.emit(out, "%s<%s>(%s, %s)" % (helper, ctype(out), self.cast(args[0], a), self.cast(args[1], b)))
+            if (fcn == "numpy.multiply" and out.kind == "f" and not args[0].isconst and not args[1].isconst
+                    and (args[0].c == args[1].c or (args[0].c in self.nonneg and args[1].c in self.nonneg))):
+                self.nonneg.add(res.c)               # x * x (and products of such)
+            return res
 
         if fcn == "numpy.true_divide":
             a, b, out = _resolve(numpy.true_divide, args)
@@ -278,7 +283,9 @@ class Program(object):
 
         if fcn in ("abs", "fabs"):
             a, out = _resolve(numpy.absolute, args)
-            return self.emit(out, "hb_abs<%s>(%s)" % (ctype(out), self.cast(args[0], a)))
+            res = self.emit(out, "hb_abs<%s>(%s)" % (ctype(out), self.cast(args[0], a)))
+            self.nonneg.add(res.c)
+            return res
         if fcn == "conj":
             a, out = _resolve(numpy.conjugate, args)
             return self.emit(out, self.cast(args[0], a))
@@ -488,6 +495,7 @@ class HistPlan(object):
         self.index = []          # [(Value index, totbins)]
         self.groups = []         # [Value group]
         self.terms = []          # unique accumulated terms: C expression (double) or None (= count of 1)
+        self.term_nonneg = []    # per term: provably >= 0 (or NaN)
         self.dest = []           # per term: list of destination columns
         self.strategy = "global"
         self.smem_f64_off = None   # byte offset of the [nbins][slots] float64 rows
@@ -499,12 +507,13 @@ class HistPlan(object):
         self.fx_set = set()        # float64 terms kept as exact 128-bit fixed point (hb_template.cuh HbFx) instead of float64
         self.fx_index = {}         # term index -> index of its scale in p.win[2 + ...]
 
-    def add_term(self, expr, col):
+    def add_term(self, expr, col, nonneg=False):
         for t, e in enumerate(self.terms):
             if e == expr:
                 self.dest[t].append(col)
                 return
         self.terms.append(expr)
+        self.term_nonneg.append(bool(nonneg))
         self.dest.append([col])
 
     @property
@@ -547,6 +556,12 @@ class HistPlan(object):
         tots = [t for v, t in self.index]
         return int(numpy.prod(tots[:self.win_split], dtype=numpy.int64)) if self.win_split else 1
 
+    def win_table_bits(self, window_bytes, options=None):
+        """Width of a row-table entry: 32 bits when first index and length fit 8 bits each and the offset 16."""
+        if self.win_trail <= 255 and window_bytes // max(self.row_bytes(options), 1) <= 65535 and (options or {}).get("win_table32", True):
+            return 32
+        return 64
+
     @property
     def win_trail(self):
         tots = [t for v, t in self.index]
@@ -583,6 +598,8 @@ def plan_hist(prog, hid, h):
             sel = prog.emit(numpy.bool_, "(%s != %s)" % (wv.c, wv.c))
             wz = prog.emit(wv.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, wv.dtype), wv.c))
             w2z = prog.emit(w2v.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, w2v.dtype), w2v.c))
+            if w2v.c in prog.nonneg:
+                prog.nonneg.add(w2z.c)
         else:
             wz, w2z = wv, w2v
 
@@ -594,13 +611,15 @@ def plan_hist(prog, hid, h):
         for val, col in ((sx, p["sumwx"]), (sx2, p["sumwx2"])):
             if val.isconst:
                 raise UnsupportedError("constant profile expression")
+            nonneg = False
             if w is None:
                 expr = "((double)%s)" % val.c               # sumx * 1
+                nonneg = val.c in prog.nonneg
             elif "const" in w:
                 expr = _mulexpr(prog, val, Value(lit(float(w["const"]), numpy.float64), numpy.float64))
             else:
                 expr = _mulexpr(prog, val, wz)
-            hp.add_term(expr, col)
+            hp.add_term(expr, col, nonneg)
 
     if w is None:
         hp.add_term(None, h["sumw"])
@@ -609,7 +628,7 @@ def plan_hist(prog, hid, h):
         hp.add_term(lit(float(w["const2"]), numpy.float64), h["sumw2"])
     else:
         hp.add_term("((double)%s)" % wz.c, h["sumw"])
-        hp.add_term("((double)%s)" % w2z.c, h["sumw2"])
+        hp.add_term("((double)%s)" % w2z.c, h["sumw2"], w2z.c in prog.nonneg)
     return hp
 
 
@@ -800,9 +819,10 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
         if window is not None:
             # per-row interval table of the hot window: [offset into the window | first in-row index << 16 | length]
             src.append("    __syncthreads();")
+            tt = "hb_u32" if window["table_bits"] == 32 else "hb_u64"
             src.append("    if (p.aux[%d] != nullptr)" % window["aux"])
             src.append("        for (int i = threadIdx.x; i < %d; i += HB_THREADS)" % window["rows"])
-            src.append("            reinterpret_cast<hb_u64*>(hb_smem + %d)[i] = reinterpret_cast<const hb_u64*>(p.aux[%d])[i];" % (window["table_off"], window["aux"]))
+            src.append("            reinterpret_cast<%s*>(hb_smem + %d)[i] = reinterpret_cast<const %s*>(p.aux[%d])[i];" % (tt, window["table_off"], tt, window["aux"]))
         src.append("    __syncthreads();")
     for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
         if is_scalar:
@@ -946,7 +966,7 @@ def _emit_row_adds(hp, options, region, bidx, nrows, indent, grow=None, gexact=N
     # fixed point: stage k of every term before stage k+1 of any, so that the returning atomics overlap
     for j, t in fxs:
         out.append("%sconst double fv%d = %s;" % (indent, j, val(t)))
-        out.append("%sconst HbFx ff%d = hb_fx_decode(fv%d, p.win[%d]);" % (indent, j, j, 2 + hp.fx_index[t]))
+        out.append("%sconst HbFx ff%d = hb_fx_decode<%s>(fv%d, p.win[%d]);" % (indent, j, "true" if hp.term_nonneg[t] else "false", j, 2 + hp.fx_index[t]))
         out.append("%shb_u32* const fa%d = %s;" % (indent, j, _slot_ptr(hp, region, j, bidx, nrows)[1]))
     for j, t in fxs:
         out.append("%sconst hb_u32 fc%d = hb_fx_stage0(fa%d, %s, ff%d);" % (indent, j, j, nrows, j))
@@ -1120,11 +1140,19 @@ def generate(spec, coltypes, options=None):
             for v, totbins in hp.index[k + 1:]:
                 wc = "(%s) * %d + %s" % (wc, totbins, v.c)
             ev.append("    const bool okw = %s;" % " && ".join(conds))
-            ev.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[okw ? (%s) : 0];" % (hp.win_table_off, wr))
-            ev.append("    const unsigned wa = (unsigned)((%s) - (int)(we.y >> 16));" % wc)
-            ev.append("    const bool inside = okw && wa < (we.y & 0xffffu);")
-            ev.append("    if (inside) {")
-            ev.append("        const int wb = (int)(we.x + wa);")
+            if hp.win_table_bits(smem_cap - smem, options) == 32:
+                # packed entry: first in-row index << 24 | length << 16 | offset  (one LDS.32 instead of an LDS.64)
+                ev.append("    const hb_u32 we = reinterpret_cast<const hb_u32*>(hb_smem + %d)[okw ? (%s) : 0];" % (hp.win_table_off, wr))
+                ev.append("    const unsigned wa = (unsigned)((%s) - (int)(we >> 24));" % wc)
+                ev.append("    const bool inside = okw && wa < ((we >> 16) & 0xffu);")
+                ev.append("    if (inside) {")
+                ev.append("        const int wb = (int)((we & 0xffffu) + wa);")
+            else:
+                ev.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[okw ? (%s) : 0];" % (hp.win_table_off, wr))
+                ev.append("    const unsigned wa = (unsigned)((%s) - (int)(we.y >> 16));" % wc)
+                ev.append("    const bool inside = okw && wa < (we.y & 0xffffu);")
+                ev.append("    if (inside) {")
+                ev.append("        const int wb = (int)(we.x + wa);")
             ev.extend(_emit_row_adds(hp, options, hp.win_off, "wb", "p.win[1]", "        ",
                                      grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol),
                                      gexact="(p.fxg[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, 6 * len(hp.f64_terms))))
@@ -1191,7 +1219,11 @@ def generate(spec, coltypes, options=None):
         nf = len(hp.row_layout(options)[0])
         merge.append("// merge the hot window of hist %d: one warp per table row, lanes along the row's interval" % hp.hid)
         merge.append("for (int wr = threadIdx.x >> 5; wr < %d; wr += HB_THREADS / 32) {" % hp.win_rows)
-        merge.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[wr];" % hp.win_table_off)
+        if hp.win_table_bits(smem_cap - smem, options) == 32:
+            merge.append("    const hb_u32 wp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[wr];" % hp.win_table_off)
+            merge.append("    const uint2 we = make_uint2(wp & 0xffffu, ((wp >> 24) << 16) | ((wp >> 16) & 0xffu));")
+        else:
+            merge.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[wr];" % hp.win_table_off)
         merge.append("    for (unsigned wa = threadIdx.x & 31u; wa < (we.y & 0xffffu); wa += 32u) {")
         merge.append("        const int wb = (int)(we.x + wa);")
         merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
@@ -1206,7 +1238,8 @@ def generate(spec, coltypes, options=None):
     if window is not None:
         bpb = window.row_bytes(options)
         winfo = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "rows": window.win_rows, "trail": window.win_trail,
-                 "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"], "aux": naux, "table_off": window.win_table_off}
+                 "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"], "aux": naux, "table_off": window.win_table_off,
+                 "table_bits": window.win_table_bits(smem_cap - smem, options)}
         naux += 1
     k.fx_terms = [(hp.fx_index[t], hp.hid, t) for hp in plans for t in hp.f64_terms if t in hp.fx_set]
     k.nfx = (1 + max(i for i, hid, t in k.fx_terms)) if k.fx_terms else 0

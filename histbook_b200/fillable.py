@@ -178,13 +178,19 @@ def choose_ragged(density, wmax):
     return first, length, float(density[inside].sum()) / total
 
 
-def window_table(first, length):
-    """The kernel's row table (hb_template / codegen `we`): per row one uint64 = offset of the row's interval in
-    the window (low 32 bits) | first in-row index << 48 | length << 32.  Returns (table, bins in the window)."""
+def window_table(first, length, bits=64):
+    """The kernel's row table (codegen `we`): per row one uint64 = offset of the row's interval in the window (low 32
+    bits) | first in-row index << 48 | length << 32 -- or, when the kernel was generated for packed entries
+    (kern.window["table_bits"] == 32), one uint32 = first << 24 | length << 16 | offset.
+    Returns (table, bins in the window)."""
     first = numpy.asarray(first, dtype=numpy.uint64)
     length = numpy.asarray(length, dtype=numpy.uint64)
     offset = numpy.concatenate([[0], numpy.cumsum(length)[:-1]]).astype(numpy.uint64)
-    table = offset | (length << numpy.uint64(32)) | (first << numpy.uint64(48))
+    if bits == 32:
+        assert (first < 256).all() and (length < 256).all() and (offset < 65536).all()
+        table = ((first << numpy.uint64(24)) | (length << numpy.uint64(16)) | offset).astype(numpy.uint32)
+    else:
+        table = offset | (length << numpy.uint64(32)) | (first << numpy.uint64(48))
     return table, int(length.sum())
 
 
@@ -325,14 +331,14 @@ def fill_hists(plan, hists, arrays, timed=False):
                         if dinfo is not None:
                             first, nlen, coverage = choose_ragged(density, dinfo["wmax"])
                             if coverage >= WINDOW_DENSE_COVERAGE:
-                                table, bins = window_table(first, nlen)
+                                table, bins = window_table(first, nlen, dinfo["table_bits"])
                                 wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum()), "dense": True}
                                 wst.window_coverage = coverage
                     if not wst.window:
                         first, nlen, coverage = choose_ragged(density, info["wmax"])
                         wst.window_coverage = coverage
                         if coverage >= WINDOW_MIN_COVERAGE:
-                            table, bins = window_table(first, nlen)
+                            table, bins = window_table(first, nlen, info["table_bits"])
                             wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum()), "dense": False}
                 if wst.window and wst.window["dense"]:
                     dsig, (dkern, dprog, _k, _kp, drng, drprog) = plan.kernel_for(cols, dense=True)
