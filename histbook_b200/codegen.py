@@ -1153,7 +1153,9 @@ def generate(spec, coltypes, options=None):
                 ev.append("    const bool inside = okw && wa < (we.y & 0xffffu);")
                 ev.append("    if (inside) {")
                 ev.append("        const int wb = (int)(we.x + wa);")
-            ev.extend(_emit_row_adds(hp, options, hp.win_off, "wb", "p.win[1]", "        ",
+            # (rows are laid out for the window's full capacity, a compile-time constant: every slot and limb sits at an
+            #  immediate offset; p.win[0] still limits what is zeroed to the bins in use)
+            ev.extend(_emit_row_adds(hp, options, hp.win_off, "wb", (smem_cap - smem) // hp.row_bytes(options), "        ",
                                      grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol),
                                      gexact="(p.fxg[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, 6 * len(hp.f64_terms))))
             ev.append("    }")
@@ -1227,7 +1229,7 @@ def generate(spec, coltypes, options=None):
         merge.append("    for (unsigned wa = threadIdx.x & 31u; wa < (we.y & 0xffffu); wa += 32u) {")
         merge.append("        const int wb = (int)(we.x + wa);")
         merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
-        merge.extend(_emit_row_merge(hp, options, hp.win_off, "wb", "p.win[1]", "        ",
+        merge.extend(_emit_row_merge(hp, options, hp.win_off, "wb", (smem_cap - smem) // hp.row_bytes(options), "        ",
                                      rowidx="(hb_i64)wr * %d + (we.y >> 16) + wa" % hp.win_trail))
         merge.append("    }")
         merge.append("}")

@@ -195,8 +195,9 @@ def window_table(first, length, bits=64):
 
 
 def window_params(kern, bins):
-    """p.win of hb_template.cuh: [u32 words of window to zero, bins in the window]."""
-    return [(bins * kern.window["bpb"] + 3) // 4, bins]
+    """p.win of hb_template.cuh: [u32 words of window to zero, bins in the window].  The kernel lays the window out
+    for its full capacity (slot blocks `wmax` rows apart), so the words to zero span the capacity whenever any bin is in use."""
+    return [(kern.window["wmax"] * kern.window["bpb"] + 3) // 4 if bins else 0, bins]
 
 
 def _abi_columns(kern, cols):

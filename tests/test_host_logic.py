@@ -162,8 +162,8 @@ def test_hot_window_placement():
     assert first.tolist() == [2] and length.tolist() == [3]
 
     class K(object):
-        window = {"bpb": 16}
-    assert window_params(K, 1000) == [4000, 1000]
+        window = {"bpb": 16, "wmax": 1200}
+    assert window_params(K, 1000) == [4800, 1000] and window_params(K, 0) == [0, 0]
 
 
 def test_string_codes():
