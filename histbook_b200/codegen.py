@@ -503,6 +503,7 @@ class HistPlan(object):
         self.win_table_off = None  # byte offset of the per-row interval table (8 bytes per row)
         self.win_split = None      # the first `win_split` fixed axes form the row index, the rest the in-row index
         self.gcap = 0              # group histograms: slab slots [0, gcap) are privatised in shared memory
+        self.replicas = 1          # statically privatised copies per block (lane & (replicas - 1) picks one): fewer same-bin lanes per atomic
         self.skip_zero = False     # filter-derived weight: rows whose every term is exactly 0.0 are not accumulated
         self.fx_set = set()        # float64 terms kept as exact 128-bit fixed point (hb_template.cuh HbFx) instead of float64
         self.fx_index = {}         # term index -> index of its scale in p.win[2 + ...]
@@ -549,7 +550,7 @@ class HistPlan(object):
 
     @property
     def nrows(self):
-        return self.nbins * max(self.gcap, 1)
+        return self.nbins * max(self.gcap, 1) * self.replicas
 
     @property
     def win_rows(self):
@@ -663,6 +664,7 @@ def choose_strategies(plans, options):
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
         hp.gcap = int(options.get("group_slots", 16)) if hp.groups else 0
+        hp.replicas = 1 if hp.groups else int(options.get("replicas", 1))
     for hp in plans:
         terms = list(hp.f64_terms)
         if mode == "mix":
@@ -1192,11 +1194,14 @@ def generate(spec, coltypes, options=None):
                 ev.append("        if (slot < %d) {" % hp.gcap)
                 ev.append("            const int srowi = slot * %d + bin;" % hp.nbins)
                 indent = "            "
+            elif hp.replicas > 1:
+                ev.append("        const int srowi = (int)(threadIdx.x & %du) * %d + bin;" % (hp.replicas - 1, hp.nbins))
             else:
                 ev.append("        const int srowi = bin;")
+            grow_idx = "srowi" if hp.groups else "bin"
             ev.extend(_emit_row_adds(hp, options, hp.smem_f64_off, "srowi", hp.nrows, indent,
-                                     grow="(p.hist[%d] + (hb_i64)srowi * %d)" % (hp.hid, hp.ncol),
-                                     gexact="(p.fxg[%d] + (hb_i64)srowi * %d)" % (hp.hid, 6 * len(hp.f64_terms))))
+                                     grow="(p.hist[%d] + (hb_i64)%s * %d)" % (hp.hid, grow_idx, hp.ncol),
+                                     gexact="(p.fxg[%d] + (hb_i64)%s * %d)" % (hp.hid, grow_idx, 6 * len(hp.f64_terms))))
             if hp.groups:
                 ev.append("        } else {")
                 ev.extend(_emit_global_adds(hp, options, "(hb_i64)slot * %d + bin" % hp.nbins, "            "))
@@ -1212,8 +1217,9 @@ def generate(spec, coltypes, options=None):
             continue
         merge.append("// merge hist %d" % hp.hid)
         merge.append("for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % hp.nrows)
-        merge.append("    double* const row = p.hist[%d] + (hb_i64)b * %d;" % (hp.hid, hp.ncol))
-        merge.extend(_emit_row_merge(hp, options, hp.smem_f64_off, "b", hp.nrows, "    ", rowidx="b"))
+        grow_idx = "b" if hp.replicas == 1 else "(b %% %d)" % hp.nbins
+        merge.append("    double* const row = p.hist[%d] + (hb_i64)%s * %d;" % (hp.hid, grow_idx, hp.ncol))
+        merge.extend(_emit_row_merge(hp, options, hp.smem_f64_off, "b", hp.nrows, "    ", rowidx=grow_idx))
         merge.append("}")
 
     if window is not None:
