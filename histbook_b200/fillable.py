@@ -80,8 +80,8 @@ class Plan(object):
 
 PILOT_EVENTS = 1 << 20          # events filled through the global path before the hot window is placed
 FX_MISS_REPILOT = 0.01          # re-run the fixed-point pilot when more than this fraction of the events missed
-FX_CHECK_FILLS = 16             # ... checked after this many fills
-FX_CHECK_EVENTS = 2 * 10**8     # ... or this many events, whichever comes first
+FX_CHECK_FILLS = 64             # ... checked after this many fills
+FX_CHECK_EVENTS = 4 * 10**9     # ... or this many events, whichever comes first
 
 
 def _fx_scales(plan, sig, kern, rng, rprog, cols, length):
