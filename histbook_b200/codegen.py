@@ -1127,11 +1127,9 @@ def generate(spec, coltypes, options=None):
                 and options.get("pair_red", True) and not options.get("deterministic", False)
                 and hp.ncol == 2 and len(hp.terms) == 2
                 and sorted(hp.dest[0] + hp.dest[1]) == [0, 1])
-        outside = ""
         if hp.strategy == "window":
             # inside the hot window -> shared memory.  Row table entry: x = offset of the row's interval in the
             # window, y = (first in-row index << 16) | length; a row without interval has length 0.
-            nf = len(hp.row_layout(options)[0])
             k = hp.win_split
             wr = "0"
             if k:
@@ -1188,7 +1186,6 @@ def generate(spec, coltypes, options=None):
         ev.append("    if (%s) {" % (" && ".join(conds) if conds else "true"))
         ev.append("        const int bin = %s;" % idx)
         if hp.strategy == "smem":
-            nslots = len(hp.row_layout(options)[0])
             indent = "        "
             if hp.groups:
                 ev.append("        if (slot < %d) {" % hp.gcap)
@@ -1224,7 +1221,6 @@ def generate(spec, coltypes, options=None):
 
     if window is not None:
         hp = window
-        nf = len(hp.row_layout(options)[0])
         merge.append("// merge the hot window of hist %d: one warp per table row, lanes along the row's interval" % hp.hid)
         merge.append("for (int wr = threadIdx.x >> 5; wr < %d; wr += HB_THREADS / 32) {" % hp.win_rows)
         if hp.win_table_bits(smem_cap - smem, options) == 32:
