@@ -1228,11 +1228,37 @@ def generate(spec, coltypes, options=None):
             merge.append("    const uint2 we = make_uint2(wp & 0xffffu, ((wp >> 24) << 16) | ((wp >> 16) & 0xffu));")
         else:
             merge.append("    const uint2 we = reinterpret_cast<const uint2*>(hb_smem + %d)[wr];" % hp.win_table_off)
-        merge.append("    for (unsigned wa = threadIdx.x & 31u; wa < (we.y & 0xffffu); wa += 32u) {")
-        merge.append("        const int wb = (int)(we.x + wa);")
-        merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
-        merge.extend(_emit_row_merge(hp, options, hp.win_off, "wb", (smem_cap - smem) // hp.row_bytes(options), "        ",
-                                     rowidx="(hb_i64)wr * %d + (we.y >> 16) + wa" % hp.win_trail))
+        nrows_w = (smem_cap - smem) // hp.row_bytes(options)
+        slots_w = hp.row_layout(options)[0]
+        paired = (hp.ncol == 2 and len(slots_w) == 2 and hp.count_term is None and sorted(hp.dest[slots_w[0]] + hp.dest[slots_w[1]]) == [0, 1]
+                  and not options.get("deterministic", False) and options.get("merge_pair", True))
+        if paired:
+            # two columns per bin: lanes 2k / 2k+1 exchange so that one RED instruction carries both halves of 16 bins'
+            # rows (hb_red_pair) -- half the sector operations at L2, where all blocks merge the same addresses at once
+            t0 = slots_w[0] if hp.dest[slots_w[0]] == [0] else slots_w[1]
+            t1 = slots_w[1] if t0 == slots_w[0] else slots_w[0]
+            merge.append("    for (unsigned wa0 = 0u; wa0 < (we.y & 0xffffu); wa0 += 32u) {")
+            merge.append("        const unsigned wa = wa0 + (threadIdx.x & 31u);")
+            merge.append("        const bool wlive = wa < (we.y & 0xffffu);")
+            merge.append("        const int wb = wlive ? (int)(we.x + wa) : 0;")
+            vals = []
+            for t in (t0, t1):
+                j = slots_w.index(t)
+                ptr = _slot_ptr(hp, hp.win_off, j, "wb", nrows_w, const=True)[1]
+                if t in hp.fx_set:
+                    vals.append("hb_fx_read(%s, %d, p.win[%d] - 1075)" % (ptr, nrows_w, 2 + hp.fx_index[t]))
+                else:
+                    vals.append("*%s" % ptr)
+            merge.append("        const double mv0 = wlive ? %s : 0.0;" % vals[0])
+            merge.append("        const double mv1 = wlive ? %s : 0.0;" % vals[1])
+            merge.append("        const int mrow = (wlive && (mv0 != 0.0 || mv1 != 0.0)) ? (int)(wr * %d + (we.y >> 16) + wa) : -1;" % hp.win_trail)
+            merge.append("        hb_red_pair(p.hist[%d], mrow, mv0, mv1);" % hp.hid)
+        else:
+            merge.append("    for (unsigned wa = threadIdx.x & 31u; wa < (we.y & 0xffffu); wa += 32u) {")
+            merge.append("        const int wb = (int)(we.x + wa);")
+            merge.append("        double* const row = p.hist[%d] + ((hb_i64)wr * %d + (we.y >> 16) + wa) * %d;" % (hp.hid, hp.win_trail, hp.ncol))
+            merge.extend(_emit_row_merge(hp, options, hp.win_off, "wb", nrows_w, "        ",
+                                         rowidx="(hb_i64)wr * %d + (we.y >> 16) + wa" % hp.win_trail))
         merge.append("    }")
         merge.append("}")
 
