@@ -128,11 +128,19 @@ def bind(name, value):
     cai = getattr(value, "__cuda_array_interface__", None)
     if cai is not None:
         return _from_cuda_array_interface(col, value, cai)
+    if mod.startswith("pyarrow"):
+        # Arrow arrays / chunked arrays: the values buffer is used in place when there are no nulls and one chunk
+        # (zero copy); nulls become NaN for floating point (to_numpy), other types with nulls are refused
+        if hasattr(value, "combine_chunks") and hasattr(value, "num_chunks"):
+            value = value.chunk(0) if value.num_chunks == 1 else value.combine_chunks()
+        if getattr(value, "null_count", 0) and not str(getattr(value, "type", "")).startswith(("float", "double", "halffloat")):
+            raise UnsupportedError("field {0!r}: Arrow {1} array with nulls".format(name, value.type))
+        value = value.to_numpy(zero_copy_only=False)
     if not isinstance(value, numpy.ndarray):
         if hasattr(value, "__dlpack__") and not isinstance(value, (list, tuple)):
             import torch
             return bind(name, torch.from_dlpack(value))
-        value = numpy.array(value)                         # fill.py:101-102,138-139
+        value = numpy.asarray(value)                       # fill.py:101-102,138-139 (numpy.array there; no copy needed here)
     if value.shape == ():
         return _scalar(col, value)
     if value.ndim != 1:

@@ -210,3 +210,27 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     assert k.source.count("hb_event(p, hb_smem") == 1
     k = gen("c2", deterministic=True)
     assert k.deterministic and len(k.fx_terms) == 2 and "hb_fxg_add128" in k.source and "hb_red_pair(" not in k.source.split("hb_event")[1]
+
+
+def test_zero_copy_ingest_of_host_containers():
+    """columns.bind uses host memory in place where it can: numpy arrays, pandas Series, Arrow arrays."""
+    import pandas
+    import pyarrow
+    from histbook_b200 import columns
+    a = numpy.arange(10, dtype=numpy.float64)
+    assert columns.bind("x", a).ptr == a.ctypes.data
+    s = pandas.Series(a)
+    assert columns.bind("x", s).ptr == s.values.ctypes.data
+    arr = pyarrow.array(a)
+    c = columns.bind("x", arr)
+    assert c.dtype == numpy.float64 and c.length == 10 and c.ptr == arr.buffers()[1].address
+    ch = pyarrow.chunked_array([a[:4], a[4:]])
+    c = columns.bind("x", ch)
+    assert c.length == 10 and numpy.array_equal(c.keepalive, a)
+    withnull = pyarrow.array([1.0, None, 3.0])
+    c = columns.bind("x", withnull)
+    assert numpy.isnan(c.keepalive[1]) and c.keepalive[2] == 3.0
+    with pytest.raises(Exception):
+        columns.bind("n", pyarrow.array([1, None, 3]))
+    i = pyarrow.array(numpy.arange(5, dtype=numpy.int32))
+    assert columns.bind("n", i).dtype == numpy.int32
