@@ -29,8 +29,10 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 warnings.filterwarnings("ignore")
 
+import histbook_b200                               # noqa: E402
 from histbook_b200 import _ref, spec as hbspec    # noqa: E402
 
+histbook_b200.uninstall()                          # the reference's own numpy path produces every output below
 hb = _ref.load()
 ENV = {n: getattr(hb, n) for n in ("Hist", "Book", "bin", "intbin", "split", "cut", "profile", "groupby", "groupbin")}
 ENV["numpy"] = numpy
@@ -141,6 +143,13 @@ case("groupby_num", ['Hist(groupby("c"), bin("x", 3, 1.0, 4.0, underflow=False, 
      [{"c": [1, 2, 3, 2, 1, 1, 1], "x": [1, 2, 3, 2, 1, 1, 3]}], "tests/test_hist.py:394 (numeric keys)")
 case("groupby_groupbin_num", ['Hist(bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False), groupby("c"), groupbin("x", 10.0))'],
      [{"c": [1, 1, 2, 2], "x": [0, 10, 15, 20], "y": [1, 2, 3, 4]}], "tests/test_hist.py:422 (numeric keys)")
+case("groupby_str", ['Hist(groupby("c"), bin("x", 3, 1.0, 4.0, underflow=False, overflow=False, nanflow=False))'],
+     [{"c": ["one", "two", "three", "two", "one", "one", "one"], "x": [1, 2, 3, 2, 1, 1, 3]}, {"c": ["two", "zero"], "x": [3.5, 1.5]}], "tests/test_hist.py:394 (string keys, plus a refill)")
+case("groupby_groupby_str", ['Hist(groupby("c1"), groupby("c2"), bin("x", 1, 1.0, 2.0, underflow=False, overflow=False, nanflow=False))'],
+     [{"c1": ["one", "two", "one", "two"], "c2": ["uno", "uno", "dos", "dos"], "x": [1, 1, 1, 1]}], "tests/test_hist.py:401")
+case("groupby_groupbin_str", ['Hist(bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False), groupby("c"), groupbin("x", 10.0))',
+                              'Hist(groupbin("x", 10.0), bin("y", 4, 1.0, 5.0, underflow=False, overflow=False, nanflow=False), groupby("c"))'],
+     [{"c": ["one", "one", "two", "two"], "x": [0, 10, 15, 20], "y": [1, 2, 3, 4]}], "tests/test_hist.py:422-435")
 case("groupbin_masked_key", ['Hist(groupbin("x", 1.0), bin("y", 2, 0.0, 2.0, underflow=False, overflow=False, nanflow=False))'],
      [{"x": [0.5, 1.5, 2.5], "y": [0.5, 5.0, 1.5]}], "hist.py:470-478 (key exists although every row is masked)")
 

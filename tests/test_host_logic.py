@@ -43,6 +43,8 @@ def _coltypes(case):
     out = {}
     for n, v in f.items():
         a = numpy.asarray(v)
+        if a.dtype.kind in "US":                 # string groupby keys reach the kernel as int64 dictionary codes
+            a = numpy.zeros(a.shape, dtype=numpy.int64)
         out[n] = (a.dtype, a.shape == ())
     for n in hbspec.spec_fields(case["spec"]):
         if n not in out and n in codegen.MAYBECONSTANTS:
