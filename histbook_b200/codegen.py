@@ -150,6 +150,7 @@ class Program(object):
         self.counter = 0
         self.consts = []        # __constant__ array definitions (split edges)
         self.inexact = set()    # library functions used that are not bit-identical to numpy
+        self.zeroed = {}        # (weight, weight^2) SSA names -> their NaN-zeroed forms (hist.py:422-427), shared by a book's histograms
         self.nonneg = set()     # SSA names known to be >= +0 or NaN (squares, absolute values): the fixed-point add skips the sign path
 
     # ------------------------------------------------------------------ helpers
@@ -594,13 +595,16 @@ def plan_hist(prog, hid, h):
         wv, w2v = prog.lower(w["w"]), prog.lower(w["w2"])
         if wv.isconst:
             raise UnsupportedError("constant weight expression")
-        if wv.dtype.kind == "f":
+        if wv.dtype.kind == "f" and (wv.c, w2v.c) in prog.zeroed:
+            wz, w2z = prog.zeroed[(wv.c, w2v.c)]             # the same weight in another histogram of the book
+        elif wv.dtype.kind == "f":
             # hist.py:422-427: rows with NaN weight contribute 0 to every column
             sel = prog.emit(numpy.bool_, "(%s != %s)" % (wv.c, wv.c))
             wz = prog.emit(wv.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, wv.dtype), wv.c))
             w2z = prog.emit(w2v.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, w2v.dtype), w2v.c))
             if w2v.c in prog.nonneg:
                 prog.nonneg.add(w2z.c)
+            prog.zeroed[(wv.c, w2v.c)] = (wz, w2z)
         else:
             wz, w2z = wv, w2v
 
@@ -735,7 +739,7 @@ def choose_strategies(plans, options):
             window.win_table_off = used
             used += (window.win_rows * 8 + 15) // 16 * 16
             window.win_off = used
-    nfx = 0
+    shared = {}
     for hp in plans:
         if hp.strategy == "global" and not det:      # (deterministic mode: global histograms add to exact accumulators too)
             hp.fx_set = set()
@@ -746,8 +750,10 @@ def choose_strategies(plans, options):
             raise UnsupportedError("deterministic mode: every float64 term must be fixed point")
         for t in hp.f64_terms:
             if t in hp.fx_set:
-                hp.fx_index[t] = nfx                 # its run-time scale lives in p.win[2 + index]
-                nfx += 1
+                # one scale (p.win[2 + index]) and one decode per distinct VALUE: in a book many histograms accumulate
+                # the same weight, weight^2, profile expression (c4: 48 terms, 12 distinct)
+                hp.fx_index[t] = shared.setdefault(hp.terms[t], len(shared))
+    nfx = len(shared)
     if nfx > MAX_WIN - 2:
         raise UnsupportedError("more than {0} fixed-point terms in one fill".format(MAX_WIN - 2))
     if not any(hp.strategy in ("smem", "window") for hp in plans) and not any(hp.fx for hp in plans):
@@ -966,9 +972,10 @@ def _emit_row_adds(hp, options, region, bidx, nrows, indent, grow=None, gexact=N
         return "1.0" if hp.terms[t] is None else hp.terms[t]
     fxs = [(j, t) for j, t in enumerate(slots) if t in hp.fx_set]
     # fixed point: stage k of every term before stage k+1 of any, so that the returning atomics overlap
+    # (the value fxv<i> and its decoded form fxd<i> were computed once at the top of the event function: _emit_fx_decodes)
     for j, t in fxs:
-        out.append("%sconst double fv%d = %s;" % (indent, j, val(t)))
-        out.append("%sconst HbFx ff%d = hb_fx_decode<%s>(fv%d, p.win[%d]);" % (indent, j, "true" if hp.term_nonneg[t] else "false", j, 2 + hp.fx_index[t]))
+        out.append("%sconst double fv%d = fxv%d;" % (indent, j, hp.fx_index[t]))
+        out.append("%sconst HbFx& ff%d = fxd%d;" % (indent, j, hp.fx_index[t]))
         out.append("%shb_u32* const fa%d = %s;" % (indent, j, _slot_ptr(hp, region, j, bidx, nrows)[1]))
     for j, t in fxs:
         out.append("%sconst hb_u32 fc%d = hb_fx_stage0(fa%d, %s, ff%d);" % (indent, j, j, nrows, j))
@@ -995,6 +1002,21 @@ def _emit_row_adds(hp, options, region, bidx, nrows, indent, grow=None, gexact=N
         for col in hp.dest[t]:
             out.append("%s    hb_red_f64(%s + %d, fv%d);" % (indent, grow, col, j))
         out.append("%s}" % indent)
+    return out
+
+
+def _emit_fx_decodes(plans):
+    """C lines for the top of the event function: every distinct fixed-point value once, decoded once."""
+    seen, out = set(), []
+    for hp in plans:
+        if hp.strategy not in ("smem", "window"):
+            continue
+        for t in hp.f64_terms:
+            if t in hp.fx_set and hp.fx_index[t] not in seen:
+                i = hp.fx_index[t]
+                seen.add(i)
+                out.append("const double fxv%d = %s;" % (i, hp.terms[t]))
+                out.append("const HbFx fxd%d = hb_fx_decode<%s>(fxv%d, p.win[%d]);" % (i, "true" if hp.term_nonneg[t] else "false", i, 2 + i))
     return out
 
 
@@ -1082,7 +1104,7 @@ def generate(spec, coltypes, options=None):
     elif smem <= 113 * 1024:
         dthreads, dblocks = 512, 2
     elif _unroll(plans, options) == 0:
-        dthreads, dblocks = 1024, 1           # the one-event-at-a-time code of big books stays within 64 registers
+        dthreads, dblocks = 768, 1            # the one-event-at-a-time code of big books stays within the 85 registers this allows
     else:
         dthreads, dblocks = 512, 1
     threads = int(options.get("threads", dthreads))
@@ -1102,6 +1124,7 @@ def generate(spec, coltypes, options=None):
 
     group_aux = {}
     ev = list(prog.body)
+    ev.extend(_emit_fx_decodes(plans))
     for hp in plans:
         ev.append("// ---- hist %d: shape %s, %s" % (hp.hid, hp.shape, hp.strategy))
         conds = []
@@ -1325,8 +1348,12 @@ def generate_range(spec, coltypes, options=None):
         return None
     ev = list(prog.body)
     nfx = 1 + max(hp.fx_index[t] for hp, t in terms)
+    done = set()
     for hp, t in terms:
         i = hp.fx_index[t]
+        if i in done:
+            continue
+        done.add(i)
         ev.append("{ const hb_u32 e = ((hb_u32)__double2hiint(%s) >> 20) & 0x7ffu;" % hp.terms[t])
         ev.append("  const hb_u32 m = __reduce_max_sync(0xffffffffu, (live && e != 0x7ffu) ? e : 0u);")
         ev.append("  if ((threadIdx.x & 31u) == 0u && m > reinterpret_cast<hb_u32*>(hb_smem)[%d]) atomicMax(reinterpret_cast<hb_u32*>(hb_smem) + %d, m); }" % (i, i))

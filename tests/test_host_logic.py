@@ -208,7 +208,8 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     k = gen("c5")                                   # 134 MB: global paired REDs only, no window
     assert [hp.strategy for hp in k.plans] == ["global"] and k.window is None and k.smem_bytes == 0
     k = gen("c4")                                   # big book: one copy of the event code, everything privatised, all fixed point
-    assert all(hp.strategy == "smem" for hp in k.plans) and len(k.fx_terms) == 48 and k.threads == 1024
+    assert all(hp.strategy == "smem" for hp in k.plans) and len(k.fx_terms) == 48 and k.threads == 768
+    assert k.nfx == 6 and k.source.count("hb_fx_decode<") == 6        # w, w^2, z, z^2, filtered w, filtered w^2: decoded once per event
     assert k.source.count("hb_event(p, hb_smem") == 1
     k = gen("c2", deterministic=True)
     assert k.deterministic and len(k.fx_terms) == 2 and "hb_fxg_add128" in k.source and "hb_red_pair(" not in k.source.split("hb_event")[1]
