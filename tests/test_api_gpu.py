@@ -227,6 +227,35 @@ def test_book_fill_and_algebra():                             # tests/test_book.
     assert book1["a"][:].tolist() == [[0], [6], [0], [4], [1], [0], [0]]
 
 
+def test_group():                                             # tests/test_book.py:144-158, Hist.group histbook/hist.py:609-659
+    book1, book2 = Book(), Book()
+    book1["a"] = Hist(bin("x", 4, 0, 4), fill=[0, 0, 0])
+    book1["b"] = Hist(bin("x", 4, 0, 4), fill=[0, 1, 1])
+    book1["d"] = Hist(bin("x", 4, 0, 4), fill=[])
+    book2["a"] = Hist(bin("x", 4, 0, 4), fill=[2, 2])
+    book2["b"] = Hist(bin("x", 4, 0, 4), fill=[0, 3, 3, 3, 3])
+    book2["c"] = Hist(bin("x", 4, 0, 4), fill=[0, 1, 2, 3])
+    book = Book.group(x=book1, y=book2)
+    assert book["a"].groupkeys("source") == set(["x", "y"])
+    assert book["b"].groupkeys("source") == set(["x", "y"])
+    assert book["c"].groupkeys("source") == set(["y"])
+    assert book["d"].groupkeys("source") == set(["x"])
+    assert book["a"]._content["x"].tolist() == [[0], [3], [0], [0], [0], [0], [0]]
+    assert book["a"]._content["y"].tolist() == [[0], [0], [0], [2], [0], [0], [0]]
+    assert book1["a"]._content.tolist() == [[0], [3], [0], [0], [0], [0], [0]]          # the sources keep their own contents
+
+    # the grouped histogram is an ordinary Hist(groupby("source"), bin(...)): it keeps filling on the device, old and new keys
+    g = Hist.group(x=book1["b"], y=book2["b"])
+    g.fill(x=[0.5, 1.5, 2.5, 2.5], source=numpy.array(["x", "y", "z", "z"]))
+    assert g.groupkeys("source") == set(["x", "y", "z"])
+    assert g._content["x"].tolist() == [[0], [2], [2], [0], [0], [0], [0]]
+    assert g._content["y"].tolist() == [[0], [1], [1], [0], [4], [0], [0]]
+    assert g._content["z"].tolist() == [[0], [0], [0], [2], [0], [0], [0]]
+    assert book1["b"]._content.tolist() == [[0], [1], [2], [0], [0], [0], [0]]
+    with pytest.raises(ValueError):
+        Hist.group(by="source", one=g)                         # groupby("source") already exists
+
+
 def test_views_and_copy_on_fill():                            # tests/test_book.py:160-173
     everything = ChannelsBook(
         mass=SamplesBook(["data", "signal", "background"],
