@@ -55,12 +55,40 @@ def is_stringlike(value):
     return False
 
 
+_CODE_OF = {}          # numpy dtype -> ABI code (dtype.name is slow; this sits on the per-fill path)
+
+
+def _code(dtype):
+    code = _CODE_OF.get(dtype)
+    if code is None:
+        code = DTYPE_CODE.get(dtype.name)
+        if code is not None and dtype.byteorder != ">":
+            _CODE_OF[dtype] = code
+    return code
+
+
+_TORCH_DTYPES = None   # torch dtype -> (numpy dtype, ABI code), built at the first torch column
+
+
+def _torch_dtypes():
+    global _TORCH_DTYPES
+    import torch
+    table = {}
+    for name in DTYPE_CODE:
+        t = getattr(torch, name, None)
+        if isinstance(t, torch.dtype):
+            table[t] = (numpy.dtype(name), DTYPE_CODE[name])
+    _TORCH_DTYPES = table
+    return table
+
+
 class Column(object):
-    __slots__ = ("name", "dtype", "is_scalar", "ptr", "location", "length", "scalar_bits", "keepalive")
+    __slots__ = ("name", "dtype", "code", "is_scalar", "ptr", "location", "length", "scalar_bits", "keepalive")
 
     def __init__(self, name):
         self.name = name
         self.dtype = None
+        self.code = None           # DTYPE_CODE of dtype
         self.is_scalar = False
         self.ptr = None
         self.location = 0          # 0 host, 1 device
@@ -69,10 +97,9 @@ class Column(object):
         self.keepalive = None      # whatever owns the memory `ptr` points into
 
     def abi(self):
-        code = DTYPE_CODE[self.dtype.name]
         if self.is_scalar:
-            return ("scalar", code, self.scalar_bits)
-        return (self.ptr, code, self.location)
+            return ("scalar", self.code, self.scalar_bits)
+        return (self.ptr, self.code, self.location)
 
 
 def _scalar(col, value):
@@ -80,6 +107,7 @@ def _scalar(col, value):
     if arr.dtype.name not in DTYPE_CODE:
         raise UnsupportedError("field {0!r}: scalars of dtype {1} are not supported".format(col.name, arr.dtype))
     col.dtype = arr.dtype
+    col.code = DTYPE_CODE[arr.dtype.name]
     col.is_scalar = True
     raw = arr.tobytes() + b"\0" * 8
     col.scalar_bits = int.from_bytes(raw[:8], "little")
@@ -98,9 +126,11 @@ def _from_cuda_array_interface(col, obj, cai):
     strides = cai.get("strides")
     if strides is not None and shape[0] > 1 and tuple(strides) != (dtype.itemsize,):
         raise UnsupportedError("field {0!r}: device arrays must be contiguous".format(col.name))
-    if dtype.name not in DTYPE_CODE or dtype.byteorder == ">":
+    code = _code(dtype)
+    if code is None:
         raise UnsupportedError("field {0!r}: dtype {1} is not supported by the B200 fill backend".format(col.name, dtype))
     col.dtype = dtype
+    col.code = code
     col.ptr = int(cai["data"][0]) if shape[0] > 0 else 0
     col.location = 1
     col.length = int(shape[0])
@@ -116,14 +146,23 @@ def bind(name, value):
         import torch
         if isinstance(value, torch.Tensor):
             if value.is_cuda:
-                if value.dim() == 1 and not value.is_contiguous():
+                # read the tensor directly: __cuda_array_interface__ builds a dict and refuses tensors that require grad
+                ndim = value.dim()
+                if ndim == 0:
+                    return _scalar(col, value.item())
+                if ndim != 1:
+                    raise UnsupportedError("field {0!r}: only one-dimensional device arrays can be filled".format(name))
+                known = (_TORCH_DTYPES or _torch_dtypes()).get(value.dtype)
+                if known is None:
+                    raise UnsupportedError("field {0!r}: dtype {1} is not supported by the B200 fill backend".format(name, value.dtype))
+                if not value.is_contiguous():
                     value = value.contiguous()
-                if value.dtype == torch.bool:
-                    value = value.view(torch.uint8)
-                    col = _from_cuda_array_interface(col, value, value.__cuda_array_interface__)
-                    col.dtype = numpy.dtype(numpy.bool_)
-                    return col
-                return _from_cuda_array_interface(col, value, value.__cuda_array_interface__)
+                col.dtype, col.code = known
+                col.length = value.shape[0]
+                col.ptr = value.data_ptr() if col.length > 0 else 0
+                col.location = 1
+                col.keepalive = value
+                return col
             value = value.detach().numpy()
     cai = getattr(value, "__cuda_array_interface__", None)
     if cai is not None:
@@ -151,6 +190,7 @@ def bind(name, value):
     if not value.flags.c_contiguous or value.dtype.byteorder == ">":
         value = numpy.ascontiguousarray(value, dtype=value.dtype.newbyteorder("="))
     col.dtype = value.dtype
+    col.code = _code(value.dtype)
     col.ptr = value.ctypes.data if value.shape[0] > 0 else 0
     col.location = 0
     col.length = int(value.shape[0])

@@ -379,15 +379,15 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exa
     Arena of 128-bit accumulators or None (deterministic mode)."""
     init()
     ncols = len(columns)
-    cols = (hb_column * max(ncols, 1))()
-    for i, c in enumerate(columns):
+    structs = []
+    for c in columns:
         if c[0] == "scalar":
-            cols[i].ptr, cols[i].dtype, cols[i].location, cols[i].is_scalar, cols[i].scalar_bits = None, c[1], 0, 1, c[2]
+            structs.append(hb_column(None, c[1], 0, 1, 0, c[2]))
         else:
-            cols[i].ptr, cols[i].dtype, cols[i].location, cols[i].is_scalar, cols[i].scalar_bits = (
-                (c[0] + offset * _ITEMSIZE[c[1]]) if c[0] else c[0], c[1], c[2], 0, 0)
+            structs.append(hb_column((c[0] + offset * _ITEMSIZE[c[1]]) if c[0] else c[0], c[1], c[2], 0, 0, 0))
+    cols = (hb_column * max(ncols, 1))(*structs)
     hist = (ctypes.c_void_p * max(len(arenas), 1))(*[a._h for a in arenas])
-    auxp = (ctypes.c_void_p * max(len(aux), 1))(*[ctypes.c_void_p(int(x)) for x in aux])
+    auxp = (ctypes.c_void_p * max(len(aux), 1))(*[int(x) for x in aux])
     winp = (ctypes.c_int32 * max(len(win), 1))(*[int(x) for x in win])
     stats = hb_stats()
     if exact is None:
