@@ -444,53 +444,6 @@ extern "C" int hb_arena_scale(hb_arena* dst, double alpha) {
     return HB_OK;
 }
 
-// per-axis marginals of |content[..., col]|: block-private shared accumulation, then global float64 REDs
-__global__ void hb_marginals_kernel(const double* __restrict__ content, int ndim, const int64_t* __restrict__ shape,
-                                    int ncol, int col, int64_t nbins, int total, double* __restrict__ out) {
-    extern __shared__ double sm[];
-    for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = 0.0;
-    __syncthreads();
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbins; b += (int64_t)gridDim.x * blockDim.x) {
-        double v = fabs(content[b * ncol + col]);
-        if (v != 0.0 && v == v) {
-            int64_t rest = b;
-            int off = total;
-            for (int k = ndim - 1; k >= 0; --k) {
-                int64_t t = shape[k];
-                off -= (int)t;
-                atomicAdd(&sm[off + (int)(rest % t)], v);
-                rest /= t;
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < total; i += blockDim.x)
-        if (sm[i] != 0.0) atomicAdd(&out[i], sm[i]);
-}
-
-extern "C" int hb_arena_marginals(const hb_arena* a, int ndim, const int64_t* shape, int ncol, int col, double* host_out) {
-    int rc = ensure_device();
-    if (rc) return rc;
-    if (!a || ndim < 1 || ndim > 8 || !shape || !host_out || ncol < 1 || col < 0 || col >= ncol) return fail(HB_ERR_ARG, "bad marginals arguments");
-    int64_t nbins = 1, total = 0;
-    for (int k = 0; k < ndim; ++k) { nbins *= shape[k]; total += shape[k]; }
-    if (nbins * ncol > a->n) return fail(HB_ERR_ARG, "shape larger than the arena");
-    if (total * 8 > 48 * 1024) return fail(HB_ERR_ARG, "too many bins per axis for the marginals kernel");
-    double* dout = nullptr;
-    int64_t* dshape = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&dout, (size_t)total * 8));
-    CUDA_TRY(cudaMalloc((void**)&dshape, (size_t)ndim * 8));
-    CUDA_TRY(cudaMemsetAsync(dout, 0, (size_t)total * 8, g_stream));
-    CUDA_TRY(cudaMemcpyAsync(dshape, shape, (size_t)ndim * 8, cudaMemcpyHostToDevice, g_stream));
-    hb_marginals_kernel<<<grid_for(nbins), 256, (size_t)total * 8, g_stream>>>(a->ptr, ndim, dshape, ncol, col, nbins, (int)total, dout);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(host_out, dout, (size_t)total * 8, cudaMemcpyDeviceToHost, g_stream));
-    CUDA_TRY(cudaStreamSynchronize(g_stream));
-    cudaFree(dout);
-    cudaFree(dshape);
-    return HB_OK;
-}
-
 // Projection (histbook/proj.py:227-296 `project`: numpy.sum of the content over the fixed axes that are not kept):
 // every thread walks input rows (bins), finds the output row by dropping the summed axes from the index, and adds
 // the row's columns there -- into a block-private shared-memory copy of the output when it is small (then one RED

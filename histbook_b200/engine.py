@@ -68,7 +68,6 @@ SYMBOLS = {
     "hb_fill": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
     "hb_fill_exact": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
     "hb_fx_finalize": (_I, [_P, _P, _I64, _I, _I, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64)]),
-    "hb_arena_marginals": (_I, [_P, _I, ctypes.POINTER(_I64), _I, _I, _P]),
     "hb_keyset_create": (_I, [_I, _PP]),
     "hb_keyset_destroy": (_I, [_P]),
     "hb_keyset_clear": (_I, [_P]),
@@ -277,19 +276,6 @@ class Arena(object):
         check(lib().hb_arena_project(self._h, len(shape), arr, int(ncol), karr, ctypes.byref(out)))
         return Arena(_handle=out)
 
-    def marginals(self, shape, ncol, col):
-        """Per-axis marginals of |content[..., col]| (list of arrays), computed on the device."""
-        shape = [int(x) for x in shape]
-        out = numpy.zeros(sum(shape), dtype=numpy.float64)
-        arr = (ctypes.c_int64 * len(shape))(*shape)
-        check(lib().hb_arena_marginals(self._h, len(shape), arr, int(ncol), int(col), out.ctypes.data_as(ctypes.c_void_p)))
-        res, off = [], 0
-        for t in shape:
-            res.append(out[off:off + t])
-            off += t
-        return res
-
-    @property
     def __cuda_array_interface__(self):
         return {"shape": (int(self.size),), "typestr": "<f8", "data": (int(self.ptr or 0), False), "version": 3, "strides": None}
 

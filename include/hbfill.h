@@ -135,11 +135,6 @@ int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
 int hb_fx_finalize(hb_arena* content, hb_arena* exact, int64_t nrows, int ncol, int nslots,
                    const int32_t* k, const uint64_t* dest_mask);
 
-/* Per-axis marginals of |content[..., col]| of an N-d histogram (shape = fixed-axis bins..., ncol), computed on
- * the device; host_out receives shape[0] + ... + shape[ndim-1] doubles.  Used to place the hot window that the
- * fill kernel privatises in shared memory. */
-int hb_arena_marginals(const hb_arena* a, int ndim, const int64_t* shape, int ncol, int col, double* host_out);
-
 /* key sets (group axes) --------------------------------------------------------------------------------- */
 /* A device-side set of 64-bit keys (raw bits of float64 / int64 group keys), capacity a power of two. */
 typedef struct hb_keyset hb_keyset;
