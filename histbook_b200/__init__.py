@@ -157,6 +157,84 @@ def _hist_project(self, *axis):
     return out
 
 
+# ----------------------------------------------------------------------------- merge algebra on the device
+
+def _device_store(hist):
+    """The store of a histogram whose bins live on the device as one plain arena (no group axes), else None."""
+    st = hist.__dict__.get("_hb")
+    if st is None or st.groups or len(hist._group) > 0 or st.host_valid or not st.dev_valid or st.arena is None:
+        return None
+    return st
+
+
+def _fresh_store(hist, arena):
+    from histbook_b200.store import Store
+    new = Store(hist._shape, [], None)
+    new.arena = arena
+    new.host, new.host_valid, new.dev_valid, new.nonempty = None, False, True, True
+    return new
+
+
+def _same_axes(self, other):
+    hb = _ref.load()
+    if not isinstance(other, hb.hist.Hist):
+        raise TypeError("histograms can only be added to other histograms")
+    if self._group + self._fixed + self._profile != other._group + other._fixed + other._profile:
+        raise TypeError("histograms can only be added to other histograms with the same axis specifications")
+
+
+def _hist_add(self, other):
+    """``Hist.__add__`` (histbook/hist.py:506-542).  Two device-resident histograms without group axes add on the device
+    (hb_arena_axpy, one IEEE add per bin like numpy's ``+``); anything else takes the reference's path on host copies."""
+    _same_axes(self, other)
+    a, b = _device_store(self), _device_store(other)
+    if a is None or b is None:
+        return _originals["Hist.__add__"](self, other)
+    out = self.__class__.__new__(self.__class__)
+    out.__dict__.update(self.__dict__)
+    arena = a.arena.clone()
+    arena.axpy(b.arena, 1.0)
+    out.__dict__["_hb"] = _fresh_store(self, arena)
+    return out
+
+
+def _hist_iadd(self, other):
+    """``Hist.__iadd__`` (histbook/hist.py:544-575)."""
+    _same_axes(self, other)
+    a, b = _device_store(self), _device_store(other)
+    if a is None or b is None:
+        return _originals["Hist.__iadd__"](self, other)
+    a.arena.axpy(b.arena, 1.0)
+    return self
+
+
+def _is_scalar_number(value):
+    import numbers
+    return isinstance(value, (numbers.Real, numpy.integer, numpy.floating))
+
+
+def _hist_mul(self, value):
+    """``Hist.__mul__`` (histbook/hist.py:577-590); ``__rmul__`` calls it."""
+    a = _device_store(self)
+    if a is None or not _is_scalar_number(value):
+        return _originals["Hist.__mul__"](self, value)
+    out = self.__class__.__new__(self.__class__)
+    out.__dict__.update(self.__dict__)
+    arena = a.arena.clone()
+    arena.scale(float(value))
+    out.__dict__["_hb"] = _fresh_store(self, arena)
+    return out
+
+
+def _hist_imul(self, value):
+    """``Hist.__imul__`` (histbook/hist.py:595-607)."""
+    a = _device_store(self)
+    if a is None or not _is_scalar_number(value):
+        return _originals["Hist.__imul__"](self, value)
+    a.arena.scale(float(value))
+    return self
+
+
 # ----------------------------------------------------------------------------- install / uninstall
 
 def install():
@@ -170,6 +248,8 @@ def install():
         "Hist.fill": Hist.__dict__["fill"], "Book.fill": Book.__dict__["fill"],
         "Hist.copy": Hist.__dict__["copy"], "Hist.copyonfill": Hist.__dict__["copyonfill"],
         "Hist.cleared": Hist.__dict__["cleared"], "Hist.project": hb.proj.Projectable.__dict__["project"],
+        "Hist.__add__": Hist.__dict__["__add__"], "Hist.__iadd__": Hist.__dict__["__iadd__"],
+        "Hist.__mul__": Hist.__dict__["__mul__"], "Hist.__imul__": Hist.__dict__["__imul__"],
     })
     Hist._content = property(_content_get, _content_set)
     Hist.fill = _hist_fill
@@ -177,6 +257,7 @@ def install():
     Hist.copy = _hist_copy
     Hist.copyonfill = _hist_copyonfill
     Hist.project = _hist_project
+    Hist.__add__, Hist.__iadd__, Hist.__mul__, Hist.__imul__ = _hist_add, _hist_iadd, _hist_mul, _hist_imul
     _installed = True
 
 
@@ -194,6 +275,8 @@ def uninstall():
     Hist.copy = _originals["Hist.copy"]
     Hist.copyonfill = _originals["Hist.copyonfill"]
     del Hist.project                      # falls back to the inherited Projectable.project
+    for name in ("__add__", "__iadd__", "__mul__", "__imul__"):
+        setattr(Hist, name, _originals["Hist." + name])
     _installed = False
 
 

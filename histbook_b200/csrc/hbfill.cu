@@ -322,7 +322,7 @@ struct hb_arena {
 
 __global__ void hb_axpy_kernel(double* __restrict__ dst, const double* __restrict__ src, double alpha, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = dst[i] + alpha * src[i];
+        dst[i] = __dadd_rn(dst[i], __dmul_rn(alpha, src[i]));      // two roundings like numpy's a + alpha*b, never an FMA
 }
 __global__ void hb_scale_kernel(double* __restrict__ dst, double alpha, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

@@ -227,6 +227,55 @@ def test_book_fill_and_algebra():                             # tests/test_book.
     assert book1["a"][:].tolist() == [[0], [6], [0], [4], [1], [0], [0]]
 
 
+def test_merge_algebra_stays_on_the_device():                 # Hist.__add__/__iadd__/__mul__/__imul__ histbook/hist.py:506-607
+    rs = numpy.random.RandomState(7)
+    cols1 = {"x": rs.normal(0, 1, 20000), "y": rs.normal(0, 1, 20000), "w": rs.uniform(0.5, 1.5, 20000)}
+    cols2 = {"x": rs.normal(0.5, 1, 30000), "y": rs.normal(0, 2, 30000), "w": rs.uniform(0.5, 1.5, 30000)}
+
+    def make():
+        return Hist(bin("x", 40, -4, 4), bin("y", 30, -4, 4), weight="w")
+    a, b = make(), make()
+    a.fill(**cols1)
+    b.fill(**cols2)
+    ca, cb = histbook_b200.peek(a).copy(), histbook_b200.peek(b).copy()
+
+    def on_device(h):
+        st = h.__dict__["_hb"]
+        return st.dev_valid and not st.host_valid
+    c = a + b
+    assert on_device(a) and on_device(b) and on_device(c)
+    assert numpy.array_equal(histbook_b200.peek(c), ca + cb)          # one IEEE add per bin, like numpy
+    d = c * 0.3
+    e = 3 * c
+    assert on_device(c) and on_device(d) and on_device(e)
+    assert numpy.array_equal(histbook_b200.peek(d), (ca + cb) * 0.3)
+    assert numpy.array_equal(histbook_b200.peek(e), (ca + cb) * 3)
+    a += b
+    assert on_device(a) and numpy.array_equal(histbook_b200.peek(a), ca + cb)
+    assert numpy.array_equal(histbook_b200.peek(b), cb)                # the right operand is untouched
+    a *= 2
+    assert on_device(a) and numpy.array_equal(histbook_b200.peek(a), (ca + cb) * 2)
+    a.fill(**cols1)                                                   # and keeps filling
+    assert abs(a._content[..., 0].sum() - (2 * (ca + cb)[..., 0].sum() + ca[..., 0].sum())) < 1e-6
+    # results do not alias their operands
+    c.fill(**cols1)
+    assert numpy.array_equal(histbook_b200.peek(b), cb) and numpy.array_equal(histbook_b200.peek(d), (ca + cb) * 0.3)
+    # the reference's errors
+    with pytest.raises(TypeError):
+        a + Hist(bin("x", 41, -4, 4), bin("y", 30, -4, 4), weight="w")
+    with pytest.raises(TypeError):
+        a + 1
+    with pytest.raises(TypeError):
+        a * "2"
+    # one side read on the host (host copy authoritative) or never filled: the reference's own path, same numbers
+    f = make()
+    f.fill(**cols2)
+    cf = f._content.copy()
+    g = b + f
+    assert numpy.array_equal(g._content, cb + cf)
+    assert numpy.array_equal((make() + b)._content, cb)
+
+
 def test_group():                                             # tests/test_book.py:144-158, Hist.group histbook/hist.py:609-659
     book1, book2 = Book(), Book()
     book1["a"] = Hist(bin("x", 4, 0, 4), fill=[0, 0, 0])
