@@ -784,6 +784,7 @@ class Kernel(object):
         self.fx_terms = []          # [(i, hist id, term index)] of the fixed-point terms; scale of term i in p.win[2 + i]
         self.nfx = 0
         self.fx_aux = None
+        self.times_aux = None
         self.naux = 0
         self.deterministic = False
         self.exact = {}
@@ -800,11 +801,12 @@ def _loadtype(dtype):
     return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
 
 
-def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False, unroll=4):
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False, unroll=4, times_aux=None, dynamic=False):
     """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
     over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
     takes the scalar path), shared-memory zeroing before and block merge after."""
     src = []
+    vcols_early = [slot for slot, (name, dtype, is_scalar) in enumerate(prog.cols) if not is_scalar]
     src.append('#include "hb_template.cuh"')
     src.append("#define HB_THREADS %d" % threads)
     src.append("#define HB_TILE (HB_THREADS * 4)")
@@ -820,6 +822,27 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
 
     src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % minblocks)
     src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
+
+    def stamp(which):
+        # option block_times (measurement only): per block [start, end of the event loop, end of the merge] in ns
+        if times_aux is not None:
+            src.append("    if (threadIdx.x == 0 && p.aux[%d] != nullptr) { hb_u64 t; asm volatile(\"mov.u64 %%0, %%%%globaltimer;\" : \"=l\"(t)); "
+                       "reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d]))[blockIdx.x * 3 + %d] = t; }" % (times_aux, times_aux, which))
+    stamp(0)
+    if dynamic:
+        # hand-out state (see the tile loop): chunks 0 and 1 of this block are static
+        src.append("    __shared__ hb_u64 hb_ring[4];")
+        src.append("    __shared__ hb_u32 hb_reads[4];")
+        src.append("    __shared__ hb_u32 hb_ticket;")
+        src.append("    if (threadIdx.x == 0) {")
+        src.append("        const hb_i64 nt = (p.n + HB_TILE - 1) / HB_TILE;")
+        src.append("        const hb_i64 t0 = (%s) + blockIdx.x, t1 = t0 + gridDim.x;" % (
+            "p.vec_ok ? (nt * 15 / 16) / gridDim.x * gridDim.x : 0" if (dynamic == "tail" and unroll != 0 and vcols_early) else "0"))
+        src.append("        hb_ticket = 0u;")
+        src.append("        for (int i = 0; i < 4; ++i) { hb_reads[i] = 0u; hb_ring[i] = 0ull; }")
+        src.append("        hb_ring[0] = (1ull << 32) | (t0 < nt ? (hb_u32)t0 : HB_SCHED_DONE);")
+        src.append("        hb_ring[1] = (2ull << 32) | (t1 < nt ? (hb_u32)t1 : HB_SCHED_DONE);")
+        src.append("    }")
     if smem or window is not None:
         # `smem` bytes of statically privatised histograms (and the window's row table), then p.win[0] words of window
         bound = "%d + p.win[0]" % (smem // 4) if window is not None else "%d" % (smem // 4)
@@ -831,6 +854,8 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
             src.append("    if (p.aux[%d] != nullptr)" % window["aux"])
             src.append("        for (int i = threadIdx.x; i < %d; i += HB_THREADS)" % window["rows"])
             src.append("            reinterpret_cast<%s*>(hb_smem + %d)[i] = reinterpret_cast<const %s*>(p.aux[%d])[i];" % (tt, window["table_off"], tt, window["aux"]))
+        src.append("    __syncthreads();")
+    elif dynamic:
         src.append("    __syncthreads();")
     for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
         if is_scalar:
@@ -876,7 +901,86 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
                "%s}" % indent]
         return out
 
-    if prefetch and vcols:
+    if dynamic:
+        # Dynamic tiles (option dynamic = "tail" | True; off by default).  Blocks run at different speeds (DRAM / L2
+        # distance of their SM, contention in the L2 RED path: with the static grid-stride split the slowest block of c2
+        # ends 2 %, of c3 3 %, of c5 20 % after the median -- tools/block_times.py).  "tail": the first 15/16 of the tiles
+        # are split statically and the rest is handed out from one global counter (p.sched[0]); True: everything is.
+        # Measured (profiles/r01_sweeps.txt): every block then ends within 1 % of the others, but the kernels are not
+        # bound block by block -- c2 +1 %, c3 and c4 +-0, c5 -1 % (more registers), c1 at 1e7 events -27 % (two more
+        # round trips in a 20 us kernel) -- so the static split stays the default.  No block barrier: the warps of a block draw tickets
+        # from a shared counter; ticket k is warp-tile k % W of the block's chunk k / W, and the chunk's tile number is
+        # published in a 4-slot ring by the warp that drew the first ticket of the chunk TWO earlier -- its global
+        # atomicAdd returns while its own loads are in flight.  That warp first waits for the previous chunk to be
+        # published, so the tile numbers of a block increase from chunk to chunk and "no tile left" (HB_SCHED_DONE) is
+        # final: a warp leaves at its first such ticket, and all W tickets of every real chunk have been drawn by then.
+        # A slot is only overwritten once all W readers of its previous chunk are through (hb_reads), so warps may
+        # drift apart freely.  Every warp draws its next ticket while the loads of the current one are in flight.  The
+        # last block to finish zeroes the counters for the next launch on this stream.
+        def draw(indent, t, c, sb, tl):
+            return [x.replace("@", indent) for x in [
+                "@if (lane == 0u) {",
+                "@    %s = atomicAdd(&hb_ticket, 1u);" % t,
+                "@    volatile hb_u64* const slot = &hb_ring[(%s / (HB_THREADS / 32)) & 3u];" % t,
+                "@    hb_u64 e = *slot;",
+                "@    while ((hb_u32)(e >> 32) != %s / (HB_THREADS / 32) + 1u) { __nanosleep(40); e = *slot; }" % t,
+                "@    atomicAdd(&hb_reads[(%s / (HB_THREADS / 32)) & 3u], 1u);" % t,
+                "@    %s = (hb_u32)e;" % tl,
+                "@}",
+                "@%s = __shfl_sync(0xffffffffu, %s, 0);" % (t, t),
+                "@%s = __shfl_sync(0xffffffffu, %s, 0);" % (tl, tl),
+                "@%s = %s / (HB_THREADS / 32); %s = %s %% (HB_THREADS / 32);" % (c, t, sb, t)]]
+        if dynamic == "tail" and unroll != 0 and vcols:
+            src.append("    const hb_i64 nstatic = p.vec_ok ? (ntiles * 15 / 16) / gridDim.x * gridDim.x : 0;")
+            src.append("    for (hb_i64 tile = blockIdx.x; tile < nstatic; tile += gridDim.x) {      // every one of these is a full tile")
+            src.append("        const hb_i64 first = tile * HB_TILE;")
+            for slot, dtype in vcols:
+                src.append("        %s v%d[4];" % (_loadtype(dtype), slot))
+            src.extend(loads("", "first", "        "))
+            src.extend(events("", "        "))
+            src.append("    }")
+        else:
+            src.append("    const hb_i64 nstatic = 0;")
+        src.append("    const unsigned lane = threadIdx.x & 31u;")
+        src.append("    unsigned ticket = 0u, chunk, sub; hb_u32 tile = 0u;")
+        src.extend(draw("    ", "ticket", "chunk", "sub", "tile"))
+        src.append("    while (true) {")
+        src.append("        const bool fetcher = (lane == 0u) && (sub == 0u);")
+        src.append("        hb_u32 fetched = 0u;")
+        src.append("        if (fetcher) {")
+        src.append("            volatile hb_u64* const prev = &hb_ring[(chunk + 1u) & 3u];")
+        src.append("            while ((hb_u32)(*prev >> 32) != chunk + 2u) __nanosleep(40);")
+        src.append("            fetched = atomicAdd(p.sched, 1u);")
+        src.append("        }")
+        src.append("        const hb_i64 first = (hb_i64)tile * HB_TILE + (hb_i64)sub * 128;")
+        src.append("        const bool vec = tile != HB_SCHED_DONE && p.vec_ok && first + 128 <= p.n;")
+        if unroll != 0:
+            for slot, dtype in vcols:
+                src.append("        %s v%d[4];" % (_loadtype(dtype), slot))
+            src.append("        if (vec) {")
+            src.extend(x.replace("threadIdx.x, HB_THREADS", "(int)lane, 32") for x in loads("", "first", "            "))
+            src.append("        }")
+        src.append("        if (fetcher) {")
+        src.append("            const unsigned s2 = (chunk + 2u) & 3u, need = (HB_THREADS / 32) * ((chunk + 2u) >> 2);")
+        src.append("            while (*reinterpret_cast<volatile hb_u32*>(&hb_reads[s2]) != need) __nanosleep(40);")
+        src.append("            const hb_u64 t = (hb_u64)nstatic + 2ull * gridDim.x + fetched;")
+        src.append("            *reinterpret_cast<volatile hb_u64*>(&hb_ring[s2]) = ((hb_u64)(chunk + 3u) << 32) | (t < (hb_u64)ntiles ? (hb_u32)t : HB_SCHED_DONE);")
+        src.append("        }")
+        src.append("        if (tile == HB_SCHED_DONE) break;")
+        src.append("        unsigned nticket = 0u, nchunk, nsub; hb_u32 ntile = 0u;")
+        src.extend(draw("        ", "nticket", "nchunk", "nsub", "ntile"))
+        wtail = [x.replace("(hb_i64)k * HB_THREADS + threadIdx.x", "(hb_i64)k * 32 + lane") for x in tail("            ")]
+        if unroll == 0:
+            src.extend(x.replace("for (int k = 0; k < 4; ++k) {", "_Pragma(\"unroll 1\") for (int k = 0; k < 4; ++k) {")[4:] for x in wtail)
+        else:
+            src.append("        if (vec) {")
+            src.extend(events("", "            "))
+            src.append("        } else {")
+            src.extend(wtail)
+            src.append("        }")
+        src.append("        chunk = nchunk; sub = nsub; tile = ntile;")
+        src.append("    }")
+    elif prefetch and vcols:
         # register double buffer: the next tile's loads are in flight while this tile's events are accumulated
         for slot, dtype in vcols:
             src.append("    %s v%d[4], v%dn[4];" % (_loadtype(dtype), slot, slot))
@@ -920,9 +1024,20 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
         src.extend(tail("            "))
         src.append("        }")
         src.append("    }")
+    if times_aux is not None:
+        src.append("    __syncthreads();")
+    stamp(1)
     if merge_lines:
         src.append("    __syncthreads();")
         src.extend("    " + line for line in merge_lines)
+    if times_aux is not None:
+        src.append("    __syncthreads();")
+    stamp(2)
+    if dynamic:
+        src.append("    if (threadIdx.x == 0) {")
+        src.append("        __threadfence();")
+        src.append("        if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1u) { p.sched[0] = 0u; p.sched[1] = 0u; __threadfence(); }")
+        src.append("    }")
     src.append("}")
     return "\n".join(src) + "\n"
 
@@ -1301,6 +1416,10 @@ def generate(spec, coltypes, options=None):
         naux += 1
         merge.append("if (threadIdx.x == 0 && *HB_FXMISS != 0u && p.aux[%d] != nullptr)" % k.fx_aux)
         merge.append("    atomicAdd(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), (hb_u64)*HB_FXMISS);" % k.fx_aux)
+    k.times_aux = None
+    if options.get("block_times", False):
+        k.times_aux = naux
+        naux += 1
     k.naux = naux
     k.deterministic = bool(options.get("deterministic", False))
     # deterministic mode: per histogram [(scale index, destination column mask)] of its float64 slots, in slot order
@@ -1310,7 +1429,8 @@ def generate(spec, coltypes, options=None):
             if hp.fx:
                 k.exact[hp.hid] = [(hp.fx_index[t], sum(1 << c for c in hp.dest[t])) for t in hp.f64_terms]
     unroll = _unroll(plans, options)
-    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll)
+    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll,
+                            times_aux=k.times_aux, dynamic=False if options.get("prefetch", False) else options.get("dynamic", False))
     k.cols = list(prog.cols)
     k.plans = plans
     k.smem_bytes = smem_cap

@@ -536,6 +536,20 @@ static int staging_reserve(int buf, int col, size_t bytes) {
     return HB_OK;
 }
 
+// Counters of the dynamic tile hand-out (HbParams::sched): one pair per stream, because launches on one stream run one
+// after the other (the last block of a launch zeroes the pair again) while launches on different streams may overlap.
+static std::vector<std::pair<cudaStream_t, hb_u32*>> g_sched;
+static int sched_for(cudaStream_t stream, hb_u32** out) {
+    for (auto& e : g_sched)
+        if (e.first == stream) { *out = e.second; return HB_OK; }
+    hb_u32* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, 256));
+    CUDA_TRY(cudaMemset(p, 0, 256));
+    g_sched.emplace_back(stream, p);
+    *out = p;
+    return HB_OK;
+}
+
 static int launch(hb_program* prog, const HbParams& params, int grid) {
     void* args[1] = {(void*)&params};
     DRV_TRY(g_drv.LaunchKernel(prog->fn, (unsigned)grid, 1, 1, (unsigned)prog->threads, 1, 1,
@@ -577,6 +591,8 @@ extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols,
     for (int a = 0; a < naux; ++a) base.aux[a] = aux[a];
     if (nwin < 0 || nwin > HB_MAX_WIN) return fail(HB_ERR_ARG, "too many window parameters");
     for (int i = 0; i < nwin; ++i) base.win[i] = win[i];
+    rc = sched_for(g_stream, &base.sched);
+    if (rc) return rc;
 
     const int tile = prog->threads * 4;
     const int resident = g_sm_count * prog->blocks_per_sm;

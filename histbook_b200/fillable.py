@@ -272,6 +272,9 @@ def fill_hists(plan, hists, arrays, timed=False):
             if vkern.fx_terms:
                 fx = _fx_scales(plan, vsig, vkern, vrng, vrprog, cols, length)
                 vaux[vkern.fx_aux] = plan.fx_stat.ptr
+            if vkern.times_aux is not None:
+                plan.block_times = engine.DeviceBuffer(numpy.zeros(3 * 4096, dtype=numpy.uint64))
+                vaux[vkern.times_aux] = plan.block_times.ptr
             exact = None
             if vkern.deterministic and vkern.exact:
                 # deterministic mode: two zeroed 192-bit accumulators (upper / lower exponent window) per (row, float64 slot)
@@ -363,6 +366,8 @@ def fill_hists(plan, hists, arrays, timed=False):
         kern, prog = used[1], used[2]
         for st in stores:
             st.mark_filled()
+        if kern.times_aux is not None and length > 0:
+            stats["block_times"] = plan.block_times.read(numpy.uint64).reshape(-1, 3)[:stats.get("grid", 0)].tolist()
         if kern.fx_terms and _options.get("fx_stats", False):
             stats["fx_missed_total"] = int(plan.fx_stat.read(numpy.uint64)[0])
         stats["deterministic"] = kern.deterministic

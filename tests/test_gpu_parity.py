@@ -163,3 +163,35 @@ def test_strategies_agree():
     bound = fill_oracle.fill(case["spec"], arrays, absolute=True)[0]
     assert numpy.all(numpy.abs(out["smem"] - out["global"]) <= 2e-12 * bound)
     assert numpy.array_equal(out["smem"][..., 4], out["global"][..., 4])
+
+
+def test_dynamic_tile_handout_agrees():
+    """Option ``dynamic`` (tiles handed out from a global counter instead of the static grid-stride split): every
+    event is still counted exactly once -- counts bit-exact, for whole launches, ragged tails and tiny fills."""
+    from histbook_b200 import fillable
+    c1, c3 = golden_util.load()["c1"], golden_util.load()["c3"]
+    rs = numpy.random.RandomState(5)
+    try:
+        for mode in ("tail", True):
+            fillable.set_options(dynamic=mode)
+            for n in (0, 1, 4095, 4097, 1000003, 6000000):
+                x, y = rs.normal(0, 1, n), rs.normal(0, 1, n)
+                sf = fillable.SpecFill(c1["spec"])
+                sf.fill(x=x)
+                sf.fill(x=x[: n // 3])
+                got = sf.contents()[0]
+                if n == 0:
+                    assert got is None or not numpy.any(got)
+                    continue
+                exp = fill_oracle.fill(c1["spec"], {"x": numpy.concatenate([x, x[: n // 3]])})[0]
+                assert numpy.array_equal(got, exp), (mode, n)
+                sf = fillable.SpecFill(c3["spec"])
+                sf.fill(x=x, y=y)
+                got = sf.contents()[0]
+                if n:
+                    exp = fill_oracle.fill(c3["spec"], {"x": x, "y": y})[0]
+                    bound = fill_oracle.fill(c3["spec"], {"x": x, "y": y}, absolute=True)[0]
+                    assert numpy.array_equal(got[..., 4], exp[..., 4]), (mode, n)
+                    assert numpy.all(numpy.abs(got - exp) <= 1e-12 * bound), (mode, n)
+    finally:
+        fillable.set_options(dynamic=None)
