@@ -801,12 +801,16 @@ def _loadtype(dtype):
     return ctype(dtype) if dtype != numpy.bool_ else "unsigned char"
 
 
-def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False, unroll=4, times_aux=None, dynamic=False):
+def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, window=None, prefetch=False, unroll=4, times_aux=None, dynamic=False, evict_first=False, red_evict_last=False):
     """The hand-written skeleton around the generated per-event function: persistent grid-stride loop
     over tiles of HB_THREADS*4 events, one vector load per column per thread (tail / unaligned input
     takes the scalar path), shared-memory zeroing before and block merge after."""
     src = []
     vcols_early = [slot for slot, (name, dtype, is_scalar) in enumerate(prog.cols) if not is_scalar]
+    if evict_first:
+        src.append("#define HB_STREAM_EVICT_FIRST 1")
+    if red_evict_last:
+        src.append("#define HB_RED_EVICT_LAST 1")
     src.append('#include "hb_template.cuh"')
     src.append("#define HB_THREADS %d" % threads)
     src.append("#define HB_TILE (HB_THREADS * 4)")
@@ -1430,7 +1434,8 @@ def generate(spec, coltypes, options=None):
                 k.exact[hp.hid] = [(hp.fx_index[t], sum(1 << c for c in hp.dest[t])) for t in hp.f64_terms]
     unroll = _unroll(plans, options)
     k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll,
-                            times_aux=k.times_aux, dynamic=False if options.get("prefetch", False) else options.get("dynamic", False))
+                            times_aux=k.times_aux, dynamic=False if options.get("prefetch", False) else options.get("dynamic", False),
+                            evict_first=bool(options.get("evict_first", True)), red_evict_last=bool(options.get("red_evict_last", False)))
     k.cols = list(prog.cols)
     k.plans = plans
     k.smem_bytes = smem_cap
