@@ -276,6 +276,7 @@ class Arena(object):
         check(lib().hb_arena_project(self._h, len(shape), arr, int(ncol), karr, ctypes.byref(out)))
         return Arena(_handle=out)
 
+    @property
     def __cuda_array_interface__(self):
         return {"shape": (int(self.size),), "typestr": "<f8", "data": (int(self.ptr or 0), False), "version": 3, "strides": None}
 

@@ -237,3 +237,9 @@ def test_zero_copy_ingest_of_host_containers():
         columns.bind("n", pyarrow.array([1, None, 3]))
     i = pyarrow.array(numpy.arange(5, dtype=numpy.int32))
     assert columns.bind("n", i).dtype == numpy.int32
+
+
+def test_arena_exposes_cuda_array_interface_as_property():
+    """dist.allreduce hands the arena to torch.as_tensor (zero copy): the protocol needs an attribute, not a method."""
+    from histbook_b200 import engine
+    assert isinstance(engine.Arena.__dict__["__cuda_array_interface__"], property)
