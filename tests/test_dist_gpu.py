@@ -1,5 +1,5 @@
-"""Two ranks on two GPUs (NCCL): fill in parallel, then ``dist.allreduce`` -- the device form of the reference's
-"fill in parallel, then add" (README.rst:29, Hist.__add__ histbook/hist.py:506-542).  Skipped with fewer than two GPUs
+"""One process per GPU (NCCL): fill in parallel, then ``dist.allreduce`` -- the device form of the reference's
+"fill in parallel, then add" (README.rst:29, Hist.__add__ histbook/hist.py:506-542).  The two-rank case is skipped with fewer than two GPUs
 (``gpurun --gpus 2 -- python -m pytest tests/test_dist_gpu.py -m gpu``); the host logic of the same merge is covered on
 CPU by tests/test_dist_gloo.py.
 
@@ -76,14 +76,18 @@ def _worker(rank, world, port, n, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
-def test_two_gpus_fill_then_allreduce(tmp_path):
+@pytest.mark.parametrize("world", [1, 2])
+def test_fill_then_allreduce(tmp_path, world):
+    """world = 1 runs everywhere (one rank, NCCL group of one: the zero-copy arena tensor and the collective call are
+    still exercised); world = 2 needs two GPUs."""
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     sys.path.insert(0, REPO)
     import histbook_b200
     n = 400003
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
     cols = _columns(n, 5)
     with histbook_b200.reference_path() as hb:              # one fill of everything on the reference's numpy path
         ref = _make(hb)
@@ -92,7 +96,7 @@ def test_two_gpus_fill_then_allreduce(tmp_path):
             h.fill(**cols)
             c = h._content
             expected["h%d" % i] = c if isinstance(c, numpy.ndarray) else dict((str(k), v) for k, v in c.items())
-    ranks = [numpy.load(os.path.join(str(tmp_path), "rank%d.npy" % r), allow_pickle=True)[0] for r in range(2)]
+    ranks = [numpy.load(os.path.join(str(tmp_path), "rank%d.npy" % r), allow_pickle=True)[0] for r in range(world)]
     for got in ranks:
         assert sorted(got) == sorted(expected)
         for name, exp in expected.items():
@@ -110,9 +114,9 @@ def test_two_gpus_fill_then_allreduce(tmp_path):
         assert numpy.array_equal(got["h0"], expected["h0"])
         for k in expected["h3"]:
             assert numpy.array_equal(got["h3"][k], expected["h3"][k])
-    # both ranks hold the same thing, bit for bit
+    # all ranks hold the same thing, bit for bit
     for name in expected:
-        a, b = ranks[0][name], ranks[1][name]
+        a, b = ranks[0][name], ranks[-1][name]
         if isinstance(a, dict):
             for k in a:
                 assert numpy.array_equal(a[k], b[k])
