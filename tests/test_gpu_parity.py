@@ -195,3 +195,40 @@ def test_dynamic_tile_handout_agrees():
                     assert numpy.all(numpy.abs(got - exp) <= 1e-12 * bound), (mode, n)
     finally:
         fillable.set_options(dynamic=None)
+
+
+OPTION_SETS = [
+    {"fx": False}, {"fx": True}, {"fx": "mix"}, {"window": False}, {"win_dense": True}, {"win_pair": False}, {"merge_pair": False},
+    {"win_table32": False}, {"pair_red": False}, {"prefetch": True}, {"replicas": 2}, {"f64_atomic": "exch"}, {"unroll": 1},
+    {"unroll": 0}, {"evict_first": False}, {"red_evict_last": True}, {"group_slots": 2}, {"threads": 256, "min_blocks": 4},
+    {"smem_budget": 16384}, {"block_times": True},
+]
+
+
+@pytest.mark.parametrize("options", OPTION_SETS, ids=lambda o: ",".join("%s=%s" % kv for kv in sorted(o.items())))
+def test_tuning_options_do_not_change_the_histogram(options):
+    """Every kernel-generation option of the sweeps (profiles/r01_sweeps.txt) is a different way to accumulate the same
+    sums: counts bit-exact and float sums within the bound against the oracle, for a hot-window histogram (c2), a
+    privatised profile (c3), a large global one (c5) and a group-axis Book member (c4's first 8 histograms)."""
+    from histbook_b200 import fillable
+    rs = numpy.random.RandomState(99)
+    n = 1200007                                                           # > the 1 M-event window pilot, ragged tail
+    cols = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n), "z": rs.normal(0, 1, n),
+            "w": rs.uniform(0.5, 1.5, n), "n": rs.poisson(3, n).astype(numpy.int64)}
+    cases = golden_util.load()
+    specs = [("c2", cases["c2"]["spec"]), ("c3", cases["c3"]["spec"]), ("c5", cases["c5"]["spec"]),
+             ("c4[:8]", dict(cases["c4"]["spec"], hists=cases["c4"]["spec"]["hists"][:8]))]
+    from histbook_b200 import spec as hbspec
+    try:
+        fillable.set_options(**options)
+        for name, spec in specs:
+            fields = hbspec.spec_fields(spec)
+            fills = [dict((f, cols[f]) for f in fields), dict((f, cols[f][: n // 3]) for f in fields)]
+            got = run_spec(spec, fills, device=True)
+            exp = bound = None
+            for arrays in fills:
+                exp = fill_oracle.fill(spec, arrays, exp)
+                bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+            compare("%s %r" % (name, options), spec, got, [golden_util.flatten(e) for e in exp], bound)
+    finally:
+        fillable.set_options(**dict((k, None) for k in options))
