@@ -144,6 +144,22 @@ extern "C" int hb_device_info(int* sm_count, int* max_smem_optin, int64_t* free_
 
 extern "C" int hb_set_stream(void* s) { g_stream = (cudaStream_t)s; return HB_OK; }
 
+// Order two streams: everything queued on `signaler` so far completes before anything queued on `waiter` from now on.
+// nullptr stands for the engine's compute stream.  Used around a fill whose device columns were produced on a stream
+// other than the engine's (a non-blocking side stream is not ordered with stream 0 by CUDA itself).
+extern "C" int hb_stream_wait(void* waiter, void* signaler) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    static cudaEvent_t ev = nullptr;
+    if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaStream_t w = waiter ? (cudaStream_t)waiter : g_stream, s = signaler ? (cudaStream_t)signaler : g_stream;
+    if (w == s) return HB_OK;
+    CUDA_TRY(cudaEventRecord(ev, s));
+    CUDA_TRY(cudaStreamWaitEvent(w, ev, 0));
+    return HB_OK;
+}
+
 extern "C" int hb_sync(void) {
     int rc = ensure_device();
     if (rc) return rc;

@@ -6,6 +6,7 @@ present, every compute entry point raises ``EngineError``.
 import ctypes
 import hashlib
 import os
+import sys
 import threading
 
 import numpy
@@ -46,6 +47,7 @@ SYMBOLS = {
     "hb_init": (_I, [_I]),
     "hb_device_info": (_I, [_IP, _IP, ctypes.POINTER(_I64), ctypes.POINTER(_I64)]),
     "hb_set_stream": (_I, [_P]),
+    "hb_stream_wait": (_I, [_P, _P]),
     "hb_sync": (_I, []),
     "hb_set_chunk_events": (_I, [_I64]),
     "hb_program_compile": (_I, [ctypes.c_char_p, ctypes.c_char_p, _I, _PP, ctypes.POINTER(ctypes.c_size_t)]),
@@ -345,6 +347,25 @@ class DeviceBuffer(object):
         p, self._p = getattr(self, "_p", None), None
         if p and _lib is not None:
             _lib.hb_device_free(p)
+
+
+# ----------------------------------------------------------------------------- streams
+
+def producer_stream():
+    """The CUDA stream device columns handed to ``fill`` are being produced on, if it is not the engine's own (stream 0):
+    torch's current stream when torch has a CUDA context.  Returns 0 otherwise."""
+    torch = sys.modules.get("torch")
+    if torch is None or not torch.cuda.is_initialized():
+        return 0
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)       # the handle without building a Stream object (~0.3 us)
+    if raw is not None:
+        return int(raw(init()) or 0)
+    return int(torch.cuda.current_stream().cuda_stream or 0)
+
+
+def stream_wait(waiter, signaler):
+    """hb_stream_wait: 0 stands for the engine's compute stream."""
+    check(lib().hb_stream_wait(ctypes.c_void_p(waiter or None), ctypes.c_void_p(signaler or None)))
 
 
 # ----------------------------------------------------------------------------- fill

@@ -217,6 +217,11 @@ def fill_hists(plan, hists, arrays, timed=False):
         arrays = _encode_strings(plan, arrays)
         cols, length = columns.bind_all(plan.fields, arrays)
         sig, (kern, prog, keys, kprog, rng, rprog) = plan.kernel_for(cols)
+        # device columns produced on another stream (torch's current one): CUDA does not order a non-blocking stream
+        # with the engine's, so the fill waits for the producer here and the producer for the fill at the end
+        side = engine.producer_stream() if length > 0 and any(c.location == 1 for c in cols.values()) else 0
+        if side:
+            engine.stream_wait(0, side)
 
         # group axes: which keys does this fill hold?  (numpy.unique in calc/__init__.py:150,178,182)
         discovered = {}
@@ -364,6 +369,8 @@ def fill_hists(plan, hists, arrays, timed=False):
                 stats["window"] = {"bins": wst.window["bins"], "rows": wst.window["rows"], "dense": wst.window["dense"]} if wst.window else None
                 stats["window_coverage"] = wst.window_coverage
         kern, prog = used[1], used[2]
+        if side:
+            engine.stream_wait(side, 0)
         for st in stores:
             st.mark_filled()
         if kern.times_aux is not None and length > 0:

@@ -83,6 +83,9 @@ int hb_init(int device);                                 /* select the device (i
 int hb_device_info(int* sm_count, int* max_smem_optin, int64_t* free_bytes, int64_t* total_bytes);
 int hb_set_stream(void* cuda_stream);                    /* compute stream for all later calls (default: stream 0) */
 int hb_sync(void);
+/* Stream order: work queued on `signaler` so far completes before work queued on `waiter` from now on (NULL = the
+ * engine's compute stream).  Brackets a fill whose device columns were produced on another stream. */
+int hb_stream_wait(void* waiter, void* signaler);
 int hb_set_chunk_events(int64_t events);                 /* staging chunk for host-resident columns */
 
 /* programs ---------------------------------------------------------------------------------------------- */

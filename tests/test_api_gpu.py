@@ -383,3 +383,25 @@ def test_randomised_book_against_the_reference_path():
     assert set(ours["d"]._content.keys()) == set(expect["d"].keys())
     for key in expect["d"]:
         assert numpy.allclose(ours["d"]._content[key], expect["d"][key], rtol=1e-11, atol=1e-9)
+
+
+def test_columns_produced_on_a_side_stream():
+    """Device columns written by kernels on a non-blocking torch stream: the fill (engine stream 0) must wait for them,
+    and the side stream must wait for the fill before it overwrites the columns again."""
+    import torch
+    side = torch.cuda.Stream()
+    n = 20_000_000
+    h = Hist(bin("x", 10, 0, 10))
+    total = 0
+    with torch.cuda.stream(side):
+        x = torch.empty(n, device="cuda", dtype=torch.float64)
+        for value in (0.5, 3.5, 7.5):
+            big = torch.full((n,), value, device="cuda", dtype=torch.float64)
+            for _ in range(6):
+                big = big * 1.0 + 0.0                      # keep the side stream busy ahead of the copy below
+            x.copy_(big)
+            h.fill(x=x)                                    # reads x; the next x.copy_ must not overtake it
+            total += n
+    c = h._content[:, 0]
+    assert c.sum() == total
+    assert c[1] == n and c[4] == n and c[8] == n
