@@ -83,7 +83,7 @@ def _torch_dtypes():
 
 
 class Column(object):
-    __slots__ = ("name", "dtype", "code", "is_scalar", "ptr", "location", "length", "scalar_bits", "keepalive")
+    __slots__ = ("name", "dtype", "code", "is_scalar", "ptr", "location", "device", "length", "scalar_bits", "keepalive")
 
     def __init__(self, name):
         self.name = name
@@ -92,6 +92,7 @@ class Column(object):
         self.is_scalar = False
         self.ptr = None
         self.location = 0          # 0 host, 1 device
+        self.device = None         # CUDA device index of a device column, when the object tells (torch tensors)
         self.length = None
         self.scalar_bits = 0
         self.keepalive = None      # whatever owns the memory `ptr` points into
@@ -161,6 +162,7 @@ def bind(name, value):
                 col.length = value.shape[0]
                 col.ptr = value.data_ptr() if col.length > 0 else 0
                 col.location = 1
+                col.device = value.device.index
                 col.keepalive = value
                 return col
             value = value.detach().numpy()

@@ -219,7 +219,13 @@ def fill_hists(plan, hists, arrays, timed=False):
         sig, (kern, prog, keys, kprog, rng, rprog) = plan.kernel_for(cols)
         # device columns produced on another stream (torch's current one): CUDA does not order a non-blocking stream
         # with the engine's, so the fill waits for the producer here and the producer for the fill at the end
-        side = engine.producer_stream() if length > 0 and any(c.location == 1 for c in cols.values()) else 0
+        on_device = [c for c in cols.values() if c.location == 1]
+        if on_device:
+            dev = engine.init()
+            for c in on_device:
+                if c.device is not None and c.device != dev:
+                    raise codegen.UnsupportedError("field {0!r} lives on cuda:{1} but this process fills on cuda:{2} (one process per GPU)".format(c.name, c.device, dev))
+        side = engine.producer_stream() if length > 0 and on_device else 0
         if side:
             engine.stream_wait(0, side)
 

@@ -405,3 +405,14 @@ def test_columns_produced_on_a_side_stream():
     c = h._content[:, 0]
     assert c.sum() == total
     assert c[1] == n and c[4] == n and c[8] == n
+
+
+def test_column_on_another_gpu_is_refused():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    h = Hist(bin("x", 10, 0, 10))
+    with pytest.raises(NotImplementedError, match="lives on cuda:1"):
+        h.fill(x=torch.ones(100, device="cuda:1", dtype=torch.float64))
+    h.fill(x=torch.ones(100, device="cuda:0", dtype=torch.float64))
+    assert h._content[:, 0].sum() == 100
