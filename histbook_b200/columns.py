@@ -83,7 +83,7 @@ def _torch_dtypes():
 
 
 class Column(object):
-    __slots__ = ("name", "dtype", "code", "is_scalar", "ptr", "location", "device", "length", "scalar_bits", "keepalive")
+    __slots__ = ("name", "dtype", "code", "is_scalar", "ptr", "location", "device", "stream", "length", "scalar_bits", "keepalive")
 
     def __init__(self, name):
         self.name = name
@@ -93,6 +93,7 @@ class Column(object):
         self.ptr = None
         self.location = 0          # 0 host, 1 device
         self.device = None         # CUDA device index of a device column, when the object tells (torch tensors)
+        self.stream = None         # __cuda_array_interface__ v3 "stream": the producer's stream the consumer has to wait for
         self.length = None
         self.scalar_bits = 0
         self.keepalive = None      # whatever owns the memory `ptr` points into
@@ -136,6 +137,9 @@ def _from_cuda_array_interface(col, obj, cai):
     col.location = 1
     col.length = int(shape[0])
     col.keepalive = obj
+    stream = cai.get("stream")
+    if stream is not None and int(stream) != 1:                # None: nothing to wait for; 1: the legacy default stream (ours)
+        col.stream = int(stream)
     return col
 
 

@@ -225,6 +225,8 @@ def fill_hists(plan, hists, arrays, timed=False):
             for c in on_device:
                 if c.device is not None and c.device != dev:
                     raise codegen.UnsupportedError("field {0!r} lives on cuda:{1} but this process fills on cuda:{2} (one process per GPU)".format(c.name, c.device, dev))
+                if c.stream is not None:                      # __cuda_array_interface__ v3: wait for the exporter's stream
+                    engine.stream_wait(0, c.stream)
         side = engine.producer_stream() if length > 0 and on_device else 0
         if side:
             engine.stream_wait(0, side)

@@ -416,3 +416,29 @@ def test_column_on_another_gpu_is_refused():
         h.fill(x=torch.ones(100, device="cuda:1", dtype=torch.float64))
     h.fill(x=torch.ones(100, device="cuda:0", dtype=torch.float64))
     assert h._content[:, 0].sum() == 100
+
+
+def test_cuda_array_interface_stream_key_is_honoured():
+    """__cuda_array_interface__ v3: an exporter that names its stream is waited for, whatever torch's current stream is."""
+    import torch
+
+    class Exported(object):
+        def __init__(self, tensor, stream):
+            self.tensor, self.stream = tensor, stream
+
+        @property
+        def __cuda_array_interface__(self):
+            out = dict(self.tensor.__cuda_array_interface__)
+            out["stream"], out["version"] = self.stream, 3
+            return out
+
+    side = torch.cuda.Stream()
+    n = 20_000_000
+    with torch.cuda.stream(side):
+        x = torch.full((n,), 2.5, device="cuda", dtype=torch.float64)
+        for _ in range(8):
+            x = x * 1.0 + 0.0
+    h = Hist(bin("x", 10, 0, 10))
+    h.fill(x=Exported(x, side.cuda_stream))                # torch's current stream is the default one here
+    assert h._content[3, 0] == n
+    side.synchronize()
