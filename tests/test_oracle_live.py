@@ -122,3 +122,39 @@ def test_oracle_equals_reference_on_random_definitions(seed):
                     assert numpy.array_equal(a, b, equal_nan=True), (source, k)
             compared += 1
     assert compared >= 22, compared
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_equals_reference_on_random_books(seed):
+    """The same through ``Book.fill`` (histbook/book.py:540-586): one pass of shared instructions, every member's
+    ``_postfill``; the oracle fills the book's spec in one call."""
+    rs = numpy.random.RandomState(3000 + seed)
+    compared = 0
+    with histbook_b200.reference_path() as hb, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = dict((name, getattr(hb, name)) for name in ("Hist", "bin", "intbin", "split", "cut", "profile", "groupby", "groupbin"))
+        for _ in range(25):
+            sources = [_definition(rs) for _ in range(int(rs.choice([2, 3, 4])))]
+            fills = [_columns(rs, int(rs.choice([17, 500, 2000]))) for _ in range(int(rs.choice([1, 2])))]
+            try:
+                hists = [eval(source, dict(env)) for source in sources]
+                book = hb.Book(**dict(("h%d" % i, h) for i, h in enumerate(hists)))
+                for cols in fills:
+                    book.fill(**cols)
+            except Exception:
+                continue
+            members = [book["h%d" % i] for i in range(len(hists))]
+            spec = hbspec.book_spec(members)
+            contents = None
+            for cols in fills:
+                contents = fill_oracle.fill(spec, cols, contents)
+            assert len(contents) == len(members)
+            for source, member, got in zip(sources, members, contents):
+                exp, got = _flat(member._content), _flat(got)
+                assert (exp is None) == (got is None), source
+                if exp is not None:
+                    assert [k for k, _ in got] == [k for k, _ in exp], source
+                    for (k, a), (_, b) in zip(got, exp):
+                        assert a.shape == b.shape and numpy.array_equal(a, b, equal_nan=True), (source, k)
+            compared += 1
+    assert compared >= 5, compared
