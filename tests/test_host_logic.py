@@ -243,3 +243,18 @@ def test_arena_exposes_cuda_array_interface_as_property():
     """dist.allreduce hands the arena to torch.as_tensor (zero copy): the protocol needs an attribute, not a method."""
     from histbook_b200 import engine
     assert isinstance(engine.Arena.__dict__["__cuda_array_interface__"], property)
+
+
+def test_cuda_array_interface_stream_key_is_recorded():
+    """__cuda_array_interface__ v3 ``stream``: None and 1 (legacy default stream) need no fence, anything else is kept
+    for hb_stream_wait (fillable.fill_hists).  Binding never touches the memory, so a fake exporter will do on CPU."""
+    from histbook_b200 import columns, engine
+
+    class Exporter(object):
+        def __init__(self, stream):
+            self.__cuda_array_interface__ = {"shape": (8,), "typestr": "<f8", "data": (0x7F0000000000, False), "version": 3, "stream": stream}
+
+    for stream, expect in ((None, None), (1, None), (2, 2), (0x5500AA00, 0x5500AA00)):
+        col = columns.bind("x", Exporter(stream))
+        assert (col.location, col.length, col.ptr, col.stream, col.code) == (1, 8, 0x7F0000000000, expect, 0)
+    assert engine.producer_stream() == 0                      # no CUDA context in this process: nothing to wait for
