@@ -1,5 +1,5 @@
 """Offline hunt with the generator of tests/test_random_definitions_gpu.py over many more seeds: device (C ABI) against the
-unmodified reference (baseline/_ref), mismatches printed instead of asserted.  Usage (GPU box): python tools/random_parity_hunt.py 100 120"""
+unmodified reference (baseline/_ref), mismatches printed instead of asserted.  Usage (GPU box): python tools/random_parity_hunt.py 100 120 [dtypes]"""
 import os
 import sys
 import warnings
@@ -20,8 +20,27 @@ from test_gpu_parity import compare  # noqa: E402
 from test_random_definitions_gpu import EXACT_EXPRS  # noqa: E402
 
 
+def cast(cols, rs):
+    """Mixed column dtypes (numpy computes in the column's dtype: float32 stays float32, small ints promote like NEP 50)."""
+    out = dict(cols)
+    mode = rs.randint(0, 4)
+    if mode == 0:
+        out["x"] = out["x"].astype(numpy.float32)
+    elif mode == 1:
+        for name in ("x", "y", "w"):
+            out[name] = out[name].astype(numpy.float32)
+    elif mode == 2:
+        out["z"] = numpy.nan_to_num(out["z"] * 10).astype(numpy.int16)
+        out["n"] = out["n"].astype(numpy.uint8)
+    else:
+        out["y"] = numpy.nan_to_num(out["y"], nan=0, posinf=9, neginf=-9).astype(numpy.int64)
+        out["w"] = out["w"].astype(numpy.float32)
+    return out
+
+
 def main():
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
+    dtypes = len(sys.argv) > 3 and sys.argv[3] == "dtypes"
     live.EXPRS = EXACT_EXPRS
     compared = unsupported = 0
     bad = []
@@ -34,6 +53,9 @@ def main():
             for _ in range(30):
                 source = live._definition(rs)
                 fills = [live._columns(rs, int(rs.choice([1, 17, 500, 4099, 20000]))) for _ in range(int(rs.choice([1, 2])))]
+                if dtypes:
+                    fills[0] = cast(fills[0], rs)
+                    fills[1:] = [dict((k, v.astype(fills[0][k].dtype)) for k, v in cols.items()) for cols in fills[1:]]
                 try:
                     hist = eval(source, dict(env))
                     for cols in fills:
