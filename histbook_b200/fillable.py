@@ -5,15 +5,14 @@ Stands in for ``Fillable._fill`` (histbook/fill.py:85-162), ``Hist._prefill`` / 
 (the neutral spec, built once), one generated kernel per set of column dtypes (NVRTC, cached), one
 launch per fill that updates every histogram of the book in a single pass over the columns.
 """
+import json
+import os
 import threading
 
 import numpy
 
 from histbook_b200 import codegen, columns, engine, spec as hbspec
 from histbook_b200.store import GroupInfo, Store
-
-import json
-import os
 
 # kernel-generation options; HB_OPTIONS='{"fx": true}' presets them for a whole process (tests, tuning)
 _options = dict(json.loads(os.environ.get("HB_OPTIONS", "") or "{}"))
@@ -22,7 +21,18 @@ last_stats = {}
 
 
 def set_options(**kwargs):
-    """Kernel-generation options (``smem_budget``, ``threads``, ``min_blocks``, ``strategy``); clears cached kernels."""
+    """Kernel-generation options; ``name=None`` restores a default.  Changing any of them drops the cached kernels
+    (they are part of the kernel source, hence of its cache key).
+
+    Semantics: ``deterministic`` (every float64 sum the correctly rounded exact sum), ``fx_stats``.
+    Accumulation: ``fx`` (False | True | "mix" | [slots] | "auto"), ``fx_auto_max_terms``, ``strategy`` ({hist id | "*":
+    "smem" | "global" | "window"}), ``smem_budget``, ``window`` / ``win_dense`` / ``win_pair`` / ``win_smem`` /
+    ``win_threads`` / ``win_min_blocks`` / ``win_table32`` / ``win_max_rows`` / ``win_max_hist_bytes``, ``merge_pair``,
+    ``pair_red``, ``group_slots``, ``replicas``, ``f64_atomic`` ("cas" | "exch").
+    Launch shape and loop: ``threads``, ``min_blocks``, ``unroll`` (4 | 1 | 0), ``prefetch``, ``dynamic`` (False | "tail" |
+    True), ``evict_first``, ``red_evict_last``.  Measurement: ``block_times``.
+    Defaults are the measured best (profiles/r01_sweeps.txt); tests/test_gpu_parity.py checks that none of them changes a
+    histogram."""
     _options.update(kwargs)
     for k in [k for k, v in _options.items() if v is None]:
         del _options[k]
