@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- fill throughput of the B200 fill path (events/s), beside the reference's numpy fill on host cores.
 
-    python bench.py                               # N=1, workload c2 (BASELINE.json configs[1]), 10 steps
+    python bench.py                               # N=1: the north-star config c4 (64-histogram Book, 1e9 events) through Book.fill
     python bench.py --workload c5 --steps 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
-        bench.py --gpus 8 --steps 10 --warmup 3   # one rank per GPU, events sharded, ranks merged with NCCL
+        bench.py --gpus 8 --steps 10 --warmup 3   # one rank per GPU; the SAME total events sharded over the ranks (strong scaling)
     python bench.py --impl reference              # the reference's own CPU path, all host cores
 
-A step = one ``fill`` of the whole workload (every event once) from device-resident columns, plus -- for N>1 --
-the rank merge (``Hist.__add__`` across ranks, histbook/hist.py:506-542) as one NCCL collective.  Prints ONE JSON line.
+A step = one ``Book.fill`` / ``Hist.fill`` (the histbook API, backend installed by ``import histbook_b200``) of this
+rank's shard of the workload from device-resident columns, plus -- for N>1 -- the rank merge through the product's
+``histbook_b200.dist.Merger`` (the distributed ``Hist.__add__``, histbook/hist.py:506-542): ONE NCCL collective per step for
+the whole book.  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -26,19 +28,24 @@ import numpy                                        # noqa: E402
 
 import bench_cpu                                    # noqa: E402
 
+CPU_SAMPLE = {"c1": 4 * 10**6, "c2": 4 * 10**6, "c3": 2 * 10**6, "c4": 10**5, "c5": 2 * 10**6}     # events per process and step
+
 
 def ncu_traffic(workload, n):
     """dram bytes per launch of the fill kernel from this round's `ncu --set full` capture (profiles/traffic.json),
-    or None when no capture exists for this workload at this size."""
+    scaled to this launch's events when the capture was taken at another size (the traffic is the input columns, O(N))."""
     path = os.path.join(REPO, "profiles", "traffic.json")
     try:
         with open(path) as f:
             entry = json.load(f).get(workload)
     except (OSError, ValueError):
         return None, None
-    if not entry or int(entry["events"]) != int(n):
+    if not entry:
         return None, None
-    return int(entry["dram_bytes_per_launch"]), entry.get("source")
+    events = int(entry["events"])
+    if events == int(n):
+        return int(entry["dram_bytes_per_launch"]), entry.get("source")
+    return int(entry["dram_bytes_per_launch"] * (float(n) / events)), "%s, captured at %d events and scaled by N" % (entry.get("source"), events)
 
 
 def peaks():
@@ -109,8 +116,7 @@ def run_reference(args):
         return
     workload = args.workload
     procs = os.cpu_count() or 1
-    # bounded sample per step: ~1-3 s of CPU work on every core
-    per_proc = {"c1": 4 * 10**6, "c2": 4 * 10**6, "c3": 2 * 10**6, "c4": 10**5, "c5": 2 * 10**6}[workload]
+    per_proc = CPU_SAMPLE[workload]                 # bounded sample per step: ~1-3 s of CPU work on every core
     kind, per_rep, total = bench_cpu.run_parallel(workload, per_proc, procs, reps=args.warmup + args.steps)
     timed = per_rep[args.warmup:]
     sec = sum(timed)
@@ -118,7 +124,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "fill events/sec", "value": value, "unit": "events/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(timed), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s" % (workload, bench_cpu.DESCRIPTION[workload]),
                    "events_per_step": total, "note": "bounded sample of the workload; fill is O(N)"},
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": procs, "kind": kind,
@@ -145,15 +151,73 @@ def device_columns(torch, workload, n, seed, device):
     return cols
 
 
-def measure(torch, dist, filler, cols, steps, warmup, world, merge):
+class Target(object):
+    """What a user calls: the histbook Hist (or Book of Hists) of a workload with the device backend installed by
+    ``import histbook_b200`` -- or, where the histbook package itself is not importable, the spec-level driver that
+    Hist.fill / Book.fill delegate to."""
+
+    def __init__(self, workload):
+        from histbook_b200 import _ref, fillable
+        case = bench_cpu.load_case(bench_cpu.WORKLOADS[workload][0])
+        self.spec = case["spec"]
+        if _ref.available():
+            import histbook_b200
+            histbook_b200.install()
+            hb = _ref.load()
+            env = dict((n, getattr(hb, n)) for n in ("Hist", "Book", "bin", "intbin", "split", "cut", "profile", "groupby", "groupbin"))
+            self.hists = [eval(src, dict(env)) for src in case["hists"]]
+            self.obj = self.hists[0] if len(self.hists) == 1 else hb.Book(dict(("h%03d" % i, h) for i, h in enumerate(self.hists)))
+            self.api = "histbook %s.fill(**columns) with the backend installed by `import histbook_b200`" % type(self.obj).__name__
+            self.fill = lambda cols: self.obj.fill(**cols)
+        else:
+            self.obj = fillable.SpecFill(self.spec)
+            self.hists = self.obj.hists
+            self.api = "fillable.SpecFill.fill(columns) (histbook itself not importable here)"
+            self.fill = self.obj.fill
+
+    def clear(self):
+        for h in self.hists:
+            h.clear()
+
+    def read(self):
+        """Device -> host read of every histogram's bins, as proj/export/vega would trigger; returns the bytes read."""
+        total = 0
+        for h in self.hists:
+            c = h._content if hasattr(h, "_content") else h.content
+            total += content_bytes(c)
+        return total
+
+    def peek(self, i):
+        st = self.hists[i].__dict__.get("_hb")
+        return None if st is None else st.peek()
+
+
+def content_bytes(c):
+    if c is None:
+        return 0
+    if isinstance(c, numpy.ndarray):
+        return c.nbytes
+    return sum(content_bytes(v) for v in c.values())
+
+
+def content_sum(c):
+    if c is None:
+        return 0.0
+    if isinstance(c, numpy.ndarray):
+        return float(c.sum())
+    return sum(content_sum(v) for v in c.values())
+
+
+def measure(torch, dist, target, cols, steps, warmup, world, merger):
     """warmup + timed steps; device time by CUDA events on the launch stream, max over ranks."""
     from histbook_b200 import fillable
     launches = 0
-    finish = getattr(merge, "finish", lambda: None)
     for _ in range(warmup):
-        filler.fill(cols)
-        merge()
-    finish()
+        target.fill(cols)
+        if merger is not None:
+            merger.start()
+    if merger is not None:
+        merger.wait()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -161,10 +225,12 @@ def measure(torch, dist, filler, cols, steps, warmup, world, merge):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        filler.fill(cols)
+        target.fill(cols)
         launches += fillable.last_stats.get("launches", 0) + fillable.last_stats.get("keys_launches", 0)
-        merge()
-    finish()                                       # every step's merge has completed before the clock stops
+        if merger is not None:
+            merger.start()                         # one snapshot + one NCCL collective for the whole book, on a side stream
+    if merger is not None:
+        merger.wait()                              # every step's merge has completed before the clock stops
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -178,10 +244,32 @@ def measure(torch, dist, filler, cols, steps, warmup, world, merge):
     return ms, launches
 
 
+def check_merge(torch, dist, target, merger, world, fills, n_rank, workload):
+    """Outside the timed region: the merged book must be the sum of the ranks' books -- every histogram's total against
+    an independent all-reduce of the rank-local totals, and the unweighted histogram's total count bit-exact against
+    the number of events all ranks filled."""
+    merged = merger.start().contents()
+    local = numpy.array([content_sum(target.peek(i)) for i in range(len(target.hists))], dtype=numpy.float64)
+    t = torch.from_numpy(local.copy()).cuda()
+    dist.all_reduce(t)
+    expect = t.cpu().numpy()
+    got = numpy.array([content_sum(c) for c in merged])
+    if not numpy.all(numpy.abs(got - expect) <= 1e-9 * numpy.maximum(numpy.abs(expect), 1.0)):
+        raise SystemExit("bench: merged histogram totals differ from the sum of the rank totals: %r vs %r" % (got.tolist()[:8], expect.tolist()[:8]))
+    counts = {"c1": 0, "c4": 0}.get(workload)      # an unweighted histogram with every flow bin: each event lands in exactly one bin
+    if counts is not None:
+        n_all = torch.tensor([n_rank], device="cuda", dtype=torch.int64)
+        dist.all_reduce(n_all)
+        if got[counts] != float(int(n_all.item()) * fills):
+            raise SystemExit("bench: merged count %r != events filled by all ranks %d" % (got[counts], int(n_all.item()) * fills))
+    return {"histograms": len(merged), "totals_checked": int(len(got)), "count_exact": counts is not None,
+            "collectives_per_merge": merger.collectives_last}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from histbook_b200 import engine, fillable
+    from histbook_b200 import dist as hbdist, engine, fillable
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,84 +285,67 @@ def run_gpu(args):
 
     workload = args.workload
     case_name, default_n, bytes_per_event, _ = bench_cpu.WORKLOADS[workload]
-    n = int(float(args.events)) if args.events else default_n          # per GPU (weak scaling: every rank gets the full workload size)
-    spec = bench_cpu.load_case(case_name)["spec"]
-    cols = device_columns(torch, workload, n, 12345 + rank, device)
-    filler = fillable.SpecFill(spec)
-    filler.fill(dict((k, v[:4096]) for k, v in cols.items()))     # compile + first touch (excluded)
-    filler.clear()
+    total_n = int(float(args.events)) if args.events else default_n
+    strong = args.scaling == "strong"
+    lo, hi = hbdist.shard(total_n, rank, world) if strong else (0, total_n)
+    n = hi - lo                                                   # events this rank fills per step
+    n_all = total_n if strong else total_n * world
 
-    # rank merge = Hist.__add__ over ranks: all-reduce for small contents, reduce-scatter for large ones.
-    # One merge per step.  The fill stream only snapshots the bins (device copy, in order with the kernels); the
-    # collective runs on a side stream and overlaps the next step's fill; two snapshot buffers alternate, and
-    # merge.finish() joins the side stream before the timed region ends.
-    merged, snaps, freed = {}, {}, {}
-    side = torch.cuda.Stream(device=device) if world > 1 else None
-    counter = [0]
+    def setup(n_rank):
+        cols = device_columns(torch, workload, n_rank, 12345 + rank, device)
+        target = Target(workload)
+        target.fill(dict((k, v[:4096]) for k, v in cols.items()))     # compile + first touch (excluded)
+        target.clear()
+        merger = hbdist.Merger(target.obj) if world > 1 else None
+        return cols, target, merger
 
-    def merge():
-        if world == 1:
-            return
-        parity = counter[0] & 1
-        counter[0] += 1
-        cur = torch.cuda.current_stream()
-        if parity in freed:
-            cur.wait_event(freed[parity])               # the collective that read this snapshot two steps ago is done
-        items = []
-        for i, arena in enumerate(filler.arenas()):
-            t = arena.as_tensor()
-            snap = snaps.get((i, parity))
-            if snap is None or snap.numel() != t.numel():
-                snap = snaps[(i, parity)] = torch.empty_like(t)
-            snap.copy_(t)
-            items.append((i, snap))
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        side.wait_event(ready)
-        with torch.cuda.stream(side):
-            for i, snap in items:
-                if snap.numel() * 8 >= (8 << 20) and snap.numel() % world == 0:
-                    out = merged.get(i)
-                    if out is None or out.numel() != snap.numel() // world:
-                        out = merged[i] = torch.empty(snap.numel() // world, device=device, dtype=torch.float64)
-                    dist.reduce_scatter_tensor(out, snap)
-                else:
-                    dist.all_reduce(snap)
-            done = torch.cuda.Event()
-            done.record(side)
-            freed[parity] = done
-
-    def finish():
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)
-    merge.finish = finish
-
+    cols, target, merger = setup(n)
+    api = target.api
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches = measure(torch, dist, filler, cols, args.steps, args.warmup, world, merge)
+    ms, launches = measure(torch, dist, target, cols, args.steps, args.warmup, world, merger)
     clocks = sampler.stop() if rank == 0 else None
     main_stats = dict(fillable.last_stats)
     ms_step = ms / args.steps
-    value = world * n / (ms_step * 1e-3)
-
-    # roofline of the dominant (only) kernel: algorithmic bytes = bytes of the input columns, each read once
-    achieved = n * bytes_per_event / (ms_step * 1e-3) / 1e9
+    value = n_all / (ms_step * 1e-3)
+    merge_check = None
     if world > 1:
-        # kernel alone (without the collective) for the roofline
-        ms_k, _ = measure(torch, dist, filler, cols, args.steps, 1, world, lambda: None)
-        achieved = n * bytes_per_event / (ms_k / args.steps * 1e-3) / 1e9
+        merge_check = check_merge(torch, dist, target, merger, world, args.warmup + args.steps, n, workload)
 
-    # ---- end to end through the public API with HOST (pinned) buffers: H2D of every column + D2H of the result per step
+    # roofline of the dominant kernel: algorithmic bytes = bytes of the input columns, each read once
+    if world > 1:
+        ms_k, _ = measure(torch, dist, target, cols, args.steps, 1, world, None)      # fill alone (without the collective)
+    else:
+        ms_k = ms
+    achieved = n * bytes_per_event / (ms_k / args.steps * 1e-3) / 1e9
+    keys_note = ""
+    if main_stats.get("keys_launches"):
+        keys_note = " (+ the key-discovery kernel of the group axes, which reads the group columns once more; its time is inside the step)"
+
+    # the other scaling mode beside it (N>1): every rank fills the whole workload size
+    other_scaling = None
+    if world > 1 and not args.no_weak:
+        cols = target = merger = None
+        torch.cuda.empty_cache()
+        n2 = total_n if strong else hbdist.shard(total_n, rank, world)[1] - hbdist.shard(total_n, rank, world)[0]
+        cols, target, merger = setup(n2)
+        ms2, _ = measure(torch, dist, target, cols, args.steps, args.warmup, world, merger)
+        t = torch.tensor([n2], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        other_scaling = {"scaling": "weak" if strong else "strong", "events_per_gpu_per_step": n2, "ms_per_step": ms2 / args.steps,
+                         "value": int(t.item()) / (ms2 / args.steps * 1e-3), "unit": "events/s"}
+
+    # ---- end to end through the public API with HOST buffers: H2D of every column + D2H of the result per step
     e2e = None
+    cols = target = merger = None
+    torch.cuda.empty_cache()
     if not args.no_e2e:
-        e2e = run_e2e(torch, dist, workload, spec, n if args.e2e_events is None else int(float(args.e2e_events)), rank, world, device, args)
+        e2e = run_e2e(torch, dist, workload, n if args.e2e_events is None else int(float(args.e2e_events)), rank, world, device, args)
 
     extras = {}
-    if rank == 0 and world == 1 and args.extras:
-        del cols
-        torch.cuda.empty_cache()
-        for other in ("c1", "c3", "c5", "c4"):
+    if rank == 0 and world == 1 and not args.no_extras:
+        for other in ("c1", "c2", "c3", "c5", "c4"):
             if other == workload:
                 continue
             try:
@@ -285,7 +356,7 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
-        per_proc = {"c1": 4 * 10**6, "c2": 4 * 10**6, "c3": 2 * 10**6, "c4": 10**5, "c5": 2 * 10**6}[workload]
+        per_proc = CPU_SAMPLE[workload]
         kind, per_rep, total = bench_cpu.run_parallel(workload, per_proc, procs, reps=3)
         sec = min(per_rep[1:])
         cpu = {"value": total / sec, "unit": "events/s", "cores": procs, "kind": kind,
@@ -296,22 +367,26 @@ def run_gpu(args):
         traffic, traffic_src = ncu_traffic(workload, n)
         line = {
             "metric": "fill events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (workload, bench_cpu.DESCRIPTION[workload]), "events_per_gpu_per_step": n,
-                       "bytes_per_event": bytes_per_event, "l2": "inputs (%.1f GB per GPU) larger than L2" % (n * bytes_per_event / 1e9)
-                       if n * bytes_per_event > 256e6 else "L2 flushed between steps is NOT done; inputs fit L2",
-                       "rank_merge": "none (1 GPU)" if world == 1 else "NCCL all-reduce / reduce-scatter of the bin contents every step, on a side stream overlapping the next step's fill; all merges complete inside the timed region",
+            "config": {"workload": "%s: %s" % (workload, bench_cpu.DESCRIPTION[workload]), "events_per_step_all_gpus": n_all,
+                       "events_per_gpu_per_step": n, "bytes_per_event": bytes_per_event, "api": api + " on device-resident torch columns",
+                       "l2": "inputs (%.1f GB per GPU) larger than L2" % (n * bytes_per_event / 1e9)
+                       if n * bytes_per_event > 256e6 else "inputs fit L2 and L2 is NOT flushed between steps",
+                       "rank_merge": "none (1 GPU)" if world == 1 else "histbook_b200.dist.Merger: one snapshot + ONE NCCL collective for the whole book every step (plus one int64 key all-gather for group axes), on a side stream overlapping the next step's fill; all merges complete inside the timed region",
+                       "merge_check": merge_check,
                        "kernel": {"regs": stats.get("regs"), "smem_bytes": stats.get("smem_bytes"), "grid": stats.get("grid"),
                                   "blocks_per_sm": stats.get("blocks_per_sm"), "hot_window": stats.get("window"),
                                   "hot_window_coverage_est": stats.get("window_coverage")}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "traffic_source": traffic_src, "algorithmic_bytes_per_launch": n * bytes_per_event,
-                         "kernel": "hb_fill_kernel (generated per book; the only kernel in the timed region)",
+                         "kernel": "hb_fill_kernel (generated per book)" + keys_note,
                          "peak_source": hbm_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if other_scaling:
+            line["other_scaling"] = other_scaling
         if extras:
             line["other_workloads"] = extras
         print(json.dumps(line))
@@ -319,99 +394,112 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def api_target(workload, spec):
-    """What a user would call: the histbook Hist (or Book) of the workload with the device backend installed
-    (``import histbook_b200``) -- or, where the histbook package itself is not importable, the spec-level driver that
-    Hist.fill / Book.fill delegate to.  Returns (fill(host_columns), read_result() -> bytes read, description)."""
-    from histbook_b200 import _ref, fillable
-    if _ref.available():
-        import histbook_b200
-        histbook_b200.install()
-        hb = _ref.load()
-        env = dict((n, getattr(hb, n)) for n in ("Hist", "Book", "bin", "intbin", "split", "cut", "profile", "groupby", "groupbin"))
-        hists = [eval(src, dict(env)) for src in bench_cpu.load_case(bench_cpu.WORKLOADS[workload][0])["hists"]]
-        target = hists[0] if len(hists) == 1 else hb.Book(dict(("h%03d" % i, h) for i, h in enumerate(hists)))
+def host_columns(torch, workload, n, seed, device, pinned):
+    """Plain numpy arrays in pageable host memory (what ``numpy.random`` gives a user) -- or page-locked ones."""
+    host, nbytes = {}, 0
+    chunk = 1 << 26
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    for name in bench_cpu.WORKLOADS[workload][3]:
+        dtype = numpy.int64 if name == "n" else numpy.float64
+        if pinned:
+            out_t = torch.empty(n, dtype=torch.int64 if name == "n" else torch.float64, pin_memory=True)
+            out = out_t.numpy()
+        else:
+            out = numpy.empty(n, dtype=dtype)
+        for a in range(0, n, chunk):
+            m = min(chunk, n - a)
+            if name == "w":
+                part = torch.rand(m, generator=g, device=device, dtype=torch.float64) + 0.5
+            elif name == "n":
+                part = torch.poisson(torch.full((m,), 3.0, device=device, dtype=torch.float32), generator=g).to(torch.int64)
+            else:
+                part = torch.randn(m, generator=g, device=device, dtype=torch.float64)
+            out[a:a + m] = part.cpu().numpy()
+        host[name] = out
+        nbytes += out.nbytes
+    return host, nbytes
 
-        def read():
-            total = 0
-            for h in hists:
-                c = h._content                      # device -> host copy, as proj/export/vega would trigger
-                total += c.nbytes if isinstance(c, numpy.ndarray) else sum(v.nbytes for v in c.values())
-            return total
-        return (lambda cols: target.fill(**cols)), read, "histbook %s.fill(**host numpy columns) + ._content (backend installed by `import histbook_b200`)" % type(target).__name__
-    filler = fillable.SpecFill(spec)
 
-    def read():
-        return sum(c.nbytes for c in filler.contents() if isinstance(c, numpy.ndarray))
-    return filler.fill, read, "SpecFill.fill(host numpy columns) + contents()"
-
-
-def run_e2e(torch, dist, workload, spec, n, rank, world, device, args):
-    """Same metric through the user-facing call with host buffers: Hist.fill(x=<numpy>, ...) then read hist content."""
-    host = {}
-    h2d = 0
-    src = device_columns(torch, workload, n, 777 + rank, device)
-    for k, v in src.items():
-        pinned = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-        pinned.copy_(v)
-        host[k] = pinned.numpy()
-        h2d += pinned.numel() * pinned.element_size()
-    del src
-    torch.cuda.empty_cache()
-    fill, read, api = api_target(workload, spec)
+def run_e2e(torch, dist, workload, n, rank, world, device, args):
+    """Same metric through the user-facing call with host buffers: Book.fill(x=<numpy>, ...) then read every histogram.
+    Headline: plain (pageable) numpy arrays; page-locked arrays beside it."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    bpe = bench_cpu.WORKLOADS[workload][2]
+    n = int(max(1, min(n, 0.35 * avail / world / bpe)))
+    out = {}
     steps = max(1, min(args.steps, 3))
-    d2h = 0
-    for it in range(1 + steps):
-        if it == 1:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-        fill(host)
-        d2h = read()                                # device -> host read of the step's result
-    torch.cuda.synchronize()
-    sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
-    return {"value": world * n * steps / sec, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "events_per_gpu_per_step": n, "api": api,
-            "h2d_gbs_per_gpu": h2d * steps / sec / 1e9, "bound": "PCIe host->device copy of the columns"}
+    for kind in ("pageable", "pinned"):
+        m = n if kind == "pageable" else max(1, min(n, (8 << 30) // bpe))        # pinning tens of GB takes longer than the measurement
+        host, h2d = host_columns(torch, workload, m, 777 + rank, device, kind == "pinned")
+        torch.cuda.empty_cache()
+        target = Target(workload)
+        d2h = 0
+        for it in range(1 + steps):
+            if it == 1:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+            target.fill(host)
+            d2h = target.read()                         # device -> host read of the step's result
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        out[kind] = {"value": world * m * steps / sec, "events_per_gpu_per_step": m, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "h2d_gbs_per_gpu": h2d * steps / sec / 1e9}
+        api = target.api
+        del host, target
+    main = out["pageable"]
+    return {"value": main["value"], "unit": "events/s", "h2d_bytes_per_step": main["h2d_bytes_per_step"], "d2h_bytes_per_step": main["d2h_bytes_per_step"],
+            "steps": steps, "events_per_gpu_per_step": main["events_per_gpu_per_step"], "api": api + " on plain numpy arrays in pageable host memory, then ._content of every histogram",
+            "h2d_gbs_per_gpu": main["h2d_gbs_per_gpu"], "host_memory": "pageable (numpy.empty)", "bound": "host->device copy of the columns",
+            "pinned": dict(out["pinned"], host_memory="page-locked (torch pin_memory)")}
 
 
 def run_extra(torch, dist, workload, device, hbm):
-    from histbook_b200 import fillable
+    from histbook_b200 import engine, fillable
     case_name, default_n, bytes_per_event, _ = bench_cpu.WORKLOADS[workload]
     n = default_n
-    if workload == "c4":
-        n = 10**8
-    spec = bench_cpu.load_case(case_name)["spec"]
     cols = device_columns(torch, workload, n, 12345, device)
-    filler = fillable.SpecFill(spec)
-    filler.fill(dict((k, v[:4096]) for k, v in cols.items()))
-    filler.clear()
-    steps = 3 if n >= 10**9 or workload == "c4" else 10
+    target = Target(workload)
+    target.fill(dict((k, v[:4096]) for k, v in cols.items()))
+    target.clear()
+    steps = 3 if n >= 10**9 else 10
     if n * bytes_per_event <= 256e6:
         # small input: flush L2 between steps, time each step separately
-        from histbook_b200 import engine
         times = []
         for it in range(3 + steps):
             engine.flush_l2()
-            filler.fill(cols, timed=True)          # CUDA events recorded around the launch inside hb_fill (stream 0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            target.fill(cols)
+            e1.record()
+            torch.cuda.synchronize()
             if it >= 3:
-                times.append(fillable.last_stats["ms_kernel"])
+                times.append(e0.elapsed_time(e1))
         ms_step = sum(times) / len(times)
-        l2 = "L2 flushed between steps; kernel time from CUDA events around the launch (host launch overhead excluded)"
+        l2 = "L2 flushed between steps; CUDA events around each Hist.fill call"
     else:
-        ms, _ = measure(torch, dist, filler, cols, steps, 3, 1, lambda: None)
+        ms, _ = measure(torch, dist, target, cols, steps, 3, 1, None)
         ms_step = ms / steps
         l2 = "inputs larger than L2"
     gbs = n * bytes_per_event / (ms_step * 1e-3) / 1e9
+    stats = dict(fillable.last_stats)
     del cols
     torch.cuda.empty_cache()
-    return {"events": n, "ms_per_step": ms_step, "events_per_s": n / (ms_step * 1e-3), "achieved_gbs": gbs, "frac": gbs / hbm,
-            "l2": l2, "kernel": dict((k, fillable.last_stats.get(k)) for k in ("regs", "smem_bytes", "grid", "blocks_per_sm"))}
+    traffic, traffic_src = ncu_traffic(workload, n)
+    return {"workload": "%s: %s" % (workload, bench_cpu.DESCRIPTION[workload]), "events": n, "ms_per_step": ms_step, "events_per_s": n / (ms_step * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": n * bytes_per_event},
+            "l2": l2, "kernel": dict((k, stats.get(k)) for k in ("regs", "smem_bytes", "grid", "blocks_per_sm", "window", "window_coverage"))}
 
 
 def main():
@@ -420,12 +508,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(bench_cpu.WORKLOADS))
-    ap.add_argument("--events", default=None, help="events per GPU per step (default: the workload's BASELINE size)")
+    ap.add_argument("--workload", default="c4", choices=sorted(bench_cpu.WORKLOADS))
+    ap.add_argument("--events", default=None, help="events per step over ALL GPUs (strong) / per GPU (weak); default: the workload's BASELINE size")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE.md section 4): the same total events sharded over the GPUs; weak: every GPU fills the whole size")
     ap.add_argument("--e2e-events", default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE configs (N=1 only)")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the second run in the other scaling mode")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the other BASELINE configs (other_workloads)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

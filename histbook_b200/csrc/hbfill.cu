@@ -641,7 +641,9 @@ extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols,
         p.n = m;
         p.flags = flags;
         const int buf = chunk_index & 1;
-        if (any_host && chunk_index >= 2)        // staging buffer reuse: wait until the kernel two chunks back is done
+        // staging buffer reuse: the copy waits until the last kernel that read this buffer is done -- the one two
+        // chunks back, or the tail of the PREVIOUS hb_fill call (waiting on a never-recorded event is a no-op)
+        if (any_host)
             CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, g_stage.consumed[buf], 0));
         bool aligned = true;
         for (int c = 0; c < ncols; ++c) {

@@ -469,6 +469,7 @@ class SpecHist(object):
 
     def __init__(self, hspec):
         self._shape = tuple(hspec["shape"])
+        self.ngroup = len(hspec["group"])
         self._copyonfill = False
 
     @property

@@ -88,3 +88,87 @@ def test_two_ranks_fill_then_add(case_name, tmp_path):
                 if case["spec"]["hists"][hid]["weight"] is None:
                     sumw = case["spec"]["hists"][hid]["sumw"]
                     assert numpy.array_equal(got[k][..., sumw], fw[k][..., sumw])
+
+
+# ------------------------------------------------------------------------------------------------
+# dist.Merger: the one-collective merge of a whole book (host-resident contents, gloo)
+
+def _host_filler(spec, contents, arrays):
+    """A fillable.SpecFill whose stores hold ``contents`` on the host, with the group-axis descriptions a device fill
+    would have recorded (codegen only, no GPU)."""
+    from histbook_b200 import codegen, fillable, spec as hbspec
+    from histbook_b200.store import GroupInfo, Store
+    sf = fillable.SpecFill(spec)
+    coltypes = dict((n, (numpy.asarray(arrays[n]).dtype, numpy.ndim(arrays[n]) == 0)) for n in sf.fields)
+    keys = codegen.generate_keys(spec, coltypes)
+    infos = dict(keys.group_goals) if keys is not None else {}
+    for h, hspec, c in zip(sf.hists, spec["hists"], contents):
+        groups = []
+        for a in hspec["group"]:
+            gk = hbspec.tree_key(a["goal"])
+            info = infos[gk]
+            groups.append(GroupInfo(a["kind"], a["keeporder"], info["kind"] == "f", info["dtype"], info["nanflow"], gk, None))
+        h.__dict__["_hb"] = Store(hspec["shape"], groups, c)
+    return sf
+
+
+def _merger_worker(rank, world, port, case_name, out_dir, lazy_rank):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import golden_util
+    from histbook_b200 import dist as hbdist, fillable
+    from oracle import fill_oracle
+    case = golden_util.load()[case_name]
+    arrays = golden_util.fills(case)[0]
+    if lazy_rank == rank:
+        sf = fillable.SpecFill(case["spec"])              # this rank never calls fill: no store at all
+    else:
+        if lazy_rank is None:
+            mine = hbdist.shard_columns(arrays, rank, world)
+        else:
+            mine = arrays                                 # the other rank fills everything
+        sf = _host_filler(case["spec"], fill_oracle.fill(case["spec"], mine), mine)
+    merger = hbdist.Merger(sf).start()
+    merged = merger.contents()
+    flat = [[(k, a) for k, a in golden_util.flatten(c)] for c in merged]
+    numpy.save(os.path.join(out_dir, "rank%d.npy" % rank), numpy.array([flat, merger.collectives], dtype=object), allow_pickle=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_name,lazy_rank", [("c2", None), ("groupbin_nan_refill", None), ("groupby_groupbin_num", None), ("c4", None),
+                                                 ("c4", 1), ("book_fill", None)])
+def test_merger_is_one_collective_and_equals_one_fill(case_name, lazy_rank, tmp_path):
+    """Two ranks, contents on the host, gloo: the whole book merges with ONE all_reduce (plus one key all-gather when it
+    has group axes), the result equals one fill of everything, and a rank that never filled (``lazy_rank``) joins the
+    same collectives instead of hanging the others."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import golden_util
+    from oracle import fill_oracle
+    port = _free_port()
+    mp.spawn(_merger_worker, args=(2, port, case_name, str(tmp_path), lazy_rank), nprocs=2, join=True)
+    case = golden_util.load()[case_name]
+    arrays = golden_util.fills(case)[0]
+    whole = fill_oracle.fill(case["spec"], arrays)
+    bound = fill_oracle.fill(case["spec"], arrays, absolute=True)
+    has_groups = any(h["group"] for h in case["spec"]["hists"])
+    for r in range(2):
+        flat, collectives = numpy.load(os.path.join(str(tmp_path), "rank%d.npy" % r), allow_pickle=True)
+        assert collectives == (2 if has_groups else 1)
+        if r == lazy_rank:
+            continue                                      # cannot name the keys (it never saw a column), but did not hang
+        for hid, (w, b) in enumerate(zip(whole, bound)):
+            fw, fb = dict(golden_util.flatten(w)), dict(golden_util.flatten(b))
+            got = dict((tuple(k), a) for k, a in flat[hid])
+            for k in fw:
+                if k not in got:
+                    assert not fw[k].any()
+                    continue
+                assert numpy.all(numpy.abs(got[k] - fw[k]) <= 1e-12 * fb[k] + 0.0)
+                if case["spec"]["hists"][hid]["weight"] is None:
+                    sumw = case["spec"]["hists"][hid]["sumw"]
+                    assert numpy.array_equal(got[k][..., sumw], fw[k][..., sumw])
