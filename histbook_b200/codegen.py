@@ -152,6 +152,7 @@ class Program(object):
         self.inexact = set()    # library functions used that are not bit-identical to numpy
         self.zeroed = {}        # (weight, weight^2) SSA names -> their NaN-zeroed forms (hist.py:422-427), shared by a book's histograms
         self.nonneg = set()     # SSA names known to be >= +0 or NaN (squares, absolute values): the fixed-point add skips the sign path
+        self.square_of = {}     # SSA name of a float64 product x * x -> SSA name of x (the sorted strategy stages x only)
 
     # ------------------------------------------------------------------ helpers
     def new(self, prefix="t"):
@@ -227,6 +228,9 @@ class Program(object):
             if (fcn == "numpy.multiply" and out.kind == "f" and not args[0].isconst and not args[1].isconst
                     and (args[0].c == args[1].c or (args[0].c in self.nonneg and args[1].c in self.nonneg))):
                 self.nonneg.add(res.c)               # x * x (and products of such)
+            if (fcn == "numpy.multiply" and out == numpy.float64 and not args[0].isconst and not args[1].isconst
+                    and args[0].c == args[1].c and args[0].dtype == numpy.float64):
+                self.square_of[res.c] = args[0].c
             return res
 
         if fcn == "numpy.true_divide":
@@ -508,14 +512,18 @@ class HistPlan(object):
         self.skip_zero = False     # filter-derived weight: rows whose every term is exactly 0.0 are not accumulated
         self.fx_set = set()        # float64 terms kept as exact 128-bit fixed point (hb_template.cuh HbFx) instead of float64
         self.fx_index = {}         # term index -> index of its scale in p.win[2 + ...]
+        self.term_src = []         # per term: SSA name when the term is that float64 value itself, else None
+        self.sgroup = None         # "sorted" strategy: the SortGroup this histogram belongs to
+        self.sslot = {}            # ... term index -> index into the group's value list
 
-    def add_term(self, expr, col, nonneg=False):
+    def add_term(self, expr, col, nonneg=False, src=None):
         for t, e in enumerate(self.terms):
             if e == expr:
                 self.dest[t].append(col)
                 return
         self.terms.append(expr)
         self.term_nonneg.append(bool(nonneg))
+        self.term_src.append(src)
         self.dest.append([col])
 
     @property
@@ -604,6 +612,8 @@ def plan_hist(prog, hid, h):
             w2z = prog.emit(w2v.dtype, "(%s ? %s : %s)" % (sel.c, lit(0.0, w2v.dtype), w2v.c))
             if w2v.c in prog.nonneg:
                 prog.nonneg.add(w2z.c)
+            if prog.square_of.get(w2v.c) == wv.c and wv.dtype == numpy.float64:
+                prog.square_of[w2z.c] = wz.c         # (nan ? 0 : w * w) == (nan ? 0 : w) * (nan ? 0 : w), bit for bit
             prog.zeroed[(wv.c, w2v.c)] = (wz, w2z)
         else:
             wz, w2z = wv, w2v
@@ -617,14 +627,16 @@ def plan_hist(prog, hid, h):
             if val.isconst:
                 raise UnsupportedError("constant profile expression")
             nonneg = False
+            src = None
             if w is None:
                 expr = "((double)%s)" % val.c               # sumx * 1
                 nonneg = val.c in prog.nonneg
+                src = val.c if val.dtype == numpy.float64 else None
             elif "const" in w:
                 expr = _mulexpr(prog, val, Value(lit(float(w["const"]), numpy.float64), numpy.float64))
             else:
                 expr = _mulexpr(prog, val, wz)
-            hp.add_term(expr, col, nonneg)
+            hp.add_term(expr, col, nonneg, src)
 
     if w is None:
         hp.add_term(None, h["sumw"])
@@ -632,9 +644,140 @@ def plan_hist(prog, hid, h):
         hp.add_term(lit(float(w["const"]), numpy.float64), h["sumw"])
         hp.add_term(lit(float(w["const2"]), numpy.float64), h["sumw2"])
     else:
-        hp.add_term("((double)%s)" % wz.c, h["sumw"])
-        hp.add_term("((double)%s)" % w2z.c, h["sumw2"], w2z.c in prog.nonneg)
+        hp.add_term("((double)%s)" % wz.c, h["sumw"], False, wz.c if wz.dtype == numpy.float64 else None)
+        hp.add_term("((double)%s)" % w2z.c, h["sumw2"], w2z.c in prog.nonneg, w2z.c if w2z.dtype == numpy.float64 else None)
     return hp
+
+
+def hist_index(hp):
+    """(C expression of the row-major linear bin index over the fixed axes, hist.py:402-403; the axes' `ok` flags)."""
+    conds = []
+    if hp.index:
+        idx = hp.index[0][0].c
+        conds.append(hp.index[0][0].extra)
+        for v, totbins in hp.index[1:]:
+            idx = "(%s) * %d + %s" % (idx, totbins, v.c)
+            conds.append(v.extra)
+    else:
+        idx = "0"
+    return idx, conds
+
+
+# ================================================================================================
+# the "sorted" strategy of big books
+# ================================================================================================
+
+SORT_THREADS = 1024        # one block per SM
+SORT_EPT = 2               # events per thread and tile
+SORT_MAX_BINS = 8192
+SORT_MAX_GROUPS = 12       # (key, rank) tickets of a tile live in registers: SORT_EPT x groups of them per thread
+SMEM_MAX = 227 * 1024
+
+
+class SortGroup(object):
+    """Histograms of a book that share one linear bin index (and row mask): their float64 terms are not added event
+    by event with atomics; per tile the events are counting-sorted by that index (ONE native shared-memory atomic per
+    event: the ticket), and every lane of the group's warps then sums a contiguous chunk of the sorted events with
+    plain loads and adds, flushing a bin's partial sum with a plain read-modify-write when the bin's run ends (it ends
+    in exactly one lane).  Replaces 152 ``numpy.add.at`` calls per fill of c4 (hist.py:439-456)."""
+
+    def __init__(self, gid, idx, conds, nbins):
+        self.gid = gid
+        self.idx = idx
+        self.conds = conds
+        self.nbins = nbins
+        self.members = []
+        self.values = []          # distinct float64 term expressions (C, evaluated inside the event function)
+        self.srcs = []            # per value: SSA name or None
+        self.dests = []           # per value: [(hist id, column, ncol)]
+        self.count_dests = []     # [(hist id, column, ncol)] fed by the number of events per bin
+        self.stage = []           # per value: ("E", k) staged slot | ("sq", k) square of staged slot k
+        self.off = {}             # shared-memory byte offsets: acc, cnt, tick, sorted, tkey, tval
+
+    def add(self, hp):
+        self.members.append(hp)
+        hp.sgroup = self
+        for t, e in enumerate(hp.terms):
+            if e is None:
+                self.count_dests.extend((hp.hid, col, hp.ncol) for col in hp.dest[t])
+                continue
+            if e not in self.values:
+                self.values.append(e)
+                self.srcs.append(hp.term_src[t])
+                self.dests.append([])
+            j = self.values.index(e)
+            hp.sslot[t] = j
+            self.dests[j].extend((hp.hid, col, hp.ncol) for col in hp.dest[t])
+
+    def smem_bytes(self, tile, lanes):
+        nv = len(self.values)
+        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + lanes * (8 + 8 * nv) + 64) // 16 * 16 + 16
+
+
+def sort_groups(plans, options):
+    """Candidate sort groups: histograms without group axes and with at least one float64 term, keyed by (linear
+    index expression, row mask); unweighted histograms with the same key join (their counts are the tickets)."""
+    mode = options.get("sort", "auto")
+    if not mode or options.get("deterministic", False):
+        return []
+    if mode == "auto" and _unroll(plans, options) != 0:
+        return []                                          # small books: the per-event strategies are faster (c2, c3)
+    forced = options.get("strategy", {})
+    by_key = {}
+    order = []
+    for hp in plans:
+        if hp.groups or forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) not in (None, "sorted"):
+            continue
+        if not (0 < hp.nbins <= SORT_MAX_BINS) or not hp.f64_terms:
+            continue
+        key = hist_index(hp)
+        key = (key[0], tuple(key[1]))
+        if key not in by_key:
+            by_key[key] = SortGroup(len(order), key[0], list(key[1]), hp.nbins)
+            order.append(by_key[key])
+        by_key[key].add(hp)
+    for hp in plans:                                       # count-only histograms ride along
+        if hp.groups or hp.f64_terms or hp.sgroup is not None or not (0 < hp.nbins <= SORT_MAX_BINS):
+            continue
+        if forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) not in (None, "sorted"):
+            continue
+        key = hist_index(hp)
+        key = (key[0], tuple(key[1]))
+        if key in by_key:
+            by_key[key].add(hp)
+    return order
+
+
+def stage_values(prog, groups):
+    """Which float64 values of the event function are staged in shared memory per tile (E[k][event]): every distinct
+    term of the groups, except squares x * x of a value that is staged itself (recomputed by the summing lane)."""
+    all_srcs = set(src for g in groups for src in g.srcs if src is not None)
+    memo = {}
+
+    def derived(src):
+        """src is x * x of a value x that is staged itself (not derived in turn: x**4 of c3 stages x**2)"""
+        if src not in memo:
+            base = prog.square_of.get(src)
+            memo[src] = base is not None and base in all_srcs and not derived(base)
+        return memo[src]
+    staged = []                 # C expressions, slot order
+    names = {}                  # SSA name -> slot
+    for g in groups:
+        for e, src in zip(g.values, g.srcs):
+            if src is not None and derived(src):
+                continue
+            if e not in staged:
+                staged.append(e)
+                if src is not None:
+                    names[src] = len(staged) - 1
+    for g in groups:
+        g.stage = []
+        for e, src in zip(g.values, g.srcs):
+            if e in staged:
+                g.stage.append(("E", staged.index(e)))
+            else:
+                g.stage.append(("sq", names[prog.square_of[src]]))
+    return staged
 
 
 def _unroll(plans, options):
@@ -644,10 +787,36 @@ def _unroll(plans, options):
     return int(options.get("unroll", 0 if len(plans) > 16 else 4))
 
 
-def choose_strategies(plans, options):
-    """Shared-memory privatisation for the histograms that fit, global REDs for the rest."""
+def choose_strategies(plans, options, prog=None, layout=None):
+    """Shared-memory privatisation for the histograms that fit, global REDs for the rest.  Returns (bytes of shared
+    memory, hot-window histogram or None); with ``prog`` given, big books may get sort groups, described in ``layout``."""
     det = bool(options.get("deterministic", False))
     forced = options.get("strategy", {})
+    # big books: histograms that share a bin index are summed per tile from events sorted by that index (SortGroup)
+    sgroups, staged, sort_bytes = [], [], 0
+    sort_cap = int(options.get("sort_smem", SMEM_MAX - 1024))
+    sort_tile = int(options.get("sort_threads", SORT_THREADS)) * int(options.get("sort_ept", SORT_EPT))
+    sort_lanes = int(options.get("sort_lanes", 64))
+    if prog is not None:
+        sgroups = sort_groups(plans, options)
+        sgroups.sort(key=lambda g: -len(g.values) * len(g.members))
+        while sgroups:
+            sgroups = sgroups[:int(options.get("sort_max_groups", SORT_MAX_GROUPS))]
+            staged = stage_values(prog, sgroups)
+            sort_bytes = sum(g.smem_bytes(sort_tile, sort_lanes) for g in sgroups) + 8 * len(staged) * sort_tile + 64
+            if sort_bytes + 16 * 1024 <= sort_cap:
+                break
+            sgroups = sgroups[:-1]                         # does not fit: the last group goes back to the per-event strategies
+        kept = set(id(g) for g in sgroups)
+        for i, g in enumerate(sgroups):
+            g.gid = i
+        for hp in plans:
+            if hp.sgroup is not None and id(hp.sgroup) not in kept:
+                hp.sgroup, hp.sslot = None, {}
+            if hp.sgroup is not None:
+                hp.strategy = "sorted"
+        if not sgroups:
+            staged, sort_bytes = [], 0
     # Which float64 terms are accumulated as exact fixed point (16 bytes per bin, native u32 atomics, ~55 instructions,
     # no retries) rather than with float64 CAS loops (8 bytes, ~10 instructions, but several times the shared-memory
     # wavefronts, and one more attempt for every other lane of the warp that is in the same bin):
@@ -664,6 +833,8 @@ def choose_strategies(plans, options):
     # (statically privatised tables share 96 KB so that two blocks fit an SM; all-fixed-point kernels and big books run one
     #  1024-thread block per SM and may take 200 KB)
     budget = int(options.get("smem_budget", (200 if (mode is True or _unroll(plans, options) == 0) else 96) * 1024))
+    if sgroups:
+        budget = min(budget, sort_cap - sort_bytes)
     for hp in plans:
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
@@ -671,7 +842,9 @@ def choose_strategies(plans, options):
         hp.replicas = 1 if hp.groups else int(options.get("replicas", 1))
     for hp in plans:
         terms = list(hp.f64_terms)
-        if mode == "mix":
+        if hp.strategy == "sorted":
+            terms = []
+        elif mode == "mix":
             terms = terms[1::2]
         elif mode == "auto":
             terms = terms if hp.nrows <= 1024 else terms[1:]
@@ -691,6 +864,8 @@ def choose_strategies(plans, options):
     order = sorted(plans, key=lambda hp: hp.smem_bytes(options))
     used = 16 if any(hp.fx_set for hp in plans) else 0     # word 0: how many terms missed their fixed-point window (HB_FXMISS)
     for hp in order:
+        if hp.strategy == "sorted":
+            continue
         want = forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*")))
         need = hp.smem_bytes(options)
         if mode == "auto" and hp.fx_set and (want == "smem" or want is None) and used + need > budget:
@@ -712,7 +887,7 @@ def choose_strategies(plans, options):
     # For c2 the populated region of (x+y, r) is a V (|x+y| <= sqrt(2) r): at 6400 bins a rectangle covers
     # 80 % of the events, per-row intervals 94.5 % (tools/window_coverage.py).
     window = None
-    if options.get("window", True):
+    if options.get("window", True) and not sgroups:
         max_rows = int(options.get("win_max_rows", 4096))
         max_bytes = int(options.get("win_max_hist_bytes", 16 << 20))
         cands = []
@@ -758,6 +933,34 @@ def choose_strategies(plans, options):
         raise UnsupportedError("more than {0} fixed-point terms in one fill".format(MAX_WIN - 2))
     if not any(hp.strategy in ("smem", "window") for hp in plans) and not any(hp.fx for hp in plans):
         used = 0
+    if sgroups:
+        # layout behind the per-event tables: [acc | cnt | tick of every group] (zeroed at kernel start), then the
+        # per-tile scratch [sorted event numbers | tails of every group], then the staged values E[k][event]
+        used = (used + 15) // 16 * 16
+        for g in sgroups:
+            g.off["acc"] = used
+            used += (8 * len(g.values) * g.nbins + 15) // 16 * 16
+        for g in sgroups:
+            g.off["cnt"] = used
+            used += (4 * g.nbins + 15) // 16 * 16
+        for g in sgroups:
+            g.off["tick"] = used
+            used += (4 * (g.nbins + 1) + 15) // 16 * 16
+        zero_end = used
+        for g in sgroups:
+            g.off["sorted"] = used
+            used += (2 * sort_tile + 15) // 16 * 16
+            g.off["tkey"] = used
+            used += (4 * sort_lanes + 15) // 16 * 16
+            g.off["tval"] = used
+            used += 8 * sort_lanes * max(len(g.values), 1)
+        e_off = used
+        used += 8 * len(staged) * sort_tile
+        sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "e_off": e_off, "tile": sort_tile,
+                       "lanes": sort_lanes, "threads": int(options.get("sort_threads", SORT_THREADS)),
+                       "ept": int(options.get("sort_ept", SORT_EPT))}
+        if layout is not None:
+            layout.update(sort_layout)
     return used, window
 
 
@@ -788,6 +991,7 @@ class Kernel(object):
         self.naux = 0
         self.deterministic = False
         self.exact = {}
+        self.sorted = None          # "sorted" strategy: {"tile", "lanes", "ept", "groups": [...], "staged"}
 
 
 def _colarg(slot, dtype, is_scalar, loaded):
@@ -1046,6 +1250,156 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
     return "\n".join(src) + "\n"
 
 
+def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
+    """Kernel of a big book with sort groups.  Per tile of HB_TILE events, one 1024-thread block per SM:
+      1. every thread evaluates HB_EPT events (one coalesced scalar load per column): histograms outside the groups are
+         updated as in the other kernels; the float64 values the groups accumulate are staged in shared memory
+         (E[k][event]); per group the event draws a ticket -- ONE native ATOMS.ADD on the group's per-tile bin counter,
+         whose return value is the event's rank inside its bin;
+      2. one warp per group turns the counters into bin start offsets (and adds them to the group's count table);
+      3. every thread writes its events' numbers to start[bin] + rank: the tile's events, sorted by bin, per group;
+      4. per group, HB_LANES lanes each walk a contiguous chunk of the sorted events, adding the staged values in
+         registers; when a bin's run ends inside the chunk the lane is the only one in which it ends and adds the
+         partial sums to the block's float64 table with plain loads and stores; a run that continues in the next
+         lane's chunk is left as a "tail" and added after a barrier by the first lane that holds a tail of that bin.
+    No float64 atomics and no fixed-point limbs: c4 went from ~100 shared atomics per event to 8 tickets + 32 counts."""
+    groups, staged = layout["groups"], layout["staged"]
+    threads, ept, tile, lanes = layout["threads"], layout["ept"], layout["tile"], layout["lanes"]
+    G = len(groups)
+    chunk = tile // lanes
+    assert chunk * lanes == tile and threads % lanes == 0
+    nwg = min(threads // lanes, 15)                        # warp-groups that take sort groups (named barriers 1..15)
+    src = []
+    src.append('#include "hb_template.cuh"')
+    src.append("#define HB_THREADS %d" % threads)
+    src.append("#define HB_EPT %d" % ept)
+    src.append("#define HB_TILE (HB_THREADS * HB_EPT)")
+    src.append("#define HB_LANES %d" % lanes)
+    src.append("#define HB_NSG %d" % G)
+    src.append("#define HB_FXMISS (reinterpret_cast<hb_u32*>(hb_smem))")
+    src.extend(prog.consts)
+    src.append("")
+    sig = ["const HbParams& p", "unsigned char* hb_smem", "const bool live", "const int eid", "hb_u32 (&kr)[HB_NSG]"]
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        sig.append("const %s c%d /* %s */" % (ctype(dtype), slot, name))
+    src.append("__device__ __forceinline__ void hb_event(%s)\n{" % ", ".join(sig))
+    src.extend("    " + line for line in event_lines)
+    src.append("    // ---- values the sort groups accumulate, staged for this tile")
+    for k, e in enumerate(staged):
+        src.append("    reinterpret_cast<double*>(hb_smem + %d)[eid] = %s;" % (layout["e_off"] + 8 * k * tile, e))
+    for g in groups:
+        src.append("    // ---- sort group %d: %d bins, %d values, histograms %s" % (g.gid, g.nbins, len(g.values), [hp.hid for hp in g.members]))
+        src.append("    {")
+        src.append("        hb_u32 t = 0xffffffffu;")
+        src.append("        if (%s) {" % " && ".join(["live"] + g.conds))
+        src.append("            const int bin = %s;" % g.idx)
+        src.append("            t = ((hb_u32)bin << 16) | atomicAdd(reinterpret_cast<hb_u32*>(hb_smem + %d) + bin, 1u);" % g.off["tick"])
+        src.append("        }")
+        src.append("        kr[%d] = t;" % g.gid)
+        src.append("    }")
+    src.append("}\n")
+
+    src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, 1) hb_fill_kernel(const HbParams p)\n{')
+    src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
+    src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (layout["zero_end"] // 4))
+    src.append("    __syncthreads();")
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        if is_scalar:
+            src.append("    const %s s%d = hb_scalar<%s>(p.scal[%d]);" % (_loadtype(dtype), slot, _loadtype(dtype), slot))
+    src.append("    const hb_i64 ntiles = (p.n + HB_TILE - 1) / HB_TILE;")
+    src.append("    const int hb_wg = threadIdx.x / HB_LANES, hb_l = threadIdx.x % HB_LANES;")
+    src.append("    for (hb_i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {")
+    src.append("        const hb_i64 first = tile * HB_TILE;")
+    for k in range(ept):
+        src.append("        hb_u32 kr%d[HB_NSG];" % k)
+    src.append("        // 1. evaluate, stage, draw tickets")
+    for k in range(ept):
+        src.append("        {")
+        src.append("            const hb_i64 i = first + %d * HB_THREADS + threadIdx.x;" % k)
+        src.append("            const bool live = i < p.n;")
+        src.append("            const hb_i64 j = live ? i : 0;")
+        src.append("            hb_event(p, hb_smem, live, %d * HB_THREADS + (int)threadIdx.x, kr%d%s);" % (k, k, "".join(
+            ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], j)" % (_loadtype(dtype), slot))
+            for slot, (name, dtype, is_scalar) in enumerate(prog.cols))))
+        src.append("        }")
+    src.append("        __syncthreads();")
+    src.append("        // 2. bin counters -> bin start offsets (one warp per group)")
+    for g in groups:
+        cnt = "reinterpret_cast<hb_u32*>(hb_smem + %d)" % g.off["cnt"] if g.count_dests else "nullptr"
+        src.append("        if ((threadIdx.x >> 5) == %d) hb_sort_scan(reinterpret_cast<hb_u32*>(hb_smem + %d), %d, %s);" % (
+            g.gid % (threads // 32), g.off["tick"], g.nbins, cnt))
+    src.append("        __syncthreads();")
+    src.append("        // 3. scatter the event numbers to start[bin] + rank")
+    for k in range(ept):
+        for g in groups:
+            src.append("        if (kr%d[%d] != 0xffffffffu) reinterpret_cast<unsigned short*>(hb_smem + %d)[reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu)] = (unsigned short)(%d * HB_THREADS + threadIdx.x);" % (
+                k, g.gid, g.off["sorted"], g.off["tick"], k, g.gid, k, g.gid, k))
+    src.append("        __syncthreads();")
+    src.append("        // 4. chunked sums over the sorted events")
+    for g in groups:
+        nv = len(g.values)
+        wg = g.gid % nwg
+        used_slots = sorted(set(k for kind, k in g.stage))
+        src.append("        if (hb_wg == %d) {   // sort group %d" % (wg, g.gid))
+        src.append("            const hb_u32* const st = reinterpret_cast<const hb_u32*>(hb_smem + %d);" % g.off["tick"])
+        src.append("            const unsigned short* const so = reinterpret_cast<const unsigned short*>(hb_smem + %d);" % g.off["sorted"])
+        src.append("            double* const acc = reinterpret_cast<double*>(hb_smem + %d);" % g.off["acc"])
+        src.append("            int* const tkeys = reinterpret_cast<int*>(hb_smem + %d);" % g.off["tkey"])
+        src.append("            double* const tvals = reinterpret_cast<double*>(hb_smem + %d);" % g.off["tval"])
+        src.append("            const hb_u32 ng = st[%d];" % g.nbins)
+        src.append("            const hb_u32 p0 = (hb_u32)hb_l * %du, p1 = min(p0 + %du, ng);" % (chunk, chunk))
+        src.append("            " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
+        src.append("            int tkey = -1;")
+        flush = " ".join("acc[%d + key] += a%d; a%d = 0.0;" % (j * g.nbins, j, j) for j in range(nv))
+        src.append("            if (p0 < ng) {")
+        src.append("                int key = hb_sort_find(st, %d, p0);" % g.nbins)
+        src.append("                hb_u32 runend = st[key + 1];")
+        src.append("                for (hb_u32 pos = p0; pos < p1; ++pos) {")
+        src.append("                    if (pos >= runend) {       // the run of `key` ends in this lane's chunk, and in no other lane's")
+        src.append("                        " + flush)
+        src.append("                        do { ++key; runend = st[key + 1]; } while (pos >= runend);")
+        src.append("                    }")
+        src.append("                    const unsigned e = so[pos];")
+        for k in used_slots:
+            src.append("                    const double v%d = reinterpret_cast<const double*>(hb_smem + %d)[e];" % (k, layout["e_off"] + 8 * k * tile))
+        for j, (kind, k) in enumerate(g.stage):
+            if kind == "E":
+                src.append("                    a%d += v%d;" % (j, k))
+            else:
+                src.append("                    a%d += hb_mul<double>(v%d, v%d);" % (j, k, k))
+        src.append("                }")
+        src.append("                if (runend > p1) tkey = key;       // the run goes on in the next lane: a tail")
+        src.append("                else { %s }" % flush)
+        src.append("            }")
+        src.append("            tkeys[hb_l] = tkey;")
+        src.append("            if (tkey >= 0) { %s }" % " ".join("tvals[%d + hb_l] = a%d;" % (j * lanes, j) for j in range(nv)))
+        src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))
+        src.append("            for (int b = hb_l; b <= %d; b += HB_LANES) reinterpret_cast<hb_u32*>(hb_smem + %d)[b] = 0u;" % (g.nbins, g.off["tick"]))
+        src.append("            if (tkey >= 0 && (hb_l == 0 || tkeys[hb_l - 1] != tkey)) {")
+        src.append("                const int key = tkey;")
+        src.append("                for (int m = hb_l + 1; m < HB_LANES && tkeys[m] == key; ++m) { %s }" % " ".join("a%d += tvals[%d + m];" % (j, j * lanes) for j in range(nv)))
+        src.append("                " + flush)
+        src.append("            }")
+        src.append("        }")
+    src.append("        __syncthreads();")
+    src.append("    }")
+    src.append("    __syncthreads();")
+    src.extend("    " + line for line in merge_lines)
+    for g in groups:
+        src.append("    // merge sort group %d" % g.gid)
+        src.append("    for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % g.nbins)
+        for j, dests in enumerate(g.dests):
+            src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b];" % (g.off["acc"] + 8 * j * g.nbins))
+            src.append("          if (v != 0.0) { %s } }" % " ".join("hb_red_f64(p.hist[%d] + (hb_i64)b * %d + %d, v);" % (hid, ncol, col) for hid, col, ncol in dests))
+        if g.count_dests:
+            src.append("        { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d)[b];" % g.off["cnt"])
+            src.append("          if (c != 0u) { const double v = (double)c; %s } }" % " ".join(
+                "hb_red_f64(p.hist[%d] + (hb_i64)b * %d + %d, v);" % (hid, ncol, col) for hid, col, ncol in g.count_dests))
+        src.append("    }")
+    src.append("}")
+    return "\n".join(src) + "\n"
+
+
 def _group_lookup(hp, aux_slot):
     """C lines that turn the group keys of one event into the slab slot of hist ``hp`` (or reject the row)."""
     K = len(hp.groups)
@@ -1208,7 +1562,8 @@ def generate(spec, coltypes, options=None):
     plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
     if len(plans) > 128:
         raise UnsupportedError("more than 128 histograms in one fill")
-    smem, window = choose_strategies(plans, options)
+    layout = {}
+    smem, window = choose_strategies(plans, options, prog, layout)
     if len(prog.cols) > 32:
         raise UnsupportedError("more than 32 input fields in one fill")
     # resident threads per SM stay near 1024 whatever the shared-memory footprint: the fixed-point adds are chains
@@ -1228,6 +1583,8 @@ def generate(spec, coltypes, options=None):
         dthreads, dblocks = 512, 1
     threads = int(options.get("threads", dthreads))
     minblocks = int(options.get("min_blocks", dblocks))
+    if layout:
+        threads, minblocks = layout["threads"], 1
     smem_cap = smem
     if window is not None:
         # one resident block of 1024 threads per SM that owns 226 of the SM's 227 KB of shared memory: with per-row
@@ -1246,15 +1603,9 @@ def generate(spec, coltypes, options=None):
     ev.extend(_emit_fx_decodes(plans))
     for hp in plans:
         ev.append("// ---- hist %d: shape %s, %s" % (hp.hid, hp.shape, hp.strategy))
-        conds = []
-        if hp.index:
-            idx = hp.index[0][0].c
-            conds.append(hp.index[0][0].extra)
-            for v, totbins in hp.index[1:]:
-                idx = "(%s) * %d + %s" % (idx, totbins, v.c)          # hist.py:402-403
-                conds.append(v.extra)
-        else:
-            idx = "0"
+        if hp.strategy == "sorted":
+            continue                                   # accumulated by its sort group (below)
+        idx, conds = hist_index(hp)
         ev.append("{")
         if hp.groups:
             if len(group_aux) >= 64:
@@ -1433,15 +1784,22 @@ def generate(spec, coltypes, options=None):
             if hp.fx:
                 k.exact[hp.hid] = [(hp.fx_index[t], sum(1 << c for c in hp.dest[t])) for t in hp.f64_terms]
     unroll = _unroll(plans, options)
-    k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll,
-                            times_aux=k.times_aux, dynamic=False if options.get("prefetch", False) else options.get("dynamic", False),
-                            evict_first=bool(options.get("evict_first", True)), red_evict_last=bool(options.get("red_evict_last", False)))
+    if layout:
+        k.source = _emit_kernel_sorted(prog, ev, merge, layout, options)
+    else:
+        k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll,
+                                times_aux=k.times_aux, dynamic=False if options.get("prefetch", False) else options.get("dynamic", False),
+                                evict_first=bool(options.get("evict_first", True)), red_evict_last=bool(options.get("red_evict_last", False)))
     k.cols = list(prog.cols)
     k.plans = plans
     k.smem_bytes = smem_cap
     k.window = winfo
     k.threads = threads
-    k.tile = threads * VEC
+    k.tile = layout["tile"] if layout else threads * VEC
+    k.sorted = dict((key, layout[key]) for key in ("tile", "lanes", "ept")) if layout else None
+    if layout:
+        k.sorted["groups"] = [{"nbins": g.nbins, "values": len(g.values), "hists": [hp.hid for hp in g.members]} for g in layout["groups"]]
+        k.sorted["staged"] = len(layout["staged"])
     k.inexact = set(prog.inexact)
     k.group_aux = group_aux
     k.key = hashlib.sha256(k.source.encode()).hexdigest()
@@ -1467,7 +1825,7 @@ def generate_range(spec, coltypes, options=None):
     options = options or {}
     prog = Program(spec, coltypes)
     plans = [plan_hist(prog, hid, h) for hid, h in enumerate(spec["hists"])]
-    choose_strategies(plans, options)
+    choose_strategies(plans, options, prog, {})
     terms = [(hp, t) for hp in plans for t in hp.f64_terms if t in hp.fx_set]
     if not terms:
         return None

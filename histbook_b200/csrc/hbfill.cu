@@ -181,6 +181,7 @@ struct hb_program {
     CUmodule module = nullptr;
     CUfunction fn = nullptr;
     int threads = 256;
+    int tile = 1024;            // events per block and round of the kernel's grid-stride loop (HB_TILE of the generated source)
     int smem = 0;
     int blocks_per_sm = 1;
     int regs = 0;
@@ -294,6 +295,7 @@ extern "C" int hb_program_load(const void* cubin, size_t cubin_size, const char*
         return fail(HB_ERR_ARG, "kernel needs more dynamic shared memory than the device allows");
     hb_program* p = new hb_program();
     p->threads = threads;
+    p->tile = threads * 4;
     p->smem = smem_bytes;
     CUresult r = g_drv.ModuleLoadData(&p->module, cubin);
     if (r != CUDA_SUCCESS) { delete p; return fail(HB_ERR_CUDA, "cuModuleLoadData: " + drv_err(r)); }
@@ -317,6 +319,12 @@ extern "C" int hb_program_destroy(hb_program* p) {
     if (!p) return HB_OK;
     if (p->module && g_drv.ModuleUnload) g_drv.ModuleUnload(p->module);
     delete p;
+    return HB_OK;
+}
+
+extern "C" int hb_program_set_tile(hb_program* p, int tile_events) {
+    if (!p || tile_events < 1) return fail(HB_ERR_ARG, "bad tile size");
+    p->tile = tile_events;
     return HB_OK;
 }
 
@@ -610,7 +618,7 @@ extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols,
     rc = sched_for(g_stream, &base.sched);
     if (rc) return rc;
 
-    const int tile = prog->threads * 4;
+    const int tile = prog->tile;
     const int resident = g_sm_count * prog->blocks_per_sm;
     int64_t per_launch = any_host ? g_chunk_events : ((int64_t)1 << 30);
     per_launch = per_launch / tile * tile;

@@ -53,6 +53,7 @@ SYMBOLS = {
     "hb_program_compile": (_I, [ctypes.c_char_p, ctypes.c_char_p, _I, _PP, ctypes.POINTER(ctypes.c_size_t)]),
     "hb_program_load": (_I, [_P, ctypes.c_size_t, ctypes.c_char_p, _I, _I, _PP]),
     "hb_program_destroy": (_I, [_P]),
+    "hb_program_set_tile": (_I, [_P, _I]),
     "hb_program_info": (_I, [_P, _IP, _IP, _IP]),
     "hb_free": (None, [_P]),
     "hb_arena_create": (_I, [_I64, _PP]),
@@ -199,11 +200,13 @@ def compile_source(source, lineinfo=True):
 class Program(object):
     """A loaded fill kernel."""
 
-    def __init__(self, cubin, kernel_name, threads, smem_bytes):
+    def __init__(self, cubin, kernel_name, threads, smem_bytes, tile=None):
         init()
         self._h = ctypes.c_void_p()
         self._cubin = cubin
         check(lib().hb_program_load(cubin, len(cubin), kernel_name.encode(), int(threads), int(smem_bytes), ctypes.byref(self._h)))
+        if tile is not None and int(tile) != 4 * int(threads):
+            check(lib().hb_program_set_tile(self._h, int(tile)))
         regs, ssm, occ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         check(lib().hb_program_info(self._h, ctypes.byref(regs), ctypes.byref(ssm), ctypes.byref(occ)))
         self.regs, self.static_smem, self.blocks_per_sm = regs.value, ssm.value, occ.value

@@ -28,7 +28,8 @@ def set_options(**kwargs):
     Accumulation: ``fx`` (False | True | "mix" | [slots] | "auto"), ``fx_auto_max_terms``, ``strategy`` ({hist id | "*":
     "smem" | "global" | "window"}), ``smem_budget``, ``window`` / ``win_dense`` / ``win_pair`` / ``win_smem`` /
     ``win_threads`` / ``win_min_blocks`` / ``win_table32`` / ``win_max_rows`` / ``win_max_hist_bytes``, ``merge_pair``,
-    ``pair_red``, ``group_slots``, ``replicas``, ``f64_atomic`` ("cas" | "exch").
+    ``pair_red``, ``group_slots``, ``replicas``, ``f64_atomic`` ("cas" | "exch"), ``sort`` ("auto" | True | False: the sorted
+    strategy of big books, codegen.SortGroup) with ``sort_lanes`` / ``sort_ept`` / ``sort_threads`` / ``sort_max_groups`` / ``sort_smem``.
     Launch shape and loop: ``threads``, ``min_blocks``, ``unroll`` (4 | 1 | 0), ``prefetch``, ``dynamic`` (False | "tail" |
     True), ``evict_first``, ``red_evict_last``.  Measurement: ``block_times``.
     Defaults are the measured best (profiles/r01_sweeps.txt); tests/test_gpu_parity.py checks that none of them changes a
@@ -75,7 +76,7 @@ class Plan(object):
             coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in self.fields)
             options = dict(_options, win_dense=True) if dense else _options
             kern = codegen.generate(self.spec, coltypes, options)
-            prog = engine.Program(engine.compile_source(kern.source), kern.name, kern.threads, kern.smem_bytes)
+            prog = engine.Program(engine.compile_source(kern.source), kern.name, kern.threads, kern.smem_bytes, tile=kern.tile)
             keys = codegen.generate_keys(self.spec, coltypes, options)
             kprog = None
             if keys is not None:
@@ -396,6 +397,7 @@ def fill_hists(plan, hists, arrays, timed=False):
         if kern.fx_terms and _options.get("fx_stats", False):
             stats["fx_missed_total"] = int(plan.fx_stat.read(numpy.uint64)[0])
         stats["deterministic"] = kern.deterministic
+        stats["sorted"] = kern.sorted
         stats["regs"] = prog.regs
         stats["smem_bytes"] = kern.smem_bytes
         stats["keys_launches"] = 1 if (keys is not None and length > 0) else 0

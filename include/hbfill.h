@@ -96,6 +96,9 @@ int hb_program_compile(const char* source, const char* header, int lineinfo,
 int hb_program_load(const void* cubin, size_t cubin_size, const char* kernel_name,
                     int threads, int smem_bytes, hb_program** out);
 int hb_program_destroy(hb_program* prog);
+/* events one block handles per round of the kernel's grid-stride loop (default 4 x threads; the sorted-book kernels
+ * of codegen.py use HB_EPT x threads): hb_fill sizes the grid with it */
+int hb_program_set_tile(hb_program* prog, int tile_events);
 int hb_program_info(const hb_program* prog, int* regs, int* static_smem, int* blocks_per_sm);
 void hb_free(void* p);
 

@@ -201,7 +201,8 @@ OPTION_SETS = [
     {"fx": False}, {"fx": True}, {"fx": "mix"}, {"window": False}, {"win_dense": True}, {"win_pair": False}, {"merge_pair": False},
     {"win_table32": False}, {"pair_red": False}, {"prefetch": True}, {"replicas": 2}, {"f64_atomic": "exch"}, {"unroll": 1},
     {"unroll": 0}, {"evict_first": False}, {"red_evict_last": True}, {"group_slots": 2}, {"threads": 256, "min_blocks": 4},
-    {"smem_budget": 16384}, {"block_times": True},
+    {"smem_budget": 16384}, {"block_times": True}, {"sort": True}, {"sort": True, "sort_lanes": 128}, {"sort": True, "sort_lanes": 32},
+    {"sort": True, "sort_ept": 1}, {"sort": False},
 ]
 
 
@@ -232,3 +233,68 @@ def test_tuning_options_do_not_change_the_histogram(options):
             compare("%s %r" % (name, options), spec, got, [golden_util.flatten(e) for e in exp], bound)
     finally:
         fillable.set_options(**dict((k, None) for k in options))
+
+
+def _sortable(name):
+    from histbook_b200 import codegen, spec as hbspec
+    case = golden_util.load()[name]
+    fills = golden_util.fills(case)
+    try:
+        coltypes = dict((f, (numpy.asarray(fills[0][f]).dtype, numpy.ndim(fills[0][f]) == 0)) for f in hbspec.spec_fields(case["spec"]) if f in fills[0])
+        return codegen.generate(case["spec"], coltypes, {"sort": True}).sorted is not None
+    except Exception:
+        return False
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n not in LIBM_CASES])
+def test_golden_sorted_strategy(name):
+    """Every golden case that has float64 terms on fixed axes, with the sorted strategy of big books forced on
+    (per-tile counting sort by bin index + chunked sums instead of per-event atomics): same bars as everywhere."""
+    from histbook_b200 import fillable
+    if not _sortable(name):
+        pytest.skip("no float64 term on a fixed-axis histogram: nothing to sort")
+    case = golden_util.load()[name]
+    fills = golden_util.fills(case)
+    try:
+        fillable.set_options(sort=True)
+        got = run_spec(case["spec"], fills)
+        assert fillable.last_stats.get("sorted"), name
+    finally:
+        fillable.set_options(sort=None)
+    bound = None
+    for arrays in fills:
+        bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
+    compare(name, case["spec"], got, golden_util.outputs(case), bound)
+
+
+@pytest.mark.parametrize("lanes", [32, 64, 128])
+def test_sorted_strategy_on_degenerate_distributions(lanes):
+    """Runs that span many lanes (every event in ONE bin; two bins; a run ending exactly on a chunk boundary), masked
+    rows, NaN weights, tiles with a single live event: the tails and the run-end ownership of codegen.SortGroup."""
+    from histbook_b200 import fillable
+    cases = golden_util.load()
+    spec = dict(cases["c4"]["spec"], hists=cases["c4"]["spec"]["hists"][:8])
+    rs = numpy.random.RandomState(3)
+    try:
+        fillable.set_options(sort=True, sort_lanes=lanes)
+        for n in (1, 31, 2048, 2049, 4096 + 64, 303104 + 17, 700001):
+            variants = []
+            const = {"x": numpy.full(n, 0.25), "y": numpy.full(n, -0.75), "z": numpy.full(n, 1.5), "w": numpy.full(n, 1.25), "n": numpy.full(n, 4, dtype=numpy.int64)}
+            variants.append(const)
+            two = dict(const, x=numpy.where(numpy.arange(n) % 64 < 32, 0.25, 3.05))            # chunk-aligned alternation
+            variants.append(two)
+            nanw = dict(const, w=numpy.where(numpy.arange(n) % 3 == 0, numpy.nan, 0.5), x=rs.normal(0, 3, n))
+            nanw["x"][::7] = numpy.nan
+            variants.append(nanw)
+            for arrays in variants:
+                sf = fillable.SpecFill(spec)
+                sf.fill(arrays)
+                sf.fill(dict((k, v[: n // 2]) for k, v in arrays.items()))
+                got = sf.contents()
+                exp = bound = None
+                for a in (arrays, dict((k, v[: n // 2]) for k, v in arrays.items())):
+                    exp = fill_oracle.fill(spec, a, exp)
+                    bound = fill_oracle.fill(spec, a, bound, absolute=True)
+                compare("degenerate n=%d" % n, spec, got, [golden_util.flatten(e) for e in exp], bound)
+    finally:
+        fillable.set_options(sort=None, sort_lanes=None)

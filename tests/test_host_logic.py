@@ -207,10 +207,17 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     assert d.window["bpb"] == 24 and k.window["bpb"] == 16
     k = gen("c5")                                   # 134 MB: global paired REDs only, no window
     assert [hp.strategy for hp in k.plans] == ["global"] and k.window is None and k.smem_bytes == 0
-    k = gen("c4")                                   # big book: one copy of the event code, everything privatised, all fixed point
+    k = gen("c4", sort=False)                       # big book, per-event strategies: one copy of the event code, everything privatised, all fixed point
     assert all(hp.strategy == "smem" for hp in k.plans) and len(k.fx_terms) == 48 and k.threads == 768
     assert k.nfx == 6 and k.source.count("hb_fx_decode<") == 6        # w, w^2, z, z^2, filtered w, filtered w^2: decoded once per event
     assert k.source.count("hb_event(p, hb_smem") == 1
+    k = gen("c4")                                   # default: one sort group per axis expression holds its 4 histograms on bin("e", 100)
+    assert k.sorted is not None and len(k.sorted["groups"]) == 8 and k.sorted["staged"] == 3 and not k.fx_terms
+    assert all(g["nbins"] == 103 and g["values"] == 6 and len(g["hists"]) == 4 for g in k.sorted["groups"])
+    assert sorted(hp.strategy for hp in k.plans).count("sorted") == 32 and k.threads == 1024 and k.tile == 2048
+    assert k.source.count("atomicAdd(") - k.source.count("hb_sadd_u32") <= 8 + 1     # one ticket per group and event
+    k = gen("c3", sort=True)                        # forced on a small book: y and y^2 staged, y^4 = (y^2)^2 recomputed
+    assert k.sorted["staged"] == 2 and k.sorted["groups"][0]["values"] == 3 and k.smem_bytes < 227 * 1024
     k = gen("c2", deterministic=True)
     assert k.deterministic and len(k.fx_terms) == 2 and "hb_fxg_add128" in k.source and "hb_red_pair(" not in k.source.split("hb_event")[1]
 
