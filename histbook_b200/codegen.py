@@ -25,6 +25,7 @@ from histbook_b200 import spec as hbspec
 
 THREADS = 256
 MAX_WIN = 128              # hb_template.cuh HB_MAX_WIN
+MAX_AUX = 64               # hb_template.cuh HB_MAX_AUX
 VEC = 4                    # events per thread per tile (hb_load4)
 
 MAYBECONSTANTS = {"pi": numpy.pi, "Pi": numpy.pi, "e": numpy.e, "E": numpy.e,
@@ -677,9 +678,13 @@ SMEM_MAX = 227 * 1024
 class SortGroup(object):
     """Histograms of a book that share one linear bin index (and row mask): their float64 terms are not added event
     by event with atomics; per tile the events are counting-sorted by that index (ONE native shared-memory atomic per
-    event: the ticket), and every lane of the group's warps then sums a contiguous chunk of the sorted events with
-    plain loads and adds, flushing a bin's partial sum with a plain read-modify-write when the bin's run ends (it ends
-    in exactly one lane).  Replaces 152 ``numpy.add.at`` calls per fill of c4 (hist.py:439-456)."""
+    event: the ticket), and every lane of the group's warps then owns a bin: it sums the bin's run of sorted events
+    with plain loads and adds and adds the result to the block's float64 table with one plain, conflict-free
+    read-modify-write per tile.  Replaces 152 ``numpy.add.at`` calls per fill of c4 (hist.py:439-456).
+    (A balanced variant -- every lane a contiguous chunk of the sorted events, runs that end inside the chunk flushed on
+    the spot, the rest handed on as "tails" -- was built first: every iteration some lane of a warp flushes, so the
+    whole warp walks the 30-instruction flush path nearly every time, twice the instructions and 2 shared-memory
+    wavefronts per event more; profiles/r02_c4_ncu.txt.)"""
 
     def __init__(self, gid, idx, conds, nbins):
         self.gid = gid
@@ -711,7 +716,7 @@ class SortGroup(object):
 
     def smem_bytes(self, tile, lanes):
         nv = len(self.values)
-        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + lanes * (8 + 8 * nv) + 64) // 16 * 16 + 16
+        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + 64) // 16 * 16 + 16
 
 
 def sort_groups(plans, options):
@@ -796,15 +801,33 @@ def choose_strategies(plans, options, prog=None, layout=None):
     sgroups, staged, sort_bytes = [], [], 0
     sort_cap = int(options.get("sort_smem", SMEM_MAX - 1024))
     sort_tile = int(options.get("sort_threads", SORT_THREADS)) * int(options.get("sort_ept", SORT_EPT))
-    sort_lanes = int(options.get("sort_lanes", 64))
+    sort_lanes = options.get("sort_lanes", "auto")
+    group_slots = int(options.get("group_slots", 16))
     if prog is not None:
         sgroups = sort_groups(plans, options)
         sgroups.sort(key=lambda g: -len(g.values) * len(g.members))
+
+        def direct_need(slots):
+            """shared memory the histograms outside the groups would like (fixed point for every float64 term)"""
+            rest = [hp for hp in plans if hp.sgroup is None or id(hp.sgroup) not in set(id(g) for g in sgroups)]
+            return 16 + sum((hp.nbins * (slots if hp.groups else 1) * (16 * len(hp.f64_terms) + (4 if hp.count_term is not None else 0)) + 15) // 16 * 16
+                            for hp in rest)
         while sgroups:
             sgroups = sgroups[:int(options.get("sort_max_groups", SORT_MAX_GROUPS))]
             staged = stage_values(prog, sgroups)
-            sort_bytes = sum(g.smem_bytes(sort_tile, sort_lanes) for g in sgroups) + 8 * len(staged) * sort_tile + 64
+            # the block's warps are dealt out to the groups (4 warps = 128 lanes per group for c4's 8 groups)
+            if sort_lanes == "auto":
+                lanes = 32
+                while lanes * 2 <= min(256, int(options.get("sort_threads", SORT_THREADS)) // len(sgroups)):
+                    lanes *= 2
+            else:
+                lanes = int(sort_lanes)
+            for slots in (group_slots, min(group_slots, 8)):
+                sort_bytes = sum(g.smem_bytes(sort_tile, lanes) for g in sgroups) + 8 * len(staged) * sort_tile + 64
+                if sort_bytes + direct_need(slots) <= sort_cap:
+                    break
             if sort_bytes + 16 * 1024 <= sort_cap:
+                sort_lanes, group_slots = lanes, slots
                 break
             sgroups = sgroups[:-1]                         # does not fit: the last group goes back to the per-event strategies
         kept = set(id(g) for g in sgroups)
@@ -817,6 +840,8 @@ def choose_strategies(plans, options, prog=None, layout=None):
                 hp.strategy = "sorted"
         if not sgroups:
             staged, sort_bytes = [], 0
+    if not sgroups:
+        sort_lanes, group_slots = 64, int(options.get("group_slots", 16))
     # Which float64 terms are accumulated as exact fixed point (16 bytes per bin, native u32 atomics, ~55 instructions,
     # no retries) rather than with float64 CAS loops (8 bytes, ~10 instructions, but several times the shared-memory
     # wavefronts, and one more attempt for every other lane of the warp that is in the same bin):
@@ -838,7 +863,7 @@ def choose_strategies(plans, options, prog=None, layout=None):
     for hp in plans:
         # group axes: the first `group_slots` slab slots (keys in first-seen order) live in shared memory --
         # without this every event of such a histogram is a contended global RED (c4: 8 per event)
-        hp.gcap = int(options.get("group_slots", 16)) if hp.groups else 0
+        hp.gcap = group_slots if hp.groups else 0
         hp.replicas = 1 if hp.groups else int(options.get("replicas", 1))
     for hp in plans:
         terms = list(hp.f64_terms)
@@ -950,10 +975,6 @@ def choose_strategies(plans, options, prog=None, layout=None):
         for g in sgroups:
             g.off["sorted"] = used
             used += (2 * sort_tile + 15) // 16 * 16
-            g.off["tkey"] = used
-            used += (4 * sort_lanes + 15) // 16 * 16
-            g.off["tval"] = used
-            used += 8 * sort_lanes * max(len(g.values), 1)
         e_off = used
         used += 8 * len(staged) * sort_tile
         sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "e_off": e_off, "tile": sort_tile,
@@ -981,7 +1002,8 @@ class Kernel(object):
         self.tile = THREADS * VEC
         self.inexact = set()
         self.key = None
-        self.group_aux = {}         # fill kernel: hist id -> aux slot of its group table
+        self.group_aux = {}         # fill kernel: hist id -> aux slot of its dense slot map (this fill's key combinations -> slab slot)
+        self.goal_aux = {}          # fill kernel: tree key of a group goal -> aux slot of the goal's key table of this fill
         self.window = None          # hot-window histogram: dict(hid, bpb, wmax, totbins, ncol, col, nf)
         self.group_goals = []       # keys kernel: [(tree key, info dict)] in aux order
         self.fx_terms = []          # [(i, hist id, term index)] of the fixed-point terms; scale of term i in p.win[2 + i]
@@ -1258,16 +1280,14 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
          whose return value is the event's rank inside its bin;
       2. one warp per group turns the counters into bin start offsets (and adds them to the group's count table);
       3. every thread writes its events' numbers to start[bin] + rank: the tile's events, sorted by bin, per group;
-      4. per group, HB_LANES lanes each walk a contiguous chunk of the sorted events, adding the staged values in
-         registers; when a bin's run ends inside the chunk the lane is the only one in which it ends and adds the
-         partial sums to the block's float64 table with plain loads and stores; a run that continues in the next
-         lane's chunk is left as a "tail" and added after a barrier by the first lane that holds a tail of that bin.
+      4. per group, every one of HB_LANES lanes owns a bin (bins b, b + HB_LANES, ...): it walks the bin's run of sorted
+         events, adds the staged values in registers and then adds the sums to the block's float64 table with plain
+         loads and stores -- nobody else touches that bin, and consecutive lanes hit consecutive banks.
     No float64 atomics and no fixed-point limbs: c4 went from ~100 shared atomics per event to 8 tickets + 32 counts."""
     groups, staged = layout["groups"], layout["staged"]
     threads, ept, tile, lanes = layout["threads"], layout["ept"], layout["tile"], layout["lanes"]
     G = len(groups)
-    chunk = tile // lanes
-    assert chunk * lanes == tile and threads % lanes == 0
+    assert threads % lanes == 0
     nwg = min(threads // lanes, 15)                        # warp-groups that take sort groups (named barriers 1..15)
     src = []
     src.append('#include "hb_template.cuh"')
@@ -1299,7 +1319,7 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
         src.append("    }")
     src.append("}\n")
 
-    src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, 1) hb_fill_kernel(const HbParams p)\n{')
+    src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % int(options.get("sort_min_blocks", 1)))
     src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
     src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (layout["zero_end"] // 4))
     src.append("    __syncthreads();")
@@ -1332,54 +1352,54 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("        // 3. scatter the event numbers to start[bin] + rank")
     for k in range(ept):
         for g in groups:
-            src.append("        if (kr%d[%d] != 0xffffffffu) reinterpret_cast<unsigned short*>(hb_smem + %d)[reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu)] = (unsigned short)(%d * HB_THREADS + threadIdx.x);" % (
-                k, g.gid, g.off["sorted"], g.off["tick"], k, g.gid, k, g.gid, k))
+            src.append("        if (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[sp] = (unsigned short)(%d * HB_THREADS + threadIdx.x); }" % (
+                k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
     src.append("        __syncthreads();")
-    src.append("        // 4. chunked sums over the sorted events")
+    src.append("        // 4. every lane of a group's warps sums the runs of its bins")
     for g in groups:
         nv = len(g.values)
         wg = g.gid % nwg
         used_slots = sorted(set(k for kind, k in g.stage))
+
+        def element(ind, e):
+            out = []
+            for k in used_slots:
+                out.append("%sconst double v%d_%s = reinterpret_cast<const double*>(hb_smem + %d)[%s];" % (ind, k, e, layout["e_off"] + 8 * k * tile, e))
+            return out
+
+        def adds(ind, e):
+            out = []
+            for j, (kind, k) in enumerate(g.stage):
+                if kind == "E":
+                    out.append("%sa%d += v%d_%s;" % (ind, j, k, e))
+                else:
+                    out.append("%sa%d += hb_mul<double>(v%d_%s, v%d_%s);" % (ind, j, k, e, k, e))
+            return out
         src.append("        if (hb_wg == %d) {   // sort group %d" % (wg, g.gid))
         src.append("            const hb_u32* const st = reinterpret_cast<const hb_u32*>(hb_smem + %d);" % g.off["tick"])
         src.append("            const unsigned short* const so = reinterpret_cast<const unsigned short*>(hb_smem + %d);" % g.off["sorted"])
         src.append("            double* const acc = reinterpret_cast<double*>(hb_smem + %d);" % g.off["acc"])
-        src.append("            int* const tkeys = reinterpret_cast<int*>(hb_smem + %d);" % g.off["tkey"])
-        src.append("            double* const tvals = reinterpret_cast<double*>(hb_smem + %d);" % g.off["tval"])
-        src.append("            const hb_u32 ng = st[%d];" % g.nbins)
-        src.append("            const hb_u32 p0 = (hb_u32)hb_l * %du, p1 = min(p0 + %du, ng);" % (chunk, chunk))
-        src.append("            " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
-        src.append("            int tkey = -1;")
-        flush = " ".join("acc[%d + key] += a%d; a%d = 0.0;" % (j * g.nbins, j, j) for j in range(nv))
-        src.append("            if (p0 < ng) {")
-        src.append("                int key = hb_sort_find(st, %d, p0);" % g.nbins)
-        src.append("                hb_u32 runend = st[key + 1];")
-        src.append("                for (hb_u32 pos = p0; pos < p1; ++pos) {")
-        src.append("                    if (pos >= runend) {       // the run of `key` ends in this lane's chunk, and in no other lane's")
-        src.append("                        " + flush)
-        src.append("                        do { ++key; runend = st[key + 1]; } while (pos >= runend);")
-        src.append("                    }")
-        src.append("                    const unsigned e = so[pos];")
-        for k in used_slots:
-            src.append("                    const double v%d = reinterpret_cast<const double*>(hb_smem + %d)[e];" % (k, layout["e_off"] + 8 * k * tile))
-        for j, (kind, k) in enumerate(g.stage):
-            if kind == "E":
-                src.append("                    a%d += v%d;" % (j, k))
-            else:
-                src.append("                    a%d += hb_mul<double>(v%d, v%d);" % (j, k, k))
+        src.append("            for (int b = hb_l; b < %d; b += HB_LANES) {" % g.nbins)
+        src.append("                hb_u32 pos = st[b];")
+        src.append("                const hb_u32 end = st[b + 1];")
+        src.append("                if (pos == end) continue;")
+        src.append("                " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
+        src.append("                for (; pos + 1u < end; pos += 2u) {       // two events per round: their loads are in flight together")
+        src.append("                    const unsigned e0 = so[pos], e1 = so[pos + 1u];")
+        src.extend(element("                    ", "e0"))
+        src.extend(element("                    ", "e1"))
+        src.extend(adds("                    ", "e0"))
+        src.extend(adds("                    ", "e1"))
         src.append("                }")
-        src.append("                if (runend > p1) tkey = key;       // the run goes on in the next lane: a tail")
-        src.append("                else { %s }" % flush)
+        src.append("                if (pos < end) {")
+        src.append("                    const unsigned e0 = so[pos];")
+        src.extend(element("                    ", "e0"))
+        src.extend(adds("                    ", "e0"))
+        src.append("                }")
+        src.append("                " + " ".join("acc[%d + b] += a%d;" % (j * g.nbins, j) for j in range(nv)) + "      // this lane alone adds to bin b")
         src.append("            }")
-        src.append("            tkeys[hb_l] = tkey;")
-        src.append("            if (tkey >= 0) { %s }" % " ".join("tvals[%d + hb_l] = a%d;" % (j * lanes, j) for j in range(nv)))
         src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))
         src.append("            for (int b = hb_l; b <= %d; b += HB_LANES) reinterpret_cast<hb_u32*>(hb_smem + %d)[b] = 0u;" % (g.nbins, g.off["tick"]))
-        src.append("            if (tkey >= 0 && (hb_l == 0 || tkeys[hb_l - 1] != tkey)) {")
-        src.append("                const int key = tkey;")
-        src.append("                for (int m = hb_l + 1; m < HB_LANES && tkeys[m] == key; ++m) { %s }" % " ".join("a%d += tvals[%d + m];" % (j, j * lanes) for j in range(nv)))
-        src.append("                " + flush)
-        src.append("            }")
         src.append("        }")
     src.append("        __syncthreads();")
     src.append("    }")
@@ -1400,21 +1420,31 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     return "\n".join(src) + "\n"
 
 
+def _goal_lookup(g, aux_slot):
+    """C lines (event-function scope) that find the position of one group goal's key among the keys THIS fill holds
+    (ascending 64-bit patterns, written by the host after discovery: fillable.fill_hists).  Done once per goal and
+    event, however many histograms group by it."""
+    n = g.c
+    out = ["const hb_u64* const gq_%s = reinterpret_cast<const hb_u64*>(p.aux[%d]);" % (n, aux_slot),
+           "const int gn_%s = (int)gq_%s[0];" % (n, n)]
+    if g.dtype.kind == "f" and not g.extra["nanflow"]:
+        # nanflow=False: NaN rows are dropped (calc/__init__.py:189-192)
+        out.append("const int gd_%s = (%s != %s) ? -1 : hb_key_find(gq_%s + 2, gn_%s, hb_keybits(%s));" % (n, g.c, g.c, n, n, g.c))
+    else:
+        out.append("const int gd_%s = hb_key_find(gq_%s + 2, gn_%s, hb_keybits(%s));" % (n, n, n, g.c))
+    return out
+
+
 def _group_lookup(hp, aux_slot):
-    """C lines that turn the group keys of one event into the slab slot of hist ``hp`` (or reject the row)."""
-    K = len(hp.groups)
-    out = ["const hb_u64* const gt = reinterpret_cast<const hb_u64*>(p.aux[%d]);" % aux_slot,
-           "bool okg = true; hb_i64 comb = 0;"]
-    for a, g in enumerate(hp.groups):
-        out.append("{")
-        if g.dtype.kind == "f" and not g.extra["nanflow"]:
-            out.append("    if (%s != %s) okg = false;        // nanflow=False: NaN rows are dropped (calc/__init__.py:189-192)" % (g.c, g.c))
-        out.append("    const int pos = hb_key_find(gt + gt[%d], (int)gt[%d], hb_keybits(%s));" % (1 + K + a, 1 + a, g.c))
-        out.append("    if (pos < 0) okg = false;")
-        out.append("    comb = comb * (hb_i64)gt[%d] + pos;" % (1 + a))
-        out.append("}")
-    out.append("int slot = -1;")
-    out.append("if (okg) slot = (int)reinterpret_cast<const hb_i64*>(gt + gt[%d])[comb];" % (1 + 2 * K))
+    """C lines that turn the group keys of one event into the slab slot of hist ``hp`` (or reject the row): the
+    positions of its goals' keys (``_goal_lookup``) index the histogram's dense slot map of this fill."""
+    out = ["const int* const gm = reinterpret_cast<const int*>(p.aux[%d]);" % aux_slot]
+    okg = " && ".join("gd_%s >= 0" % g.c for g in hp.groups)
+    comb = "gd_%s" % hp.groups[0].c
+    for g in hp.groups[1:]:
+        comb = "(%s) * gn_%s + gd_%s" % (comb, g.c, g.c)
+    out.append("const bool okg = %s;" % okg)
+    out.append("const int slot = okg ? gm[%s] : -1;" % comb)
     return out
 
 
@@ -1599,7 +1629,17 @@ def generate(spec, coltypes, options=None):
             smem_cap = smem
 
     group_aux = {}
+    goal_aux = {}                                      # tree key of a group goal -> aux slot of its key table
     ev = list(prog.body)
+    done_goals = set()
+    for hp in plans:
+        for a, g in enumerate(hp.groups):
+            goalkey = hbspec.tree_key(spec["hists"][hp.hid]["group"][a]["goal"])
+            if goalkey not in goal_aux:
+                goal_aux[goalkey] = len(goal_aux)
+            if g.c not in done_goals:
+                done_goals.add(g.c)
+                ev.extend(_goal_lookup(g, goal_aux[goalkey]))
     ev.extend(_emit_fx_decodes(plans))
     for hp in plans:
         ev.append("// ---- hist %d: shape %s, %s" % (hp.hid, hp.shape, hp.strategy))
@@ -1608,9 +1648,9 @@ def generate(spec, coltypes, options=None):
         idx, conds = hist_index(hp)
         ev.append("{")
         if hp.groups:
-            if len(group_aux) >= 64:
-                raise UnsupportedError("more than 64 histograms with group axes in one fill")
-            group_aux[hp.hid] = len(group_aux)
+            if len(group_aux) + len(goal_aux) >= MAX_AUX - 4:
+                raise UnsupportedError("more than {0} histograms with group axes in one fill".format(MAX_AUX - 4 - len(goal_aux)))
+            group_aux[hp.hid] = len(goal_aux) + len(group_aux)
             ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
             conds = ["okg", "slot >= 0"] + conds
         conds = ["live"] + conds
@@ -1757,7 +1797,7 @@ def generate(spec, coltypes, options=None):
 
     k = Kernel()
     winfo = None
-    naux = len(group_aux)
+    naux = len(group_aux) + len(goal_aux)
     if window is not None:
         bpb = window.row_bytes(options)
         winfo = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "rows": window.win_rows, "trail": window.win_trail,
@@ -1802,6 +1842,7 @@ def generate(spec, coltypes, options=None):
         k.sorted["staged"] = len(layout["staged"])
     k.inexact = set(prog.inexact)
     k.group_aux = group_aux
+    k.goal_aux = goal_aux
     k.key = hashlib.sha256(k.source.encode()).hexdigest()
     return k
 

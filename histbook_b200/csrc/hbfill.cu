@@ -17,8 +17,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hbfill.h"
@@ -182,6 +185,7 @@ struct hb_program {
     CUfunction fn = nullptr;
     int threads = 256;
     int tile = 1024;            // events per block and round of the kernel's grid-stride loop (HB_TILE of the generated source)
+    int max_blocks_per_sm = 0;  // > 0: the grid is sized for at most this many resident blocks per SM (parts of a split book share the SMs)
     int smem = 0;
     int blocks_per_sm = 1;
     int regs = 0;
@@ -325,6 +329,12 @@ extern "C" int hb_program_destroy(hb_program* p) {
 extern "C" int hb_program_set_tile(hb_program* p, int tile_events) {
     if (!p || tile_events < 1) return fail(HB_ERR_ARG, "bad tile size");
     p->tile = tile_events;
+    return HB_OK;
+}
+
+extern "C" int hb_program_set_max_blocks_per_sm(hb_program* p, int blocks) {
+    if (!p || blocks < 0) return fail(HB_ERR_ARG, "bad block limit");
+    p->max_blocks_per_sm = blocks;
     return HB_OK;
 }
 
@@ -541,11 +551,21 @@ extern "C" int64_t hb_arena_size(const hb_arena* a) { return a ? a->n : 0; }
 
 static const int kDtypeSize[11] = {8, 4, 8, 4, 2, 1, 8, 4, 2, 1, 1};
 
+// Host columns travel in chunks through two device staging buffers per column (chunk k + 1 is copied while the kernels
+// read chunk k).  Page-locked host memory (cudaHostAlloc / cudaHostRegister, torch pin_memory) is copied from where it
+// lies.  Pageable memory -- what numpy.random or pandas hand out -- first goes through a ring of page-locked bounce
+// buffers, filled by a few worker threads (one memcpy stream per thread): cudaMemcpyAsync from pageable memory is a
+// synchronous, single-threaded staging copy inside the driver (measured 9.4 GB/s against 44.7 GB/s from page-locked
+// memory, BENCH r2 c4), the ring restores the overlap of the host copy, the DMA and the kernels.
+#define HB_RING 3
 struct Staging {
     void* dev[2][HB_MAX_COLS] = {};
     size_t cap[2][HB_MAX_COLS] = {};
     cudaEvent_t copied[2] = {};
     cudaEvent_t consumed[2] = {};
+    void* pin[HB_RING][HB_MAX_COLS] = {};
+    size_t pin_cap[HB_RING][HB_MAX_COLS] = {};
+    cudaEvent_t sent[HB_RING] = {};          // the DMA out of ring slot r has completed
     bool init = false;
 };
 static Staging g_stage;
@@ -558,6 +578,100 @@ static int staging_reserve(int buf, int col, size_t bytes) {
     CUDA_TRY(cudaMalloc(&g_stage.dev[buf][col], bytes));
     g_stage.cap[buf][col] = bytes;
     return HB_OK;
+}
+
+static int ring_reserve(int slot, int col, size_t bytes) {
+    if (g_stage.pin_cap[slot][col] >= bytes) return HB_OK;
+    if (g_stage.pin[slot][col]) cudaFreeHost(g_stage.pin[slot][col]);
+    g_stage.pin[slot][col] = nullptr;
+    g_stage.pin_cap[slot][col] = 0;
+    CUDA_TRY(cudaHostAlloc(&g_stage.pin[slot][col], bytes, cudaHostAllocDefault));
+    g_stage.pin_cap[slot][col] = bytes;
+    return HB_OK;
+}
+
+// a small pool of copy threads (created at the first pageable column)
+struct CopyJob { char* dst; const char* src; size_t bytes; };
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable wake, done;
+    std::vector<CopyJob> jobs;
+    size_t next = 0, finished = 0;
+    bool stop = false;
+
+    void run() {
+        std::unique_lock<std::mutex> lock(m);
+        while (true) {
+            wake.wait(lock, [this] { return stop || next < jobs.size(); });
+            if (stop) return;
+            const CopyJob j = jobs[next++];
+            lock.unlock();
+            memcpy(j.dst, j.src, j.bytes);
+            lock.lock();
+            if (++finished == jobs.size()) done.notify_all();
+        }
+    }
+    void start(int n) {
+        for (int i = 0; i < n; ++i) workers.emplace_back([this] { run(); });
+    }
+    // copies all jobs; the calling thread works too
+    void copy(std::vector<CopyJob>& batch) {
+        if (batch.empty()) return;
+        std::unique_lock<std::mutex> lock(m);
+        jobs.swap(batch);
+        next = 0;
+        finished = 0;
+        wake.notify_all();
+        while (next < jobs.size()) {
+            const CopyJob j = jobs[next++];
+            lock.unlock();
+            memcpy(j.dst, j.src, j.bytes);
+            lock.lock();
+            ++finished;
+        }
+        done.wait(lock, [this] { return finished == jobs.size(); });
+        jobs.clear();
+        next = finished = 0;
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
+        }
+        wake.notify_all();
+        for (auto& t : workers) t.join();
+    }
+};
+static CopyPool* g_pool = nullptr;
+static int g_copy_threads = -1;
+
+static CopyPool* copy_pool() {
+    if (!g_pool) {
+        if (g_copy_threads < 0) {
+            const char* env = getenv("HB_COPY_THREADS");
+            unsigned hw = std::thread::hardware_concurrency();
+            g_copy_threads = env ? atoi(env) : (int)(hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+            if (g_copy_threads < 1) g_copy_threads = 1;
+        }
+        g_pool = new CopyPool();
+        g_pool->start(g_copy_threads - 1);
+    }
+    return g_pool;
+}
+
+extern "C" int hb_set_copy_threads(int n) {
+    if (n < 1 || n > 64) return fail(HB_ERR_ARG, "copy threads must be 1..64");
+    if (g_pool) { delete g_pool; g_pool = nullptr; }
+    g_copy_threads = n;
+    return HB_OK;
+}
+
+static bool is_pageable(const void* ptr) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return true; }
+    return attr.type == cudaMemoryTypeUnregistered;
 }
 
 // Counters of the dynamic tile hand-out (HbParams::sched): one pair per stream, because launches on one stream run one
@@ -574,10 +688,16 @@ static int sched_for(cudaStream_t stream, hb_u32** out) {
     return HB_OK;
 }
 
-static int launch(hb_program* prog, const HbParams& params, int grid) {
+// streams of the parts of a multi-program fill (hb_fill_multi): the kernels of a book that was split run side by side
+#define HB_MAX_PARTS 8
+static cudaStream_t g_part_stream[HB_MAX_PARTS] = {};
+static cudaEvent_t g_part_done[HB_MAX_PARTS] = {};
+static cudaEvent_t g_fork = nullptr;
+
+static int launch(hb_program* prog, const HbParams& params, int grid, cudaStream_t stream) {
     void* args[1] = {(void*)&params};
     DRV_TRY(g_drv.LaunchKernel(prog->fn, (unsigned)grid, 1, 1, (unsigned)prog->threads, 1, 1,
-                               (unsigned)prog->smem, (CUstream)g_stream, args, nullptr));
+                               (unsigned)prog->smem, (CUstream)stream, args, nullptr));
     return HB_OK;
 }
 
@@ -590,43 +710,88 @@ extern "C" int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64
 extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
                              int nhists, hb_arena* const* hists, hb_arena* const* exact, int naux, const void* const* aux,
                              int nwin, const int32_t* win, int flags, hb_stats* stats) {
+    hb_launch one;
+    memset(&one, 0, sizeof(one));
+    one.prog = prog;
+    one.ncols = ncols;
+    one.colmap = nullptr;
+    one.nhists = nhists;
+    one.hists = hists;
+    one.exact = exact;
+    one.naux = naux;
+    one.aux = aux;
+    one.nwin = nwin;
+    one.win = win;
+    return hb_fill_multi(1, &one, ncols, cols, n, flags, stats);
+}
+
+extern "C" int hb_fill_multi(int nlaunch, const hb_launch* L, int ncols, const hb_column* cols, int64_t n, int flags, hb_stats* stats) {
     int rc = ensure_device();
     if (rc) return rc;
-    if (!prog || ncols < 0 || ncols > HB_MAX_COLS || nhists < 0 || nhists > HB_MAX_HISTS || naux < 0 || naux > HB_MAX_AUX || n < 0)
+    if (nlaunch < 1 || nlaunch > HB_MAX_PARTS || !L || ncols < 0 || ncols > HB_MAX_COLS || n < 0)
         return fail(HB_ERR_ARG, "bad hb_fill arguments");
     std::lock_guard<std::mutex> lock(g_mutex);
 
-    HbParams base;
-    memset(&base, 0, sizeof(base));
-    bool any_host = false;
+    bool any_host = false, any_pageable = false;
+    bool pageable[HB_MAX_COLS] = {};
     for (int c = 0; c < ncols; ++c) {
         if (cols[c].dtype < 0 || cols[c].dtype > 10) return fail(HB_ERR_ARG, "bad column dtype");
-        if (cols[c].is_scalar) base.scal[c] = cols[c].scalar_bits;
-        else {
-            if (!cols[c].ptr && n > 0) return fail(HB_ERR_ARG, "null column pointer");
-            if (cols[c].location == 0) any_host = true;
+        if (cols[c].is_scalar) continue;
+        if (!cols[c].ptr && n > 0) return fail(HB_ERR_ARG, "null column pointer");
+        if (cols[c].location == 0) {
+            any_host = true;
+            if (n > 0 && is_pageable(cols[c].ptr)) { pageable[c] = true; any_pageable = true; }
         }
     }
-    for (int h = 0; h < nhists; ++h) {
-        if (!hists[h]) return fail(HB_ERR_ARG, "null arena");
-        base.hist[h] = hists[h]->ptr;
-        base.fxg[h] = (exact && exact[h]) ? reinterpret_cast<hb_u64*>(exact[h]->ptr) : nullptr;
+    std::vector<HbParams> base((size_t)nlaunch);
+    int tile = 1;
+    for (int l = 0; l < nlaunch; ++l) {
+        const hb_launch& q = L[l];
+        if (!q.prog || q.ncols < 0 || q.ncols > HB_MAX_COLS || q.nhists < 0 || q.nhists > HB_MAX_HISTS || q.naux < 0 || q.naux > HB_MAX_AUX ||
+            q.nwin < 0 || q.nwin > HB_MAX_WIN)
+            return fail(HB_ERR_ARG, "bad hb_fill arguments");
+        HbParams& b = base[l];
+        memset(&b, 0, sizeof(b));
+        for (int i = 0; i < q.ncols; ++i) {
+            const int c = q.colmap ? q.colmap[i] : i;
+            if (c < 0 || c >= ncols) return fail(HB_ERR_ARG, "column map out of range");
+            if (cols[c].is_scalar) b.scal[i] = cols[c].scalar_bits;
+        }
+        for (int h = 0; h < q.nhists; ++h) {
+            if (!q.hists[h]) return fail(HB_ERR_ARG, "null arena");
+            b.hist[h] = q.hists[h]->ptr;
+            b.fxg[h] = (q.exact && q.exact[h]) ? reinterpret_cast<hb_u64*>(q.exact[h]->ptr) : nullptr;
+        }
+        for (int a = 0; a < q.naux; ++a) b.aux[a] = q.aux[a];
+        for (int i = 0; i < q.nwin; ++i) b.win[i] = q.win[i];
+        // chunk boundaries must be tile boundaries of every program: least common multiple (tiles are threads x 1, 2 or 4)
+        int t = q.prog->tile, a = tile, g = t;
+        while (a) { int r = g % a; g = a; a = r; }
+        tile = tile / g * t;
     }
-    for (int a = 0; a < naux; ++a) base.aux[a] = aux[a];
-    if (nwin < 0 || nwin > HB_MAX_WIN) return fail(HB_ERR_ARG, "too many window parameters");
-    for (int i = 0; i < nwin; ++i) base.win[i] = win[i];
-    rc = sched_for(g_stream, &base.sched);
-    if (rc) return rc;
+    const bool multi = nlaunch > 1;
+    if (multi) {
+        if (!g_fork) CUDA_TRY(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+        for (int l = 0; l < nlaunch; ++l) {
+            if (!g_part_stream[l]) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&g_part_stream[l], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&g_part_done[l], cudaEventDisableTiming));
+            }
+        }
+    }
+    for (int l = 0; l < nlaunch; ++l) {
+        rc = sched_for(multi ? g_part_stream[l] : g_stream, &base[l].sched);
+        if (rc) return rc;
+    }
 
-    const int tile = prog->tile;
-    const int resident = g_sm_count * prog->blocks_per_sm;
-    int64_t per_launch = any_host ? g_chunk_events : ((int64_t)1 << 30);
+    // pageable host memory: smaller chunks, so that the three stages (host copy, DMA, kernels) overlap on modest fills too
+    int64_t per_launch = any_host ? (any_pageable ? std::min<int64_t>(g_chunk_events, (int64_t)1 << 22) : g_chunk_events) : ((int64_t)1 << 30);
     per_launch = per_launch / tile * tile;
     if (per_launch < tile) per_launch = tile;
 
     hb_stats st;
     memset(&st, 0, sizeof(st));
-    st.blocks_per_sm = prog->blocks_per_sm;
+    st.blocks_per_sm = L[0].prog->blocks_per_sm;
 
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (flags & HB_FILL_TIMED) {
@@ -639,21 +804,43 @@ extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols,
             CUDA_TRY(cudaEventCreateWithFlags(&g_stage.copied[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&g_stage.consumed[b], cudaEventDisableTiming));
         }
+        for (int r = 0; r < HB_RING; ++r) CUDA_TRY(cudaEventCreateWithFlags(&g_stage.sent[r], cudaEventDisableTiming | cudaEventBlockingSync));
         g_stage.init = true;
     }
+    if (multi) {
+        // the parts start after everything queued on the compute stream so far (clears, uploads, the previous fill)
+        CUDA_TRY(cudaEventRecord(g_fork, g_stream));
+        for (int l = 0; l < nlaunch; ++l) CUDA_TRY(cudaStreamWaitEvent(g_part_stream[l], g_fork, 0));
+    }
 
+    std::vector<CopyJob> jobs;
     int chunk_index = 0;
     for (int64_t off = 0; off < n; off += per_launch, ++chunk_index) {
         const int64_t m = (n - off < per_launch) ? (n - off) : per_launch;
-        HbParams p = base;
-        p.n = m;
-        p.flags = flags;
-        const int buf = chunk_index & 1;
+        const int buf = chunk_index & 1, slot = chunk_index % HB_RING;
+        const void* colptr[HB_MAX_COLS] = {};
+        if (any_pageable) {
+            // ring slot reuse: its last DMA must be through before the workers overwrite it
+            CUDA_TRY(cudaEventSynchronize(g_stage.sent[slot]));
+            jobs.clear();
+            copy_pool();
+            const int np = g_copy_threads > 0 ? g_copy_threads : 1;
+            for (int c = 0; c < ncols; ++c) {
+                if (cols[c].is_scalar || !pageable[c]) continue;
+                const size_t esize = (size_t)kDtypeSize[cols[c].dtype], bytes = (size_t)m * esize;
+                rc = ring_reserve(slot, c, (size_t)per_launch * esize);
+                if (rc) return rc;
+                const char* src = (const char*)cols[c].ptr + (size_t)off * esize;
+                const size_t step = ((bytes + np - 1) / np + 4095) / 4096 * 4096;
+                for (size_t o = 0; o < bytes; o += step)
+                    jobs.push_back({(char*)g_stage.pin[slot][c] + o, src + o, std::min(step, bytes - o)});
+            }
+            copy_pool()->copy(jobs);
+        }
         // staging buffer reuse: the copy waits until the last kernel that read this buffer is done -- the one two
         // chunks back, or the tail of the PREVIOUS hb_fill call (waiting on a never-recorded event is a no-op)
         if (any_host)
             CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, g_stage.consumed[buf], 0));
-        bool aligned = true;
         for (int c = 0; c < ncols; ++c) {
             if (cols[c].is_scalar) continue;
             const size_t esize = (size_t)kDtypeSize[cols[c].dtype];
@@ -661,31 +848,56 @@ extern "C" int hb_fill_exact(hb_program* prog, int ncols, const hb_column* cols,
             if (cols[c].location == 0) {
                 rc = staging_reserve(buf, c, (size_t)per_launch * esize);
                 if (rc) return rc;
-                CUDA_TRY(cudaMemcpyAsync(g_stage.dev[buf][c], src, (size_t)m * esize, cudaMemcpyHostToDevice, g_copy_stream));
+                const void* from = pageable[c] ? g_stage.pin[slot][c] : (const void*)src;
+                CUDA_TRY(cudaMemcpyAsync(g_stage.dev[buf][c], from, (size_t)m * esize, cudaMemcpyHostToDevice, g_copy_stream));
                 st.h2d_bytes += (int64_t)((size_t)m * esize);
-                p.cols[c] = g_stage.dev[buf][c];
+                colptr[c] = g_stage.dev[buf][c];
             } else {
-                p.cols[c] = src;
+                colptr[c] = src;
             }
-            if (((uintptr_t)p.cols[c]) % (4 * esize) != 0) aligned = false;
         }
-        p.vec_ok = aligned ? 1 : 0;
-        if (any_host) {
-            CUDA_TRY(cudaEventRecord(g_stage.copied[buf], g_copy_stream));
-            CUDA_TRY(cudaStreamWaitEvent(g_stream, g_stage.copied[buf], 0));
+        if (any_pageable) CUDA_TRY(cudaEventRecord(g_stage.sent[slot], g_copy_stream));
+        if (any_host) CUDA_TRY(cudaEventRecord(g_stage.copied[buf], g_copy_stream));
+        for (int l = 0; l < nlaunch; ++l) {
+            const hb_launch& q = L[l];
+            cudaStream_t stream = multi ? g_part_stream[l] : g_stream;
+            HbParams p = base[l];
+            p.n = m;
+            p.flags = flags;
+            bool aligned = true;
+            for (int i = 0; i < q.ncols; ++i) {
+                const int c = q.colmap ? q.colmap[i] : i;
+                if (cols[c].is_scalar) continue;
+                p.cols[i] = colptr[c];
+                if (((uintptr_t)p.cols[i]) % (4 * (size_t)kDtypeSize[cols[c].dtype]) != 0) aligned = false;
+            }
+            p.vec_ok = aligned ? 1 : 0;
+            if (any_host) CUDA_TRY(cudaStreamWaitEvent(stream, g_stage.copied[buf], 0));
+            const int ptile = q.prog->tile;
+            int per_sm = q.prog->blocks_per_sm;
+            if (q.prog->max_blocks_per_sm > 0 && per_sm > q.prog->max_blocks_per_sm) per_sm = q.prog->max_blocks_per_sm;
+            const int resident = g_sm_count * per_sm;
+            int64_t ntiles = (m + ptile - 1) / ptile;
+            int grid = (int)(ntiles < resident ? ntiles : resident);
+            if (grid < 1) grid = 1;
+            // equal shares: with r = ceil(ntiles / grid) rounds of the grid-stride loop, ceil(ntiles / r) blocks do r tiles each
+            // instead of a last round that keeps a fraction of the SMs busy (c1 at 1e7 events: 8.25 tiles per resident block)
+            const int64_t rounds = (ntiles + grid - 1) / grid;
+            if (rounds > 1) grid = (int)((ntiles + rounds - 1) / rounds);
+            rc = launch(q.prog, p, grid, stream);
+            if (rc) return rc;
+            st.launches += 1;
+            st.grid = grid;
+            if (multi) {
+                CUDA_TRY(cudaEventRecord(g_part_done[l], stream));
+                CUDA_TRY(cudaStreamWaitEvent(g_stream, g_part_done[l], 0));       // join: the compute stream continues after every part
+            }
         }
-        int64_t ntiles = (m + tile - 1) / tile;
-        int grid = (int)(ntiles < resident ? ntiles : resident);
-        if (grid < 1) grid = 1;
-        // equal shares: with r = ceil(ntiles / grid) rounds of the grid-stride loop, ceil(ntiles / r) blocks do r tiles each
-        // instead of a last round that keeps a fraction of the SMs busy (c1 at 1e7 events: 8.25 tiles per resident block)
-        const int64_t rounds = (ntiles + grid - 1) / grid;
-        if (rounds > 1) grid = (int)((ntiles + rounds - 1) / rounds);
-        rc = launch(prog, p, grid);
-        if (rc) return rc;
         if (any_host) CUDA_TRY(cudaEventRecord(g_stage.consumed[buf], g_stream));
-        st.launches += 1;
-        st.grid = grid;
+        if (multi && off + per_launch < n) {
+            CUDA_TRY(cudaEventRecord(g_fork, g_stream));
+            for (int l = 0; l < nlaunch; ++l) CUDA_TRY(cudaStreamWaitEvent(g_part_stream[l], g_fork, 0));
+        }
     }
     st.events = n;
     if (any_host) CUDA_TRY(cudaStreamSynchronize(g_copy_stream));   // caller may now reuse / free its host columns

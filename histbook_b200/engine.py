@@ -28,6 +28,13 @@ class hb_column(ctypes.Structure):
                 ("is_scalar", ctypes.c_int32), ("reserved", ctypes.c_int32), ("scalar_bits", ctypes.c_uint64)]
 
 
+class hb_launch(ctypes.Structure):
+    _fields_ = [("prog", ctypes.c_void_p), ("ncols", ctypes.c_int32), ("colmap", ctypes.POINTER(ctypes.c_int32)),
+                ("nhists", ctypes.c_int32), ("hists", ctypes.POINTER(ctypes.c_void_p)), ("exact", ctypes.POINTER(ctypes.c_void_p)),
+                ("naux", ctypes.c_int32), ("aux", ctypes.POINTER(ctypes.c_void_p)), ("nwin", ctypes.c_int32),
+                ("win", ctypes.POINTER(ctypes.c_int32))]
+
+
 class hb_stats(ctypes.Structure):
     _fields_ = [("events", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("launches", ctypes.c_int32),
                 ("grid", ctypes.c_int32), ("blocks_per_sm", ctypes.c_int32), ("reserved", ctypes.c_int32),
@@ -54,6 +61,9 @@ SYMBOLS = {
     "hb_program_load": (_I, [_P, ctypes.c_size_t, ctypes.c_char_p, _I, _I, _PP]),
     "hb_program_destroy": (_I, [_P]),
     "hb_program_set_tile": (_I, [_P, _I]),
+    "hb_program_set_max_blocks_per_sm": (_I, [_P, _I]),
+    "hb_fill_multi": (_I, [_I, ctypes.POINTER(hb_launch), _I, ctypes.POINTER(hb_column), _I64, _I, ctypes.POINTER(hb_stats)]),
+    "hb_set_copy_threads": (_I, [_I]),
     "hb_program_info": (_I, [_P, _IP, _IP, _IP]),
     "hb_free": (None, [_P]),
     "hb_arena_create": (_I, [_I64, _PP]),
@@ -200,13 +210,15 @@ def compile_source(source, lineinfo=True):
 class Program(object):
     """A loaded fill kernel."""
 
-    def __init__(self, cubin, kernel_name, threads, smem_bytes, tile=None):
+    def __init__(self, cubin, kernel_name, threads, smem_bytes, tile=None, max_blocks_per_sm=0):
         init()
         self._h = ctypes.c_void_p()
         self._cubin = cubin
         check(lib().hb_program_load(cubin, len(cubin), kernel_name.encode(), int(threads), int(smem_bytes), ctypes.byref(self._h)))
         if tile is not None and int(tile) != 4 * int(threads):
             check(lib().hb_program_set_tile(self._h, int(tile)))
+        if max_blocks_per_sm:
+            check(lib().hb_program_set_max_blocks_per_sm(self._h, int(max_blocks_per_sm)))
         regs, ssm, occ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         check(lib().hb_program_info(self._h, ctypes.byref(regs), ctypes.byref(ssm), ctypes.byref(occ)))
         self.regs, self.static_smem, self.blocks_per_sm = regs.value, ssm.value, occ.value
@@ -408,5 +420,42 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exa
         ex = (ctypes.c_void_p * max(len(arenas), 1))(*[(a._h if a is not None else None) for a in exact])
         check(lib().hb_fill_exact(program._h, ncols, cols, int(n), len(arenas), hist, ex, len(aux), auxp, len(win), winp,
                                   HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
+    return {"events": stats.events, "h2d_bytes": stats.h2d_bytes, "launches": stats.launches, "grid": stats.grid,
+            "blocks_per_sm": stats.blocks_per_sm, "ms_kernel": stats.ms_kernel}
+
+
+def fill_multi(parts, columns, n, timed=False, offset=0):
+    """One pass over ``columns`` for several programs at once (hb_fill_multi): ``parts`` = list of dicts with keys
+    program, colmap (indices into ``columns`` per column slot of the program), arenas, aux, win, exact (or None).
+    Every host chunk is staged once; the parts' kernels run side by side on their own streams."""
+    init()
+    ncols = len(columns)
+    structs = []
+    for c in columns:
+        if c[0] == "scalar":
+            structs.append(hb_column(None, c[1], 0, 1, 0, c[2]))
+        else:
+            structs.append(hb_column((c[0] + offset * _ITEMSIZE[c[1]]) if c[0] else c[0], c[1], c[2], 0, 0, 0))
+    cols = (hb_column * max(ncols, 1))(*structs)
+    launches = (hb_launch * len(parts))()
+    keep = []
+    for q, part in zip(launches, parts):
+        arenas, aux, win, exact = part["arenas"], part.get("aux", ()), part.get("win", ()), part.get("exact")
+        colmap = (ctypes.c_int32 * max(len(part["colmap"]), 1))(*[int(i) for i in part["colmap"]])
+        hist = (ctypes.c_void_p * max(len(arenas), 1))(*[a._h for a in arenas])
+        auxp = (ctypes.c_void_p * max(len(aux), 1))(*[int(x) for x in aux])
+        winp = (ctypes.c_int32 * max(len(win), 1))(*[int(x) for x in win])
+        ex = None
+        if exact is not None:
+            ex = (ctypes.c_void_p * max(len(arenas), 1))(*[(a._h if a is not None else None) for a in exact])
+        keep.append((colmap, hist, auxp, winp, ex))
+        q.prog = part["program"]._h
+        q.ncols, q.colmap = len(part["colmap"]), colmap
+        q.nhists, q.hists = len(arenas), hist
+        q.exact = ex if ex is not None else ctypes.POINTER(ctypes.c_void_p)()
+        q.naux, q.aux = len(aux), auxp
+        q.nwin, q.win = len(win), winp
+    stats = hb_stats()
+    check(lib().hb_fill_multi(len(parts), launches, ncols, cols, int(n), HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
     return {"events": stats.events, "h2d_bytes": stats.h2d_bytes, "launches": stats.launches, "grid": stats.grid,
             "blocks_per_sm": stats.blocks_per_sm, "ms_kernel": stats.ms_kernel}

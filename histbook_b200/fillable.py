@@ -44,13 +44,17 @@ class Plan(object):
     """What has to be computed for a fixed list of histograms (built once, like Fillable.fields)."""
     generation = 0
 
-    def __init__(self, hists=None, spec=None):
+    def __init__(self, hists=None, spec=None, options=None):
         self.spec = hbspec.book_spec(hists) if spec is None else spec
+        self.options = dict(options or {})   # overrides of the process-wide options (the parts of a split book)
+        self.parts = {}             # dtype signature -> None | [(Plan of the part, indices of its histograms)]
+        self.discovery = {}         # dtype signature -> (keys Kernel, keys Program) of the whole book
         self.nhists = len(self.spec["hists"])
         self.fields = hbspec.spec_fields(self.spec)
         self.kernels = {}           # dtype signature -> (fill Kernel, Program, keys Kernel, keys Program, range Kernel, range Program)
         self.generation = Plan.generation
         self.keysets = None
+        self.goal_tables = None     # tree key of a group goal -> (key patterns of the last fill, their device table)
         # fields that are the direct argument of a groupby axis may hold strings: dictionary-encoded on the host
         self.groupby_fields = {}    # field name -> tree key of the groupby goal
         for h in self.spec["hists"]:
@@ -68,15 +72,16 @@ class Plan(object):
     def kernel_for(self, cols, dense=False):
         """The kernels for these column dtypes.  ``dense`` selects the second variant of a hot-window kernel (see
         fill_hists): part of the window's float64 terms in fixed point, plain REDs for the few events outside."""
-        if self.generation != Plan.generation:
-            self.kernels.clear()
-            self.generation = Plan.generation
+        self._fresh()
         sig = tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields) + (("dense",) if dense else ())
         if sig not in self.kernels:
             coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in self.fields)
-            options = dict(_options, win_dense=True) if dense else _options
+            options = dict(_options, **self.options)
+            if dense:
+                options["win_dense"] = True
             kern = codegen.generate(self.spec, coltypes, options)
-            prog = engine.Program(engine.compile_source(kern.source), kern.name, kern.threads, kern.smem_bytes, tile=kern.tile)
+            prog = engine.Program(engine.compile_source(kern.source), kern.name, kern.threads, kern.smem_bytes, tile=kern.tile,
+                                  max_blocks_per_sm=int(options.get("max_blocks_per_sm", 0)))
             keys = codegen.generate_keys(self.spec, coltypes, options)
             kprog = None
             if keys is not None:
@@ -88,7 +93,68 @@ class Plan(object):
             self.kernels[sig] = (kern, prog, keys, kprog, rng, rprog)
         return sig, self.kernels[sig]
 
+    def _fresh(self):
+        if self.generation != Plan.generation:
+            self.kernels.clear()
+            self.parts.clear()
+            self.discovery.clear()
+            self.generation = Plan.generation
 
+    def parts_for(self, cols):
+        """None, or the parts this book is filled in: [(Plan, histogram indices)].  A book is split
+        * when it has more histograms than one kernel's parameter block takes (each part at most PART_MAX_HISTS), or
+        * when it is a big book with at least ``parts_min_groups`` sort groups: two half-books, each one 512-thread block
+          per SM with its own tiles, so that on every SM one half's arithmetic (evaluate, index, tickets) overlaps the
+          other half's shared-memory traffic (the sums over the sorted events) -- one 1024-thread block runs the two
+          phases one after the other with the block waiting at every barrier (profiles/r02_c4_ncu.txt).
+        All parts are filled in ONE pass over the columns (engine.fill_multi)."""
+        self._fresh()
+        sig = tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields)
+        if sig not in self.parts:
+            options = dict(_options, **self.options)
+            want = options.get("parts", "auto")
+            k, extra = 1, {}
+            if self.options.get("_part") or want in (1, False) or options.get("deterministic", False):
+                k = 1
+            elif self.nhists > PART_MAX_HISTS:
+                k = -(-self.nhists // PART_MAX_HISTS)
+            if k == 1 and not self.options.get("_part") and want not in (1, False) and not options.get("deterministic", False):
+                coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in self.fields)
+                try:
+                    kern = codegen.generate(self.spec, coltypes, options)
+                except codegen.UnsupportedError:
+                    kern = None
+                if kern is not None and kern.sorted and len(kern.sorted["groups"]) >= int(options.get("parts_min_groups", 4)):
+                    k = int(want) if want != "auto" else 2
+                    extra = {"sort_threads": 512, "sort_min_blocks": 2, "max_blocks_per_sm": 1, "sort": True}
+            if k <= 1:
+                self.parts[sig] = None
+            else:
+                n = self.nhists
+                bounds = [n * i // k for i in range(k + 1)]
+                parts = []
+                for a, b in zip(bounds, bounds[1:]):
+                    sub = dict(self.spec, hists=self.spec["hists"][a:b])
+                    parts.append((Plan(spec=sub, options=dict(self.options, _part=True, **extra)), list(range(a, b))))
+                self.parts[sig] = parts
+        return self.parts[sig]
+
+    def discovery_for(self, cols):
+        """The key-discovery kernel of the whole book (one pass, whatever the number of parts)."""
+        self._fresh()
+        sig = tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields)
+        if sig not in self.discovery:
+            coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in self.fields)
+            keys = codegen.generate_keys(self.spec, coltypes, dict(_options, **self.options))
+            kprog = None
+            if keys is not None:
+                kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, 0)
+            self.discovery[sig] = (keys, kprog)
+        return self.discovery[sig]
+
+
+PART_MAX_HISTS = 96             # histograms per kernel of a split book (HbParams holds 128 arena pointers)
+MAX_GROUP_KEYS = 1 << 22        # distinct keys of one group axis in one fill (the discovery table grows up to twice this)
 PILOT_EVENTS = 1 << 20          # events filled through the global path before the hot window is placed
 FX_MISS_REPILOT = 0.01          # re-run the fixed-point pilot when more than this fraction of the events missed
 FX_CHECK_FILLS = 64             # ... checked after this many fills
@@ -222,11 +288,132 @@ def _store_of(hist):
     return st
 
 
+def _discover(plan, keys, kprog, cols, length):
+    """Keys every group goal takes in this fill: {tree key of the goal: (64-bit patterns, info)} (numpy.unique in
+    calc/__init__.py:150,178,182).  One small kernel over the group columns + one device hash set per goal; a set that
+    fills beyond one half is replaced by one four times the size and the pass repeated."""
+    discovered = {}
+    if keys is None:
+        return discovered
+    if plan.keysets is None or len(plan.keysets) != len(keys.group_goals):
+        plan.keysets = [engine.KeySet(1 << 12) for _ in keys.group_goals]
+    while True:
+        for ks in plan.keysets:
+            ks.clear()
+        if length > 0:
+            engine.fill(kprog, _abi_columns(keys, cols), length, [], aux=[ks.ptr for ks in plan.keysets])
+        grown = False
+        for i, ((goalkey, info), ks) in enumerate(zip(keys.group_goals, plan.keysets)):
+            patterns, overflowed = ks.read()
+            if overflowed or 2 * len(patterns) > ks.capacity:
+                # numpy.unique has no limit: a fuller table means longer probes, a full one lost keys -- take a
+                # table four times the size and run the discovery again (load factor at most 1/2 when accepted)
+                if ks.capacity >= MAX_GROUP_KEYS * 2:
+                    raise codegen.UnsupportedError("a group axis produced more than {0} distinct keys in one fill".format(MAX_GROUP_KEYS))
+                plan.keysets[i] = engine.KeySet(ks.capacity * 4)
+                grown = True
+            discovered[goalkey] = (patterns, info)
+        if not grown:
+            return discovered
+
+
+def _bind_stores(plan, kern, hists, discovered):
+    """The stores of ``hists`` made current on the device, group keys of this fill admitted; returns (stores, aux
+    pointers of the kernel's group tables: per goal the fill's keys, per group histogram its dense slot map)."""
+    aux = [0] * (len(kern.group_aux) + len(kern.goal_aux))
+    if kern.goal_aux:
+        # per group goal: [number of keys, 0, this fill's keys as ascending unsigned 64-bit patterns] (codegen._goal_lookup)
+        if plan.goal_tables is None:
+            plan.goal_tables = {}
+        for goalkey, slot in kern.goal_aux.items():
+            patterns = tuple(sorted(int(x) for x in discovered[goalkey][0]))
+            cached = plan.goal_tables.get(goalkey)
+            if cached is None or cached[0] != patterns:
+                cached = plan.goal_tables[goalkey] = (patterns, engine.DeviceBuffer(numpy.array((len(patterns), 0) + patterns, dtype=numpy.uint64)))
+            aux[slot] = cached[1].ptr
+    stores = []
+    for hid, (hist, hspec) in enumerate(zip(hists, plan.spec["hists"])):
+        st = _store_of(hist)
+        if hist.__dict__.get("_copyonfill", False):       # hist.py:351-353
+            st = hist.__dict__["_hb"] = _clone_store(st)
+            hist.__dict__["_copyonfill"] = False
+        if hspec["group"]:
+            infos = []
+            fill_keys = []
+            for a in hspec["group"]:
+                goalkey = hbspec.tree_key(a["goal"])
+                patterns, info = discovered[goalkey]
+                codes = None
+                for field, gk in plan.groupby_fields.items():
+                    if gk == goalkey and field in plan.string_codes:
+                        codes = plan.string_codes[field]
+                infos.append(GroupInfo(a["kind"], a["keeporder"], info["kind"] == "f", info["dtype"], info["nanflow"], goalkey, codes))
+                fill_keys.append([int(x) for x in patterns])
+            st.groups = infos
+            st.to_device()
+            st.admit(fill_keys)
+            aux[kern.group_aux[hid]] = st.table[1].ptr
+        else:
+            st.to_device()
+        stores.append(st)
+    return stores, aux
+
+
+def _fill_parts(plan, parts, hists, cols, length, timed):
+    """A split book (Plan.parts_for): one discovery pass, one pass over the columns, one kernel per part and chunk."""
+    on_device = [c for c in cols.values() if c.location == 1]
+    if on_device:
+        dev = engine.init()
+        for c in on_device:
+            if c.device is not None and c.device != dev:
+                raise codegen.UnsupportedError("field {0!r} lives on cuda:{1} but this process fills on cuda:{2} (one process per GPU)".format(c.name, c.device, dev))
+            if c.stream is not None:
+                engine.stream_wait(0, c.stream)
+    side = engine.producer_stream() if length > 0 and on_device else 0
+    if side:
+        engine.stream_wait(0, side)
+    keys, kprog = plan.discovery_for(cols)
+    discovered = _discover(plan, keys, kprog, cols, length)
+    order = list(plan.fields)
+    launches, finals, all_stores, kerns = [], [], [], []
+    for sub, idx in parts:
+        sub.string_codes, sub.groupby_fields = plan.string_codes, plan.groupby_fields
+        sig, (kern, prog, _k, _kp, rng, rprog) = sub.kernel_for(cols)
+        if kern.window is not None:
+            raise codegen.UnsupportedError("a part of a split book wants a hot window")       # (windows are for single large histograms)
+        stores, aux = _bind_stores(sub, kern, [hists[i] for i in idx], discovered)
+        aux = aux + [0] * (kern.naux - len(aux))
+        fx = []
+        if kern.fx_terms:
+            fx = _fx_scales(sub, sig, kern, rng, rprog, cols, length)
+            aux[kern.fx_aux] = sub.fx_stat.ptr
+        launches.append({"program": prog, "colmap": [order.index(name) for name, dtype, is_scalar in kern.cols],
+                         "arenas": [st.arena for st in stores], "aux": aux, "win": [0, 0] + fx, "exact": None})
+        all_stores.extend(stores)
+        kerns.append((kern, prog))
+    stats = {"events": length, "launches": 0}
+    if length > 0:
+        stats = engine.fill_multi(launches, [cols[name].abi() for name in order], length, timed=timed)
+    if side:
+        engine.stream_wait(side, 0)
+    for st in all_stores:
+        st.mark_filled()
+    kern, prog = kerns[0]
+    stats.update({"deterministic": False, "sorted": kern.sorted, "regs": prog.regs, "smem_bytes": kern.smem_bytes, "parts": len(parts),
+                  "keys_launches": 1 if (keys is not None and length > 0) else 0})
+    last_stats.clear()
+    last_stats.update(stats)
+    return length
+
+
 def fill_hists(plan, hists, arrays, timed=False):
     """One pass over ``arrays`` filling every histogram in ``hists`` (deduplicated, in plan order)."""
     with _lock:
         arrays = _encode_strings(plan, arrays)
         cols, length = columns.bind_all(plan.fields, arrays)
+        parts = plan.parts_for(cols)
+        if parts is not None:
+            return _fill_parts(plan, parts, hists, cols, length, timed)
         sig, (kern, prog, keys, kprog, rng, rprog) = plan.kernel_for(cols)
         # device columns produced on another stream (torch's current one): CUDA does not order a non-blocking stream
         # with the engine's, so the fill waits for the producer here and the producer for the fill at the end
@@ -243,46 +430,9 @@ def fill_hists(plan, hists, arrays, timed=False):
             engine.stream_wait(0, side)
 
         # group axes: which keys does this fill hold?  (numpy.unique in calc/__init__.py:150,178,182)
-        discovered = {}
-        if keys is not None:
-            if plan.keysets is None or len(plan.keysets) != len(keys.group_goals):
-                plan.keysets = [engine.KeySet(1 << 12) for _ in keys.group_goals]
-            for ks in plan.keysets:
-                ks.clear()
-            if length > 0:
-                engine.fill(kprog, _abi_columns(keys, cols), length, [], aux=[ks.ptr for ks in plan.keysets])
-            for (goalkey, info), ks in zip(keys.group_goals, plan.keysets):
-                patterns, overflowed = ks.read()
-                if overflowed:
-                    raise codegen.UnsupportedError("a group axis produced more than {0} distinct keys in one fill".format(ks.capacity // 2))
-                discovered[goalkey] = (patterns, info)
+        discovered = _discover(plan, keys, kprog, cols, length)
 
-        stores = []
-        aux = [0] * len(kern.group_aux)
-        for hid, (hist, hspec) in enumerate(zip(hists, plan.spec["hists"])):
-            st = _store_of(hist)
-            if hist.__dict__.get("_copyonfill", False):       # hist.py:351-353
-                st = hist.__dict__["_hb"] = _clone_store(st)
-                hist.__dict__["_copyonfill"] = False
-            if hspec["group"]:
-                infos = []
-                fill_keys = []
-                for a in hspec["group"]:
-                    goalkey = hbspec.tree_key(a["goal"])
-                    patterns, info = discovered[goalkey]
-                    codes = None
-                    for field, gk in plan.groupby_fields.items():
-                        if gk == goalkey and field in plan.string_codes:
-                            codes = plan.string_codes[field]
-                    infos.append(GroupInfo(a["kind"], a["keeporder"], info["kind"] == "f", info["dtype"], info["nanflow"], goalkey, codes))
-                    fill_keys.append([int(x) for x in patterns])
-                st.groups = infos
-                st.to_device()
-                st.admit(fill_keys)
-                aux[kern.group_aux[hid]] = st.table.ptr
-            else:
-                st.to_device()
-            stores.append(st)
+        stores, aux = _bind_stores(plan, kern, hists, discovered)
 
         stats = {"events": length, "launches": 0}
         used = (sig, kern, prog, rng, rprog)

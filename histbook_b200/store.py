@@ -100,8 +100,7 @@ class Store(object):
         # group bookkeeping (device side)
         self.tuples = collections.OrderedDict()      # tuple(patterns) -> slot
         self.skeleton = None                          # nested OrderedDict pattern -> ... -> slot, reference insertion order
-        self.table = None                             # engine.DeviceBuffer with the lookup table of the last fill
-        self.table_version = None
+        self.table = None                             # (fill key lists, engine.DeviceBuffer): dense slot map of the last fill's key combinations
         # hot-window privatisation (fillable.choose_window): None = not placed yet, False = not worth it
         self.window = None            # {"table": DeviceBuffer, "bins", "rows"}
         self.window_key = None        # (rows, trail, wmax) of the kernel the window was placed for
@@ -229,31 +228,20 @@ class Store(object):
         if self.arena.size < need:
             grow = max(need, 2 * self.arena.size)
             self.arena.resize(grow)
-        if len(self.tuples) != before or self.table is None:
-            self._build_table()
+        self._slot_map(ordered)
 
-    def _build_table(self):
-        """Lookup table for hb_template.cuh hb_key_find / _group_lookup:
-        [K][n_0..n_{K-1}][off_0..off_{K-1}][off_slotmap] then per-axis ascending key patterns, then the dense slot map."""
-        K = len(self.groups)
-        axes = []
-        for a in range(K):
-            axes.append(sorted(set(t[a] for t in self.tuples)))
+    def _slot_map(self, ordered):
+        """Dense map for the fill kernel (codegen._group_lookup): position of the event's key on every axis among THIS
+        fill's keys (ascending unsigned patterns, the order of the goal tables fillable.fill_hists uploads) -> slab
+        slot.  ``ordered`` is the per-axis key lists in any order; rebuilt only when the fill's key lists change."""
+        axes = tuple(tuple(sorted(set(int(p) for p in keys))) for keys in ordered)
+        if self.table is not None and self.table[0] == axes:
+            return
         sizes = [len(x) for x in axes]
-        words = [K] + sizes + [0] * K + [0]
-        off = len(words)
-        for a in range(K):
-            words[1 + K + a] = off
-            words.extend(axes[a])
-            off += sizes[a]
-        words[1 + 2 * K] = off
-        total = int(numpy.prod(sizes, dtype=numpy.int64)) if K else 0
-        slotmap = numpy.full(max(total, 1), -1, dtype=numpy.int64)
-        index = [dict((p, i) for i, p in enumerate(x)) for x in axes]
-        for t, slot in self.tuples.items():
-            comb = 0
-            for a in range(K):
-                comb = comb * sizes[a] + index[a][t[a]]
-            slotmap[comb] = slot
-        table = numpy.concatenate([numpy.array(words, dtype=numpy.uint64), slotmap.view(numpy.uint64)])
-        self.table = engine.DeviceBuffer(table)
+        total = int(numpy.prod(sizes, dtype=numpy.int64)) if sizes else 0
+        slotmap = numpy.full(max(total, 1), -1, dtype=numpy.int32)
+        if total:
+            import itertools
+            for comb, tup in enumerate(itertools.product(*axes)):
+                slotmap[comb] = self.tuples[tup]
+        self.table = (axes, engine.DeviceBuffer(slotmap))

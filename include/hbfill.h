@@ -99,6 +99,9 @@ int hb_program_destroy(hb_program* prog);
 /* events one block handles per round of the kernel's grid-stride loop (default 4 x threads; the sorted-book kernels
  * of codegen.py use HB_EPT x threads): hb_fill sizes the grid with it */
 int hb_program_set_tile(hb_program* prog, int tile_events);
+/* size the grid for at most `blocks` resident blocks per SM (0 = as many as fit): the parts of a book that was split
+ * into several programs share the SMs (hb_fill_multi) */
+int hb_program_set_max_blocks_per_sm(hb_program* prog, int blocks);
 int hb_program_info(const hb_program* prog, int* regs, int* static_smem, int* blocks_per_sm);
 void hb_free(void* p);
 
@@ -126,6 +129,29 @@ int64_t hb_arena_size(const hb_arena* a);
 int hb_fill(hb_program* prog, int ncols, const hb_column* cols, int64_t n,
             int nhists, hb_arena* const* hists, int naux, const void* const* aux,
             int nwin, const int32_t* win, int flags, hb_stats* stats);
+
+/* A book split into several programs ("parts": more histograms than one kernel's parameter block or shared memory
+ * holds, or -- big books -- two half-books whose kernels share every SM so that one's arithmetic overlaps the other's
+ * shared-memory traffic): ONE pass over the host columns (every chunk is staged once), every part's kernel launched
+ * on its own stream per chunk, all joined on the compute stream.  Stands in for the single loop over all histograms
+ * of Book.fill (histbook/book.py:566-586).  `cols` is the union of the parts' columns; colmap[i] = index in `cols`
+ * of the part's column slot i (NULL: identity). */
+typedef struct {
+    hb_program* prog;
+    int32_t ncols;
+    const int32_t* colmap;
+    int32_t nhists;
+    hb_arena* const* hists;
+    hb_arena* const* exact;       /* deterministic mode (see hb_fill_exact), or NULL */
+    int32_t naux;
+    const void* const* aux;
+    int32_t nwin;
+    const int32_t* win;
+} hb_launch;
+int hb_fill_multi(int nlaunch, const hb_launch* launches, int ncols, const hb_column* cols, int64_t n, int flags, hb_stats* stats);
+/* worker threads that copy pageable host columns into the page-locked bounce ring (default: min(8, cores / 2);
+ * environment HB_COPY_THREADS) */
+int hb_set_copy_threads(int n);
 
 /* Deterministic mode.  hb_fill_exact is hb_fill with, per histogram, a second arena (`exact[h]`, may be NULL) that
  * holds two 192-bit fixed-point accumulators (upper and lower exponent window, 2 x 3 64-bit words) per (row, float64 slot): kernels generated with the
