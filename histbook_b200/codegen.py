@@ -433,16 +433,28 @@ class Program(object):
                 cmp_t = numpy.dtype(numpy.float64)      # float32 -> float64 is exact, comparisons are unchanged
             else:
                 raise UnsupportedError("split axis comparing in {0}".format(common))
-            cname = self.new("hb_edges")
             bits = numpy.array(edges).astype(cmp_t).view(numpy.int64)
-            self.consts.append("__constant__ hb_i64 %s[%d] = {%s};" % (
-                cname, len(edges), ", ".join(("%dLL" % b) if b != -2**63 else "(-9223372036854775807LL - 1)" for b in bits.tolist())))
             name, ok = self.new("i"), self.new("ok")
             isnan = "(%s != %s)" % (v.c, v.c) if v.dtype.kind == "f" else "false"
+            flags = ", ".join("true" if c != "_" and c != "H" else "false" for c in f)
             self.body.append("bool %s = true;" % ok)
-            self.body.append("const int %s = hb_split_axis<%s, %s>(%s, %s, %s, %d, %s);" % (
-                name, ctype(cmp_t), ", ".join("true" if c != "_" and c != "H" else "false" for c in f),
-                self.cast(v, cmp_t), isnan, cname, len(edges), ok))
+            if len(edges) <= 16:
+                # few edges: the count of edges <= v as a chain of compares against literals -- the edges sit in the
+                # instruction stream / literal pool, no indexed constant loads (which go through the MIO queue: 7 % of the
+                # c4 kernel's stall samples with the bisection over a __constant__ array, profiles/r02_c4_ncu.txt)
+                vv = self.new("sv")
+                self.body.append("const %s %s = %s;" % (ctype(cmp_t), vv, self.cast(v, cmp_t)))
+                lits = [lit(e, cmp_t) for e in numpy.array(edges).astype(cmp_t).tolist()]
+                count = " + ".join("(int)(%s <= %s)" % (e, vv) for e in lits)
+                onedge = " || ".join("(%s == %s)" % (e, vv) for e in lits)
+                self.body.append("const int %s = hb_split_index<%s>(%s, %s, %s, %d, %s);" % (
+                    name, flags, count, ("(%s)" % onedge) if f[3] in "_H" else "false", isnan, len(edges), ok))
+            else:
+                cname = self.new("hb_edges")
+                self.consts.append("__constant__ hb_i64 %s[%d] = {%s};" % (
+                    cname, len(edges), ", ".join(("%dLL" % b) if b != -2**63 else "(-9223372036854775807LL - 1)" for b in bits.tolist())))
+                self.body.append("const int %s = hb_split_axis<%s, %s>(%s, %s, %s, %d, %s);" % (
+                    name, ctype(cmp_t), flags, self.cast(v, cmp_t), isnan, cname, len(edges), ok))
             return Value(name, numpy.int32, kind="index", extra=ok)
 
         if fcn == "histbook.cut":
@@ -1322,6 +1334,9 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % int(options.get("sort_min_blocks", 1)))
     src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
     src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (layout["zero_end"] // 4))
+    if int(options.get("sort_stagger_us", 0)) > 0:
+        # two blocks share an SM: the second starts late, so that its phases fall between the first one's
+        src.append("    if (blockIdx.x >= (gridDim.x + 1) / 2 || (p.flags & 2)) { for (int i = 0; i < %d; ++i) __nanosleep(1000); }" % int(options["sort_stagger_us"]))
     src.append("    __syncthreads();")
     for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
         if is_scalar:
@@ -1332,16 +1347,18 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("        const hb_i64 first = tile * HB_TILE;")
     for k in range(ept):
         src.append("        hb_u32 kr%d[HB_NSG];" % k)
-    src.append("        // 1. evaluate, stage, draw tickets")
+    src.append("        // 1. evaluate, stage, draw tickets (the columns of all HB_EPT events are loaded first: their latencies overlap)")
     for k in range(ept):
-        src.append("        {")
-        src.append("            const hb_i64 i = first + %d * HB_THREADS + threadIdx.x;" % k)
-        src.append("            const bool live = i < p.n;")
-        src.append("            const hb_i64 j = live ? i : 0;")
-        src.append("            hb_event(p, hb_smem, live, %d * HB_THREADS + (int)threadIdx.x, kr%d%s);" % (k, k, "".join(
-            ", " + _colarg(slot, dtype, is_scalar, "hb_load1<%s>(p.cols[%d], j)" % (_loadtype(dtype), slot))
+        src.append("        const hb_i64 i%d = first + %d * HB_THREADS + threadIdx.x;" % (k, k))
+        src.append("        const bool live%d = i%d < p.n;" % (k, k))
+        src.append("        const hb_i64 j%d = live%d ? i%d : 0;" % (k, k, k))
+        for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+            if not is_scalar:
+                src.append("        const %s ld%d_%d = hb_load1<%s>(p.cols[%d], j%d);" % (_loadtype(dtype), k, slot, _loadtype(dtype), slot, k))
+    for k in range(ept):
+        src.append("        hb_event(p, hb_smem, live%d, %d * HB_THREADS + (int)threadIdx.x, kr%d%s);" % (k, k, k, "".join(
+            ", " + _colarg(slot, dtype, is_scalar, "ld%d_%d" % (k, slot))
             for slot, (name, dtype, is_scalar) in enumerate(prog.cols))))
-        src.append("        }")
     src.append("        __syncthreads();")
     src.append("        // 2. bin counters -> bin start offsets (one warp per group)")
     for g in groups:
@@ -1915,11 +1932,12 @@ def generate_keys(spec, coltypes, options=None):
         cond = "if (live) "
         if g.dtype.kind == "f" and not g.extra["nanflow"]:
             cond = "if (live && !(%s != %s)) " % (g.c, g.c)
-        ev.append("%shb_keyset_insert(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), hb_keybits(%s));" % (cond, j, g.c))
+        ev.append("%shb_keyset_insert_cached(reinterpret_cast<hb_u64*>(const_cast<void*>(p.aux[%d])), hb_keybits(%s), reinterpret_cast<hb_u64*>(hb_smem) + %d);" % (cond, j, g.c, 256 * j))
         infos.append(dict(g.extra, kind="f" if g.dtype.kind == "f" else "i"))
     threads = int(options.get("threads", THREADS))
     k = Kernel()
-    k.source = _emit_kernel(prog, ev, 0, [], threads, 2)
+    k.smem_bytes = 2048 * len(goals)                   # hb_keyset_insert_cached: 256 filter entries per goal
+    k.source = _emit_kernel(prog, ev, k.smem_bytes, [], threads, 2)
     k.cols = list(prog.cols)
     k.threads = threads
     k.tile = threads * VEC

@@ -309,6 +309,9 @@ extern "C" int hb_program_load(const void* cubin, size_t cubin_size, const char*
         r = g_drv.FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_bytes);
         if (r != CUDA_SUCCESS) { g_drv.ModuleUnload(p->module); delete p; return fail(HB_ERR_CUDA, "cuFuncSetAttribute(smem): " + drv_err(r)); }
     }
+    // the whole unified L1 as shared memory: every kernel here streams its inputs past L1 (ld.global.nc.L1::no_allocate) and
+    // lives in shared memory; and the two half-book kernels of a split book only share an SM if the carve-out holds both
+    g_drv.FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
     g_drv.FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn);
     g_drv.FuncGetAttribute(&p->static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn);
     int occ = 0;
@@ -769,7 +772,10 @@ extern "C" int hb_fill_multi(int nlaunch, const hb_launch* L, int ncols, const h
         while (a) { int r = g % a; g = a; a = r; }
         tile = tile / g * t;
     }
-    const bool multi = nlaunch > 1;
+    // Parts run one after the other on the compute stream unless HB_FILL_CONCURRENT asks for a stream each.  (Measured on
+    // c4's two half-books, kernels only, 1e8 events: side by side with one block per SM each 10.0 ms; one after the other with
+    // two blocks per SM each 8.3 ms; the whole book as one 1024-thread kernel 9.4 ms -- tools/parts_probe.py.)
+    const bool multi = nlaunch > 1 && (flags & HB_FILL_CONCURRENT) != 0;
     if (multi) {
         if (!g_fork) CUDA_TRY(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
         for (int l = 0; l < nlaunch; ++l) {

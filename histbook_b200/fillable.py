@@ -85,7 +85,7 @@ class Plan(object):
             keys = codegen.generate_keys(self.spec, coltypes, options)
             kprog = None
             if keys is not None:
-                kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, 0)
+                kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, keys.smem_bytes)
             rng = rprog = None
             if kern.fx_terms:
                 rng = codegen.generate_range(self.spec, coltypes, options)
@@ -103,11 +103,12 @@ class Plan(object):
     def parts_for(self, cols):
         """None, or the parts this book is filled in: [(Plan, histogram indices)].  A book is split
         * when it has more histograms than one kernel's parameter block takes (each part at most PART_MAX_HISTS), or
-        * when it is a big book with at least ``parts_min_groups`` sort groups: two half-books, each one 512-thread block
-          per SM with its own tiles, so that on every SM one half's arithmetic (evaluate, index, tickets) overlaps the
-          other half's shared-memory traffic (the sums over the sorted events) -- one 1024-thread block runs the two
-          phases one after the other with the block waiting at every barrier (profiles/r02_c4_ncu.txt).
-        All parts are filled in ONE pass over the columns (engine.fill_multi)."""
+        * when it is a big book with at least ``parts_min_groups`` sort groups: two half-books, each filled by 512-thread
+          blocks, two per SM with their own tiles, so that one block's arithmetic (evaluate, index, tickets) overlaps the
+          other's shared-memory traffic (the sums over the sorted events) -- one 1024-thread block runs its phases one
+          after the other and waits at every barrier (kernels only, 1e8 events: 9.4 ms whole, 2 x 4.15 ms in halves;
+          tools/parts_probe.py).
+        All parts are filled in ONE pass over the columns (engine.fill_multi): every chunk is staged once."""
         self._fresh()
         sig = tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields)
         if sig not in self.parts:
@@ -126,7 +127,7 @@ class Plan(object):
                     kern = None
                 if kern is not None and kern.sorted and len(kern.sorted["groups"]) >= int(options.get("parts_min_groups", 4)):
                     k = int(want) if want != "auto" else 2
-                    extra = {"sort_threads": 512, "sort_min_blocks": 2, "max_blocks_per_sm": 1, "sort": True}
+                    extra = {"sort_threads": 512, "sort_min_blocks": 2, "sort": True}
             if k <= 1:
                 self.parts[sig] = None
             else:
@@ -148,7 +149,7 @@ class Plan(object):
             keys = codegen.generate_keys(self.spec, coltypes, dict(_options, **self.options))
             kprog = None
             if keys is not None:
-                kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, 0)
+                kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, keys.smem_bytes)
             self.discovery[sig] = (keys, kprog)
         return self.discovery[sig]
 
@@ -329,7 +330,7 @@ def _bind_stores(plan, kern, hists, discovered):
             patterns = tuple(sorted(int(x) for x in discovered[goalkey][0]))
             cached = plan.goal_tables.get(goalkey)
             if cached is None or cached[0] != patterns:
-                cached = plan.goal_tables[goalkey] = (patterns, engine.DeviceBuffer(numpy.array((len(patterns), 0) + patterns, dtype=numpy.uint64)))
+                cached = plan.goal_tables[goalkey] = (patterns, engine.DeviceBuffer(numpy.array((len(patterns), 0) + patterns + (0,) * max(0, 8 - len(patterns)), dtype=numpy.uint64)))
             aux[slot] = cached[1].ptr
     stores = []
     for hid, (hist, hspec) in enumerate(zip(hists, plan.spec["hists"])):

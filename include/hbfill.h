@@ -73,6 +73,7 @@ typedef struct {
 } hb_stats;
 
 #define HB_FILL_TIMED 1     /* bracket the launches with CUDA events and synchronise (fills hb_stats.ms_kernel) */
+#define HB_FILL_CONCURRENT 4   /* hb_fill_multi: one stream per part instead of one launch after the other */
 
 const char* hb_last_error(void);
 int hb_version(void);
