@@ -279,6 +279,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     engine.init(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # (a bare "NCCL version ..." line on stdout is not part of the one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = torch.device("cuda", local)
     hbm, hbm_src = peaks()

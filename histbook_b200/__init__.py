@@ -183,10 +183,55 @@ def _same_axes(self, other):
         raise TypeError("histograms can only be added to other histograms with the same axis specifications")
 
 
+def _group_stores(self, other):
+    """Both stores when the two histograms have group axes, live on the device and spell their keys alike (same key
+    types; string keys from the same dictionary), else None."""
+    a, b = self.__dict__.get("_hb"), other.__dict__.get("_hb")
+    for st in (a, b):
+        if st is None or not st.groups or st.host_valid or not st.dev_valid or st.arena is None:
+            return None
+    if len(a.groups) != len(b.groups) or a.blocksize != b.blocksize:
+        return None
+    for g, h in zip(a.groups, b.groups):
+        if g.floatkey != h.floatkey or g.dtype != h.dtype or g.codes is not h.codes or g.kind != h.kind:
+            return None
+    return a, b
+
+
+def _group_axpy(a, b, inplace):
+    """Slab of ``a`` plus slab of ``b`` on the device, keys united the way the reference's recursion does it
+    (histbook/hist.py:513-537: keys of ``a`` keep their places, new keys of ``b`` follow in b's order)."""
+    from histbook_b200.store import Store
+    order = list(a.tuples) + [t for t in b.tuples if t not in a.tuples]
+    bs = a.blocksize
+    if inplace:
+        out = a
+    else:
+        out = Store(a.shape, a.groups, None)
+        out.arena = a.arena.clone()
+        out.host, out.host_valid, out.dev_valid, out.nonempty = None, False, True, True
+    need = max(len(order), 1) * bs
+    if out.arena.size < need:
+        out.arena.resize(need)
+    where = dict((t, i) for i, t in enumerate(order))
+    for t, slot in b.tuples.items():
+        out.arena.axpy_at(where[t] * bs, b.arena, slot * bs, bs, 1.0)
+    out.set_tuples(order)
+    return out
+
+
 def _hist_add(self, other):
-    """``Hist.__add__`` (histbook/hist.py:506-542).  Two device-resident histograms without group axes add on the device
-    (hb_arena_axpy, one IEEE add per bin like numpy's ``+``); anything else takes the reference's path on host copies."""
+    """``Hist.__add__`` (histbook/hist.py:506-542).  Two device-resident histograms add on the device (hb_arena_axpy, one
+    IEEE add per bin like numpy's ``+``; with group axes slot by slot after uniting the keys); anything else takes the
+    reference's path on host copies."""
     _same_axes(self, other)
+    pair = _group_stores(self, other)
+    if pair is not None:
+        out = self.__class__.__new__(self.__class__)
+        out.__dict__.update(self.__dict__)
+        out.__dict__["_hb"] = _group_axpy(pair[0], pair[1], False)
+        out.__dict__.pop("_hb_plan", None)
+        return out
     a, b = _device_store(self), _device_store(other)
     if a is None or b is None:
         return _originals["Hist.__add__"](self, other)
@@ -201,6 +246,10 @@ def _hist_add(self, other):
 def _hist_iadd(self, other):
     """``Hist.__iadd__`` (histbook/hist.py:544-575)."""
     _same_axes(self, other)
+    pair = _group_stores(self, other)
+    if pair is not None:
+        _group_axpy(pair[0], pair[1], True)
+        return self
     a, b = _device_store(self), _device_store(other)
     if a is None or b is None:
         return _originals["Hist.__iadd__"](self, other)
@@ -235,6 +284,38 @@ def _hist_imul(self, value):
     return self
 
 
+# ----------------------------------------------------------------------------- serialisation (histbook/hist.py:700-741, book.py:180-198)
+
+def _hist_tojson(self):
+    """``Hist.tojson`` (histbook/hist.py:700-720) reading the bins through ``peek``: the device copy stays the
+    authoritative one (a plain ``_content`` read hands the host copy to the caller, who may mutate it, so the next
+    fill would upload it again), and large contents come over through page-locked staging (hb_arena_read)."""
+    st = self.__dict__.get("_hb")
+    if st is None or st.host_valid:
+        return _originals["Hist.tojson"](self)
+    real = self.__dict__["_hb"]
+    from histbook_b200.store import Store
+    try:
+        self.__dict__["_hb"] = Store(self._shape, [], st.peek())      # a throw-away host view for the reference's own code
+        return _originals["Hist.tojson"](self)
+    finally:
+        self.__dict__["_hb"] = real
+
+
+def _hist_getstate(self):
+    """``Hist.__getstate__`` (histbook/hist.py:732-734), same arrangement: pickling does not disturb the device copy."""
+    st = self.__dict__.get("_hb")
+    if st is None or st.host_valid:
+        return _originals["Hist.__getstate__"](self)
+    real = self.__dict__["_hb"]
+    from histbook_b200.store import Store
+    try:
+        self.__dict__["_hb"] = Store(self._shape, [], st.peek())
+        return _originals["Hist.__getstate__"](self)
+    finally:
+        self.__dict__["_hb"] = real
+
+
 # ----------------------------------------------------------------------------- install / uninstall
 
 def install():
@@ -250,6 +331,7 @@ def install():
         "Hist.cleared": Hist.__dict__["cleared"], "Hist.project": hb.proj.Projectable.__dict__["project"],
         "Hist.__add__": Hist.__dict__["__add__"], "Hist.__iadd__": Hist.__dict__["__iadd__"],
         "Hist.__mul__": Hist.__dict__["__mul__"], "Hist.__imul__": Hist.__dict__["__imul__"],
+        "Hist.tojson": Hist.__dict__["tojson"], "Hist.__getstate__": Hist.__dict__["__getstate__"],
     })
     Hist._content = property(_content_get, _content_set)
     Hist.fill = _hist_fill
@@ -258,6 +340,7 @@ def install():
     Hist.copyonfill = _hist_copyonfill
     Hist.project = _hist_project
     Hist.__add__, Hist.__iadd__, Hist.__mul__, Hist.__imul__ = _hist_add, _hist_iadd, _hist_mul, _hist_imul
+    Hist.tojson, Hist.__getstate__ = _hist_tojson, _hist_getstate
     _installed = True
 
 
@@ -275,7 +358,7 @@ def uninstall():
     Hist.copy = _originals["Hist.copy"]
     Hist.copyonfill = _originals["Hist.copyonfill"]
     del Hist.project                      # falls back to the inherited Projectable.project
-    for name in ("__add__", "__iadd__", "__mul__", "__imul__"):
+    for name in ("__add__", "__iadd__", "__mul__", "__imul__", "tojson", "__getstate__"):
         setattr(Hist, name, _originals["Hist." + name])
     _installed = False
 

@@ -520,6 +520,7 @@ class HistPlan(object):
         self.win_off = None        # "window" strategy: byte offset of the runtime-sized hot window region
         self.win_table_off = None  # byte offset of the per-row interval table (8 bytes per row)
         self.win_split = None      # the first `win_split` fixed axes form the row index, the rest the in-row index
+        self.win_box = False       # the window is a box [lo_k, lo_k + n_k) on every fixed axis (run-time parameters p.win[...]) instead of per-row intervals
         self.gcap = 0              # group histograms: slab slots [0, gcap) are privatised in shared memory
         self.replicas = 1          # statically privatised copies per block (lane & (replicas - 1) picks one): fewer same-bin lanes per atomic
         self.skip_zero = False     # filter-derived weight: rows whose every term is exactly 0.0 are not accumulated
@@ -951,6 +952,21 @@ def choose_strategies(plans, options, prog=None, layout=None):
             window.win_table_off = used
             used += (window.win_rows * 8 + 15) // 16 * 16
             window.win_off = used
+        elif options.get("box", True) and not det:
+            # Histograms beyond that (c5: 203^3 x 2 float64 = 134 MB): the window is a box, [lo_k, lo_k + n_k) on every
+            # axis, placed at run time around the bulk of what the histogram already holds (fillable.choose_box).  A
+            # 24^3 box of c5 is 221 KB and takes 45 % of N(0,1)^3 events out of the L2 RED path, which is what bounds
+            # that kernel (227e9 float64 REDs/s, the device's scattered-RED rate: profiles/atomics_microbench_r01.txt).
+            boxes = [hp for hp in plans if hp.strategy == "global" and not hp.groups and len(hp.index) >= 1 and hp.nbins * hp.ncol * 8 > max_bytes
+                     and forced.get(hp.hid, forced.get(str(hp.hid), forced.get("*"))) in (None, "window") and len(hp.index) <= 6]
+            if boxes:
+                window = max(boxes, key=lambda hp: hp.nbins)
+                window.strategy = "window"
+                window.win_box = True
+                window.win_split = 0
+                used = (used + 15) // 16 * 16
+                window.win_table_off = used
+                window.win_off = used
     shared = {}
     for hp in plans:
         if hp.strategy == "global" and not det:      # (deterministic mode: global histograms add to exact accumulators too)
@@ -1089,7 +1105,7 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
         # `smem` bytes of statically privatised histograms (and the window's row table), then p.win[0] words of window
         bound = "%d + p.win[0]" % (smem // 4) if window is not None else "%d" % (smem // 4)
         src.append("    for (int i = threadIdx.x; i < %s; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % bound)
-        if window is not None:
+        if window is not None and window.get("box") is None:
             # per-row interval table of the hot window: [offset into the window | first in-row index << 16 | length]
             src.append("    __syncthreads();")
             tt = "hb_u32" if window["table_bits"] == 32 else "hb_u64"
@@ -1645,6 +1661,7 @@ def generate(spec, coltypes, options=None):
             window.strategy, window = "global", None
             smem_cap = smem
 
+    nfx_total = 1 + max([hp.fx_index[t] for hp in plans for t in hp.f64_terms if t in hp.fx_set] + [-1])
     group_aux = {}
     goal_aux = {}                                      # tree key of a group goal -> aux slot of its key table
     ev = list(prog.body)
@@ -1677,7 +1694,24 @@ def generate(spec, coltypes, options=None):
                 and options.get("pair_red", True) and not options.get("deterministic", False)
                 and hp.ncol == 2 and len(hp.terms) == 2
                 and sorted(hp.dest[0] + hp.dest[1]) == [0, 1])
-        if hp.strategy == "window":
+        if hp.strategy == "window" and hp.win_box:
+            # inside the box -> shared memory.  p.win[wbase + 2k] = first index of the box on axis k, [wbase + 2k + 1] = its extent
+            wbase = 2 + nfx_total
+            ev.append("    const bool okw = %s;" % " && ".join(conds))
+            tests, wb = [], None
+            for a, (v, totbins) in enumerate(hp.index):
+                ev.append("    const unsigned wq%d = (unsigned)(%s - p.win[%d]);" % (a, v.c, wbase + 2 * a))
+                tests.append("wq%d < (unsigned)p.win[%d]" % (a, wbase + 2 * a + 1))
+                wb = "wq%d" % a if wb is None else "(%s) * (unsigned)p.win[%d] + wq%d" % (wb, wbase + 2 * a + 1, a)
+            ev.append("    const bool inside = okw && %s;" % " && ".join(tests))
+            ev.append("    if (inside) {")
+            ev.append("        const int wb = (int)(%s);" % wb)
+            ev.extend(_emit_row_adds(hp, options, hp.win_off, "wb", (smem_cap - smem) // hp.row_bytes(options), "        ",
+                                     grow="(p.hist[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, hp.ncol),
+                                     gexact="(p.fxg[%d] + (hb_i64)(%s) * %d)" % (hp.hid, idx, 6 * len(hp.f64_terms))))
+            ev.append("    }")
+            conds = ["okw", "!inside"]
+        elif hp.strategy == "window":
             # inside the hot window -> shared memory.  Row table entry: x = offset of the row's interval in the
             # window, y = (first in-row index << 16) | length; a row without interval has length 0.
             k = hp.win_split
@@ -1769,7 +1803,36 @@ def generate(spec, coltypes, options=None):
         merge.extend(_emit_row_merge(hp, options, hp.smem_f64_off, "b", hp.nrows, "    ", rowidx=grow_idx))
         merge.append("}")
 
-    if window is not None:
+    if window is not None and window.win_box:
+        hp = window
+        wbase = 2 + nfx_total
+        nrows_w = (smem_cap - smem) // hp.row_bytes(options)
+        slots_w = hp.row_layout(options)[0]
+        paired = (hp.ncol == 2 and len(slots_w) == 2 and hp.count_term is None and sorted(hp.dest[slots_w[0]] + hp.dest[slots_w[1]]) == [0, 1]
+                  and options.get("merge_pair", True))
+        merge.append("// merge the box of hist %d: bin wb of the box -> its row in the histogram" % hp.hid)
+        merge.append("for (int wb0 = 0; wb0 < p.win[1]; wb0 += HB_THREADS) {")
+        merge.append("    const int wb = wb0 + (int)threadIdx.x;")
+        merge.append("    const bool wlive = wb < p.win[1];")
+        merge.append("    unsigned wrest = wlive ? (unsigned)wb : 0u;")
+        merge.append("    hb_i64 grow = 0, gstride = 1;")
+        for a in range(len(hp.index) - 1, -1, -1):
+            merge.append("    { const unsigned wn = (unsigned)max(p.win[%d], 1); grow += (hb_i64)(wrest %% wn + (unsigned)p.win[%d]) * gstride; wrest /= wn; gstride *= %d; }" % (
+                wbase + 2 * a + 1, wbase + 2 * a, hp.index[a][1]))
+        if paired:
+            t0 = slots_w[0] if hp.dest[slots_w[0]] == [0] else slots_w[1]
+            t1 = slots_w[1] if t0 == slots_w[0] else slots_w[0]
+            vals = ["*%s" % _slot_ptr(hp, hp.win_off, slots_w.index(t), "(wlive ? wb : 0)", nrows_w, const=True)[1] for t in (t0, t1)]
+            merge.append("    const double mv0 = wlive ? %s : 0.0;" % vals[0])
+            merge.append("    const double mv1 = wlive ? %s : 0.0;" % vals[1])
+            merge.append("    hb_red_pair(p.hist[%d], (wlive && (mv0 != 0.0 || mv1 != 0.0)) ? grow : (hb_i64)-1, mv0, mv1);" % hp.hid)
+        else:
+            merge.append("    if (wlive) {")
+            merge.append("        double* const row = p.hist[%d] + grow * %d;" % (hp.hid, hp.ncol))
+            merge.extend(_emit_row_merge(hp, options, hp.win_off, "wb", nrows_w, "        ", rowidx="grow"))
+            merge.append("    }")
+        merge.append("}")
+    elif window is not None:
         hp = window
         merge.append("// merge the hot window of hist %d: one warp per table row, lanes along the row's interval" % hp.hid)
         merge.append("for (int wr = threadIdx.x >> 5; wr < %d; wr += HB_THREADS / 32) {" % hp.win_rows)
@@ -1820,7 +1883,10 @@ def generate(spec, coltypes, options=None):
         winfo = {"hid": window.hid, "bpb": bpb, "wmax": (smem_cap - smem) // bpb, "rows": window.win_rows, "trail": window.win_trail,
                  "ncol": window.ncol, "col": spec["hists"][window.hid]["sumw"], "aux": naux, "table_off": window.win_table_off,
                  "table_bits": window.win_table_bits(smem_cap - smem, options)}
-        naux += 1
+        if window.win_box:
+            winfo.update({"box": [t for v, t in window.index], "box_base": 2 + nfx_total, "rows": 0, "aux": None})
+        else:
+            naux += 1
     k.fx_terms = [(hp.fx_index[t], hp.hid, t) for hp in plans for t in hp.f64_terms if t in hp.fx_set]
     k.nfx = (1 + max(i for i, hid, t in k.fx_terms)) if k.fx_terms else 0
     if k.fx_terms:

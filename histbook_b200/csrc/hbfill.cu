@@ -24,8 +24,17 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/hbfill.h"
 #include "hb_template.cuh"
+
+// NVTX ranges around the host-visible stages (compile, load, staging copies, launches, reads): visible in Nsight
+// Systems / any NVTX consumer; a few nanoseconds each without a tool attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -254,6 +263,7 @@ extern "C" int hb_program_compile(const char* source, const char* header, int li
                                   void** cubin, size_t* cubin_size) {
     if (!source || !header || !cubin || !cubin_size) return fail(HB_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lock(g_mutex);
+    NvtxRange range("hb_program_compile (NVRTC)");
     int rc = load_nvrtc();
     if (rc) return rc;
     nvrtcProgram prog;
@@ -350,6 +360,93 @@ extern "C" int hb_program_info(const hb_program* p, int* regs, int* static_smem,
 }
 
 // ------------------------------------------------------------------------------------------------
+// host copies
+
+// a small pool of copy threads (created at the first pageable column)
+struct CopyJob { char* dst; const char* src; size_t bytes; };
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable wake, done;
+    std::vector<CopyJob> jobs;
+    size_t next = 0, finished = 0;
+    bool stop = false;
+
+    void run() {
+        std::unique_lock<std::mutex> lock(m);
+        while (true) {
+            wake.wait(lock, [this] { return stop || next < jobs.size(); });
+            if (stop) return;
+            const CopyJob j = jobs[next++];
+            lock.unlock();
+            memcpy(j.dst, j.src, j.bytes);
+            lock.lock();
+            if (++finished == jobs.size()) done.notify_all();
+        }
+    }
+    void start(int n) {
+        for (int i = 0; i < n; ++i) workers.emplace_back([this] { run(); });
+    }
+    // copies all jobs; the calling thread works too
+    void copy(std::vector<CopyJob>& batch) {
+        if (batch.empty()) return;
+        std::unique_lock<std::mutex> lock(m);
+        jobs.swap(batch);
+        next = 0;
+        finished = 0;
+        wake.notify_all();
+        while (next < jobs.size()) {
+            const CopyJob j = jobs[next++];
+            lock.unlock();
+            memcpy(j.dst, j.src, j.bytes);
+            lock.lock();
+            ++finished;
+        }
+        done.wait(lock, [this] { return finished == jobs.size(); });
+        jobs.clear();
+        next = finished = 0;
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
+        }
+        wake.notify_all();
+        for (auto& t : workers) t.join();
+    }
+};
+static CopyPool* g_pool = nullptr;
+static int g_copy_threads = -1;
+
+static CopyPool* copy_pool() {
+    if (!g_pool) {
+        if (g_copy_threads < 0) {
+            const char* env = getenv("HB_COPY_THREADS");
+            unsigned hw = std::thread::hardware_concurrency();
+            g_copy_threads = env ? atoi(env) : (int)(hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+            if (g_copy_threads < 1) g_copy_threads = 1;
+        }
+        g_pool = new CopyPool();
+        g_pool->start(g_copy_threads - 1);
+    }
+    return g_pool;
+}
+
+extern "C" int hb_set_copy_threads(int n) {
+    if (n < 1 || n > 64) return fail(HB_ERR_ARG, "copy threads must be 1..64");
+    if (g_pool) { delete g_pool; g_pool = nullptr; }
+    g_copy_threads = n;
+    return HB_OK;
+}
+
+static bool is_pageable(const void* ptr) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return true; }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// ------------------------------------------------------------------------------------------------
 // arenas
 
 struct hb_arena {
@@ -443,12 +540,53 @@ extern "C" int hb_arena_resize(hb_arena* a, int64_t ndoubles) {
     return HB_OK;
 }
 
+// Device -> host copy of bin contents.  Large reads into pageable memory (numpy arrays: every `Hist._content`, pickle and
+// JSON of c5's 134 MB) go through two page-locked staging buffers: the DMA of chunk k + 1 runs while the copy threads
+// move chunk k into the caller's array (a plain cudaMemcpy into pageable memory is a serial staged copy in the driver).
+static void* g_read_pin[2] = {nullptr, nullptr};
+static cudaEvent_t g_read_done[2] = {nullptr, nullptr};
+static const size_t kReadChunk = (size_t)8 << 20;
+
 extern "C" int hb_arena_read(const hb_arena* a, int64_t offset, int64_t count, double* host_out) {
     int rc = ensure_device();
     if (rc) return rc;
     if (!a || offset < 0 || count < 0 || offset + count > a->n || !host_out) return fail(HB_ERR_ARG, "arena read out of range");
-    CUDA_TRY(cudaMemcpyAsync(host_out, a->ptr + offset, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    NvtxRange range("hb_arena_read");
+    const size_t bytes = (size_t)count * sizeof(double);
+    if (bytes < 2 * kReadChunk || !is_pageable(host_out)) {
+        CUDA_TRY(cudaMemcpyAsync(host_out, a->ptr + offset, bytes, cudaMemcpyDeviceToHost, g_stream));
+        CUDA_TRY(cudaStreamSynchronize(g_stream));
+        return HB_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (int b = 0; b < 2; ++b) {
+        if (!g_read_pin[b]) {
+            CUDA_TRY(cudaHostAlloc(&g_read_pin[b], kReadChunk, cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&g_read_done[b], cudaEventDisableTiming | cudaEventBlockingSync));
+        }
+    }
+    const char* src = (const char*)(a->ptr + offset);
+    char* dst = (char*)host_out;
+    const size_t nchunks = (bytes + kReadChunk - 1) / kReadChunk;
+    std::vector<CopyJob> jobs;
+    copy_pool();
+    const int np = g_copy_threads > 0 ? g_copy_threads : 1;
+    for (size_t k = 0; k <= nchunks; ++k) {
+        if (k < nchunks) {
+            const size_t o = k * kReadChunk, m = std::min(kReadChunk, bytes - o);
+            CUDA_TRY(cudaMemcpyAsync(g_read_pin[k & 1], src + o, m, cudaMemcpyDeviceToHost, g_stream));
+            CUDA_TRY(cudaEventRecord(g_read_done[k & 1], g_stream));
+        }
+        if (k > 0) {
+            const size_t o = (k - 1) * kReadChunk, m = std::min(kReadChunk, bytes - o);
+            CUDA_TRY(cudaEventSynchronize(g_read_done[(k - 1) & 1]));
+            jobs.clear();
+            const size_t step = ((m + np - 1) / np + 4095) / 4096 * 4096;
+            for (size_t q = 0; q < m; q += step)
+                jobs.push_back({dst + o + q, (const char*)g_read_pin[(k - 1) & 1] + q, std::min(step, m - q)});
+            copy_pool()->copy(jobs);
+        }
+    }
     return HB_OK;
 }
 
@@ -467,6 +605,19 @@ extern "C" int hb_arena_axpy(hb_arena* dst, const hb_arena* src, double alpha) {
     if (!dst || !src || dst->n != src->n) return fail(HB_ERR_ARG, "arena sizes differ");
     if (dst->n == 0) return HB_OK;
     hb_axpy_kernel<<<grid_for(dst->n), 256, 0, g_stream>>>(dst->ptr, src->ptr, alpha, dst->n);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+// dst[dst_off .. dst_off + count) += alpha * src[src_off .. src_off + count): one slab slot of a group-axis histogram
+// added to another's (Hist.__add__ on dict contents, histbook/hist.py:513-537)
+extern "C" int hb_arena_axpy_at(hb_arena* dst, int64_t dst_off, const hb_arena* src, int64_t src_off, int64_t count, double alpha) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!dst || !src || count < 0 || dst_off < 0 || src_off < 0 || dst_off + count > dst->n || src_off + count > src->n)
+        return fail(HB_ERR_ARG, "hb_arena_axpy_at out of range");
+    if (count == 0) return HB_OK;
+    hb_axpy_kernel<<<grid_for(count), 256, 0, g_stream>>>(dst->ptr + dst_off, src->ptr + src_off, alpha, count);
     CUDA_TRY(cudaGetLastError());
     return HB_OK;
 }
@@ -593,90 +744,6 @@ static int ring_reserve(int slot, int col, size_t bytes) {
     return HB_OK;
 }
 
-// a small pool of copy threads (created at the first pageable column)
-struct CopyJob { char* dst; const char* src; size_t bytes; };
-struct CopyPool {
-    std::vector<std::thread> workers;
-    std::mutex m;
-    std::condition_variable wake, done;
-    std::vector<CopyJob> jobs;
-    size_t next = 0, finished = 0;
-    bool stop = false;
-
-    void run() {
-        std::unique_lock<std::mutex> lock(m);
-        while (true) {
-            wake.wait(lock, [this] { return stop || next < jobs.size(); });
-            if (stop) return;
-            const CopyJob j = jobs[next++];
-            lock.unlock();
-            memcpy(j.dst, j.src, j.bytes);
-            lock.lock();
-            if (++finished == jobs.size()) done.notify_all();
-        }
-    }
-    void start(int n) {
-        for (int i = 0; i < n; ++i) workers.emplace_back([this] { run(); });
-    }
-    // copies all jobs; the calling thread works too
-    void copy(std::vector<CopyJob>& batch) {
-        if (batch.empty()) return;
-        std::unique_lock<std::mutex> lock(m);
-        jobs.swap(batch);
-        next = 0;
-        finished = 0;
-        wake.notify_all();
-        while (next < jobs.size()) {
-            const CopyJob j = jobs[next++];
-            lock.unlock();
-            memcpy(j.dst, j.src, j.bytes);
-            lock.lock();
-            ++finished;
-        }
-        done.wait(lock, [this] { return finished == jobs.size(); });
-        jobs.clear();
-        next = finished = 0;
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lock(m);
-            stop = true;
-        }
-        wake.notify_all();
-        for (auto& t : workers) t.join();
-    }
-};
-static CopyPool* g_pool = nullptr;
-static int g_copy_threads = -1;
-
-static CopyPool* copy_pool() {
-    if (!g_pool) {
-        if (g_copy_threads < 0) {
-            const char* env = getenv("HB_COPY_THREADS");
-            unsigned hw = std::thread::hardware_concurrency();
-            g_copy_threads = env ? atoi(env) : (int)(hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
-            if (g_copy_threads < 1) g_copy_threads = 1;
-        }
-        g_pool = new CopyPool();
-        g_pool->start(g_copy_threads - 1);
-    }
-    return g_pool;
-}
-
-extern "C" int hb_set_copy_threads(int n) {
-    if (n < 1 || n > 64) return fail(HB_ERR_ARG, "copy threads must be 1..64");
-    if (g_pool) { delete g_pool; g_pool = nullptr; }
-    g_copy_threads = n;
-    return HB_OK;
-}
-
-static bool is_pageable(const void* ptr) {
-    cudaPointerAttributes attr;
-    cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
-    if (e != cudaSuccess) { cudaGetLastError(); return true; }
-    return attr.type == cudaMemoryTypeUnregistered;
-}
-
 // Counters of the dynamic tile hand-out (HbParams::sched): one pair per stream, because launches on one stream run one
 // after the other (the last block of a launch zeroes the pair again) while launches on different streams may overlap.
 static std::vector<std::pair<cudaStream_t, hb_u32*>> g_sched;
@@ -734,6 +801,7 @@ extern "C" int hb_fill_multi(int nlaunch, const hb_launch* L, int ncols, const h
     if (nlaunch < 1 || nlaunch > HB_MAX_PARTS || !L || ncols < 0 || ncols > HB_MAX_COLS || n < 0)
         return fail(HB_ERR_ARG, "bad hb_fill arguments");
     std::lock_guard<std::mutex> lock(g_mutex);
+    NvtxRange range("hb_fill");
 
     bool any_host = false, any_pageable = false;
     bool pageable[HB_MAX_COLS] = {};
@@ -841,7 +909,7 @@ extern "C" int hb_fill_multi(int nlaunch, const hb_launch* L, int ncols, const h
                 for (size_t o = 0; o < bytes; o += step)
                     jobs.push_back({(char*)g_stage.pin[slot][c] + o, src + o, std::min(step, bytes - o)});
             }
-            copy_pool()->copy(jobs);
+            { NvtxRange r2("hb_fill: pageable -> page-locked ring"); copy_pool()->copy(jobs); }
         }
         // staging buffer reuse: the copy waits until the last kernel that read this buffer is done -- the one two
         // chunks back, or the tail of the PREVIOUS hb_fill call (waiting on a never-recorded event is a no-op)

@@ -473,15 +473,7 @@ class Merger(object):
                 st.arena.resize(max(size, 1))
             if size:
                 st.arena.as_tensor()[:size].copy_(flat[off:off + size])
-            st.tuples = collections.OrderedDict((tup, slot) for slot, tup in enumerate(order))
-            skeleton = collections.OrderedDict()
-            for tup, slot in st.tuples.items():
-                node = skeleton
-                for k in tup[:-1]:
-                    node = node.setdefault(k, collections.OrderedDict())
-                node[tup[-1]] = slot
-            st.skeleton = skeleton
-            st.table = None
+            st.set_tuples(order)
             self._maps.pop(id(st), None)
             st.mark_filled()
         return self

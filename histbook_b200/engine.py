@@ -74,6 +74,7 @@ SYMBOLS = {
     "hb_arena_read": (_I, [_P, _I64, _I64, _P]),
     "hb_arena_write": (_I, [_P, _I64, _I64, _P]),
     "hb_arena_axpy": (_I, [_P, _P, ctypes.c_double]),
+    "hb_arena_axpy_at": (_I, [_P, _I64, _P, _I64, _I64, ctypes.c_double]),
     "hb_arena_scale": (_I, [_P, ctypes.c_double]),
     "hb_arena_project": (_I, [_P, _I, ctypes.POINTER(_I64), _I, ctypes.POINTER(ctypes.c_int32), _PP]),
     "hb_arena_ptr": (_P, [_P]),
@@ -280,6 +281,9 @@ class Arena(object):
 
     def axpy(self, other, alpha=1.0):
         check(lib().hb_arena_axpy(self._h, other._h, float(alpha)))
+
+    def axpy_at(self, dst_off, other, src_off, count, alpha=1.0):
+        check(lib().hb_arena_axpy_at(self._h, int(dst_off), other._h, int(src_off), int(count), float(alpha)))
 
     def scale(self, alpha):
         check(lib().hb_arena_scale(self._h, float(alpha)))

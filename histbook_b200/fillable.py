@@ -256,6 +256,74 @@ def choose_ragged(density, wmax):
     return first, length, float(density[inside].sum()) / total
 
 
+def choose_box(marginals, wmax):
+    """Place a box window: one interval [lo_k, lo_k + n_k) per fixed axis with at most ``wmax`` bins in the box, around
+    the bulk of the histogram.  ``marginals[k]`` = what the histogram holds, summed over all other axes.  Every axis
+    takes the shortest interval that holds a common fraction f of its marginal; f is the largest that fits (bisection).
+    Returns (lo[k], n[k], product of the marginal fractions = coverage if the axes were independent)."""
+    margs = []
+    for m in marginals:
+        m = numpy.abs(numpy.asarray(m, dtype=numpy.float64))
+        m[~numpy.isfinite(m)] = 0.0
+        margs.append(m)
+    if wmax < 1 or any(m.sum() <= 0.0 for m in margs):
+        return [0] * len(margs), [0] * len(margs), 0.0
+
+    def shortest(m, f):
+        """shortest [a, b) with sum(m[a:b]) >= f * total (two pointers)"""
+        need = f * m.sum()
+        c = numpy.concatenate([[0.0], numpy.cumsum(m)])
+        best = (0, len(m))
+        a = 0
+        for b in range(1, len(m) + 1):
+            while a + 1 < b and c[b] - c[a + 1] >= need:
+                a += 1
+            if c[b] - c[a] >= need and b - a < best[1] - best[0]:
+                best = (a, b)
+        return best
+
+    def boxes(f):
+        return [shortest(m, f) for m in margs]
+
+    def volume(bx):
+        v = 1
+        for a, b in bx:
+            v *= (b - a)
+        return v
+    lo_f, hi_f = 0.0, 1.0
+    best = boxes(0.0)
+    if volume(best) > wmax:
+        return [0] * len(margs), [0] * len(margs), 0.0
+    for _ in range(24):
+        mid = 0.5 * (lo_f + hi_f)
+        bx = boxes(mid)
+        if volume(bx) <= wmax:
+            lo_f, best = mid, bx
+        else:
+            hi_f = mid
+    # use what is left of the capacity: widen one axis at a time towards the heavier neighbouring bin
+    grown = True
+    while grown:
+        grown = False
+        order = sorted(range(len(margs)), key=lambda k: best[k][1] - best[k][0])
+        for k in order:
+            a, b = best[k]
+            left = margs[k][a - 1] if a > 0 else -1.0
+            right = margs[k][b] if b < len(margs[k]) else -1.0
+            if left < 0 and right < 0:
+                continue
+            cand = (a - 1, b) if left >= right else (a, b + 1)
+            trial = list(best)
+            trial[k] = cand
+            if volume(trial) <= wmax:
+                best, grown = trial, True
+                break
+    coverage = 1.0
+    for m, (a, b) in zip(margs, best):
+        coverage *= float(m[a:b].sum() / m.sum())
+    return [a for a, b in best], [b - a for a, b in best], coverage
+
+
 def window_table(first, length, bits=64):
     """The kernel's row table (codegen `we`): per row one uint64 = offset of the row's interval in the window (low 32
     bits) | first in-row index << 48 | length << 32 -- or, when the kernel was generated for packed entries
@@ -474,7 +542,7 @@ def fill_hists(plan, hists, arrays, timed=False):
             return {"kern": vkern, "prog": vprog, "abi": _abi_columns(vkern, cols), "aux": vaux, "fx": fx, "exact": exact, "finalize": finalize}
 
         def launch(v, n, win, offset=0):
-            out = engine.fill(v["prog"], v["abi"], n, arenas, aux=v["aux"], win=win + v["fx"], timed=timed, offset=offset, exact=v["exact"])
+            out = engine.fill(v["prog"], v["abi"], n, arenas, aux=v["aux"], win=win + v["fx"] + v.get("box", []), timed=timed, offset=offset, exact=v["exact"])
             v["finalize"]()
             return out
 
@@ -494,7 +562,23 @@ def fill_hists(plan, hists, arrays, timed=False):
                 done = 0
                 extra = 0.0
                 key = (info["rows"], info["trail"], info["wmax"])
-                if wst.window is None or wst.window_key != key:
+                if info.get("box") is not None and (wst.window is None or wst.window_key != key):
+                    # box window (c5-class histograms): placed from the marginal distributions, which are summed on the device
+                    if not wst.nonempty:
+                        base = prepare(used)
+                        done = min(length, max(kern.tile, PILOT_EVENTS // kern.tile * kern.tile))
+                        extra = launch(base, done, [0, 0])["ms_kernel"]
+                    dims = info["box"]
+                    margs = []
+                    for a in range(len(dims)):
+                        proj = wst.arena.project(dims, info["ncol"], [k == a for k in range(len(dims))])
+                        margs.append(proj.read().reshape(dims[a], info["ncol"])[:, info["col"]])
+                    lo, nn, coverage = choose_box(margs, info["wmax"])
+                    wst.window_key = key
+                    wst.window_coverage = coverage
+                    bins = int(numpy.prod(nn, dtype=numpy.int64)) if coverage >= WINDOW_MIN_COVERAGE else 0
+                    wst.window = {"box": [int(x) for pair in zip(lo, nn) for x in pair], "bins": bins, "rows": len(dims), "dense": False} if bins else False
+                elif wst.window is None or wst.window_key != key:
                     if not wst.nonempty:
                         base = prepare(used)
                         base["aux"][info["aux"]] = 0          # null row table = no window
@@ -524,12 +608,17 @@ def fill_hists(plan, hists, arrays, timed=False):
                     used = (dsig, dkern, dprog, drng, drprog)
                 v = prepare(used)
                 vinfo = used[1].window
-                if wst.window:
+                box_tail = []
+                if vinfo.get("box") is not None:
+                    win = window_params(used[1], wst.window["bins"]) if wst.window else [0, 0]
+                    box_tail = list(wst.window["box"]) if wst.window else [0] * (2 * len(vinfo["box"]))
+                elif wst.window:
                     v["aux"][vinfo["aux"]] = wst.window["table"].ptr
                     win = window_params(used[1], wst.window["bins"])
                 else:
                     v["aux"][vinfo["aux"]] = 0
                     win = [0, 0]
+                v["box"] = box_tail
                 stats = {"events": length, "launches": 1 if done else 0, "ms_kernel": extra}
                 if length > done:
                     main = launch(v, length - done, win, offset=done)

@@ -201,6 +201,19 @@ class Store(object):
             self.arena.write(numpy.concatenate(blocks))
         self.table = None
 
+    def set_tuples(self, order):
+        """Adopt ``order`` (key-pattern tuples, slot = position) as the slab layout: tuples, nested skeleton in the
+        reference's insertion order, lookup table dropped."""
+        self.tuples = collections.OrderedDict((tup, slot) for slot, tup in enumerate(order))
+        skeleton = collections.OrderedDict()
+        for tup, slot in self.tuples.items():
+            node = skeleton
+            for k in tup[:-1]:
+                node = node.setdefault(k, collections.OrderedDict())
+            node[tup[-1]] = slot
+        self.skeleton = skeleton
+        self.table = None
+
     def admit(self, fill_keys):
         """Register the keys one fill produced.  ``fill_keys[a]`` = patterns seen on axis ``a`` in this fill.
 

@@ -115,6 +115,8 @@ int hb_arena_resize(hb_arena* a, int64_t ndoubles);      /* keeps the common pre
 int hb_arena_read(const hb_arena* a, int64_t offset, int64_t count, double* host_out);
 int hb_arena_write(hb_arena* a, int64_t offset, int64_t count, const double* host_in);
 int hb_arena_axpy(hb_arena* dst, const hb_arena* src, double alpha);   /* dst += alpha * src */
+/* dst[dst_off, dst_off + count) += alpha * src[src_off, src_off + count): slab slots of group-axis histograms */
+int hb_arena_axpy_at(hb_arena* dst, int64_t dst_off, const hb_arena* src, int64_t src_off, int64_t count, double alpha);
 int hb_arena_scale(hb_arena* dst, double alpha);                       /* dst *= alpha */
 /* Hist.project (histbook/proj.py:227-296) on the device: sum the content over the fixed axes with keep[k] == 0.
  * `shape` = bins per fixed axis (ndim <= 8), ncol = size of the last (column) dimension, which is always kept.

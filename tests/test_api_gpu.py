@@ -442,3 +442,67 @@ def test_cuda_array_interface_stream_key_is_honoured():
     h.fill(x=Exported(x, side.cuda_stream))                # torch's current stream is the default one here
     assert h._content[3, 0] == n
     side.synchronize()
+
+
+def test_group_axis_histograms_add_on_the_device():           # Hist.__add__/__iadd__ on dict contents, histbook/hist.py:513-537
+    """Two device-resident histograms with group axes are added slab slot by slab slot after uniting their keys; the
+    result -- values, keys and key order -- is what the reference's recursion gives on host copies."""
+    rs = numpy.random.RandomState(3)
+    n1 = rs.poisson(3, 30000).astype(numpy.int64)
+    n2 = rs.poisson(6, 20000).astype(numpy.int64) + 3             # other keys, some shared
+    cols1 = {"x": rs.normal(0, 1, 30000), "n": n1, "w": rs.uniform(0.5, 1.5, 30000)}
+    cols2 = {"x": rs.normal(0, 1, 20000), "n": n2, "w": rs.uniform(0.5, 1.5, 20000)}
+
+    def make():
+        return Hist(groupbin("n", 2), groupby("n"), bin("x", 20, -3, 3), weight="w")
+    a, b = make(), make()
+    a.fill(**cols1)
+    b.fill(**cols2)
+    with histbook_b200.reference_path() as hb:
+        ra = hb.Hist(hb.groupbin("n", 2), hb.groupby("n"), hb.bin("x", 20, -3, 3), weight="w")
+        rb = hb.Hist(hb.groupbin("n", 2), hb.groupby("n"), hb.bin("x", 20, -3, 3), weight="w")
+        ra.fill(**cols1)
+        rb.fill(**cols2)
+        rc = ra + rb
+        expected = rc._content
+
+    def check(got, exp):
+        assert list(got) == list(exp)
+        for k in exp:
+            assert list(got[k]) == list(exp[k]), k
+            for k2 in exp[k]:
+                assert numpy.all(numpy.abs(got[k][k2] - exp[k][k2]) <= 1e-12 * numpy.maximum(numpy.abs(exp[k][k2]), 1.0))
+    c = a + b
+    for h in (a, b, c):
+        st = h.__dict__["_hb"]
+        assert st.dev_valid and not st.host_valid                 # nothing went through the host
+    check(histbook_b200.peek(c), expected)
+    nkeys_b = len(b.__dict__["_hb"].tuples)
+    a += b
+    assert a.__dict__["_hb"].dev_valid and not a.__dict__["_hb"].host_valid
+    check(histbook_b200.peek(a), expected)
+    assert len(b.__dict__["_hb"].tuples) == nkeys_b                # the right operand is untouched
+    a.fill(**cols2)                                                # and keeps filling: the united keys are known to the next kernel
+    assert abs(sum(v[..., 0].sum() for d in a._content.values() for v in d.values()) - (cols1["w"].sum() + 2 * cols2["w"].sum())) < 1e-6
+
+
+def test_serialisation_keeps_the_device_copy():               # Hist.tojson / __getstate__, histbook/hist.py:700-741
+    """Pickle and JSON read the bins without taking the device copy out of service (a plain ``_content`` read would make
+    the host copy the authoritative one and the next fill would upload it again); large contents cross in chunks
+    through page-locked staging."""
+    rs = numpy.random.RandomState(5)
+    h = Hist(bin("x", 300, -4, 4), bin("y", 300, -4, 4), bin("z", 40, -4, 4), weight="w")       # 302 * 302 * 42 * 2 doubles = 61 MB
+    cols = {"x": rs.normal(0, 1, 200000), "y": rs.normal(0, 1, 200000), "z": rs.normal(0, 1, 200000), "w": rs.uniform(0.5, 1.5, 200000)}
+    h.fill(**cols)
+    st = h.__dict__["_hb"]
+    blob = pickle.dumps(h)
+    assert h.__dict__["_hb"] is st and st.dev_valid and not st.host_valid
+    h2 = pickle.loads(blob)
+    assert numpy.array_equal(h2._content, histbook_b200.peek(h))
+    g = Hist(groupby("c"), bin("x", 10, -3, 3))
+    g.fill(c=["a", "b", "a", "c"], x=[0.1, 0.2, 0.3, 0.4])
+    j = g.tojson()
+    assert g.__dict__["_hb"].dev_valid and not g.__dict__["_hb"].host_valid
+    assert sorted(j["content"]) == ["a", "b", "c"] and sum(sum(r[0] for r in v) for v in j["content"].values()) == 4.0
+    h.fill(**cols)                                                # no upload in between: still the same arena, twice the weight
+    assert h.__dict__["_hb"] is st and abs(h._content[..., 0].sum() - 2 * cols["w"].sum()) < 1e-6
