@@ -347,3 +347,31 @@ def test_half_books_agree_with_the_single_kernel():
             if spec["hists"][hid]["weight"] is None:
                 s = spec["hists"][hid]["sumw"]
                 assert numpy.array_equal(x[..., s], y[..., s])
+
+
+def test_box_window_on_a_large_histogram():
+    """c5's 134 MB histogram with data narrow enough for a box window to pay (sigma = 6 bins: a 24^3 box holds ~85 %):
+    the events inside go to shared memory, the rest to paired REDs; same bars against the oracle, window reported."""
+    from histbook_b200 import fillable
+    spec = golden_util.load()["c5"]["spec"]
+    rs = numpy.random.RandomState(41)
+    n = 1500001
+    cols = {"x": rs.normal(0.3, 0.3, n), "y": rs.normal(-1.0, 0.3, n), "z": rs.normal(0, 0.3, n), "w": rs.uniform(0.5, 1.5, n)}
+    cols["x"][::5003] = numpy.nan
+    cols["y"][1::4001] = 7.5
+    sf = fillable.SpecFill(spec)
+    fills = [dict((k, torch_or_numpy(v[: n // 2])) for k, v in cols.items()), dict((k, torch_or_numpy(v[n // 2:])) for k, v in cols.items())]
+    for f in fills:
+        sf.fill(f)
+    win = fillable.last_stats.get("window")
+    assert win and win["bins"] > 8000 and fillable.last_stats["window_coverage"] > 0.6, fillable.last_stats
+    exp = bound = None
+    for a in (dict((k, v[: n // 2]) for k, v in cols.items()), dict((k, v[n // 2:]) for k, v in cols.items())):
+        exp = fill_oracle.fill(spec, a, exp)
+        bound = fill_oracle.fill(spec, a, bound, absolute=True)
+    compare("c5 box", spec, sf.contents(), [golden_util.flatten(e) for e in exp], bound)
+
+
+def torch_or_numpy(v):
+    import torch
+    return torch.from_numpy(numpy.ascontiguousarray(v)).cuda()

@@ -205,8 +205,10 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     d = gen("c2", win_dense=True)                   # dense variant: sum(w^2) in fixed point, plain REDs outside
     assert len(d.fx_terms) == 1 and "hb_red_pair(" not in d.source.split("hb_event")[1] and d.window["wmax"] < k.window["wmax"]
     assert d.window["bpb"] == 24 and k.window["bpb"] == 16
-    k = gen("c5")                                   # 134 MB: global paired REDs only, no window
+    k = gen("c5", box=False)                        # 134 MB: global paired REDs only, no window
     assert [hp.strategy for hp in k.plans] == ["global"] and k.window is None and k.smem_bytes == 0
+    k = gen("c5")                                   # default: a box window [lo_k, lo_k + n_k) per axis, placed at run time (if it would hold >= 25 %)
+    assert k.plans[0].strategy == "window" and k.window["box"] == [203, 203, 203] and k.window["box_base"] == 2 and "hb_red_pair" in k.source
     k = gen("c4", sort=False)                       # big book, per-event strategies: one copy of the event code, everything privatised, all fixed point
     assert all(hp.strategy == "smem" for hp in k.plans) and len(k.fx_terms) == 48 and k.threads == 768
     assert k.nfx == 6 and k.source.count("hb_fx_decode<") == 6        # w, w^2, z, z^2, filtered w, filtered w^2: decoded once per event
@@ -265,3 +267,19 @@ def test_cuda_array_interface_stream_key_is_recorded():
         col = columns.bind("x", Exporter(stream))
         assert (col.location, col.length, col.ptr, col.stream, col.code) == (1, 8, 0x7F0000000000, expect, 0)
     assert engine.producer_stream() == 0                      # no CUDA context in this process: nothing to wait for
+
+
+def test_box_window_placement():
+    """fillable.choose_box: one interval per axis around the bulk, at most wmax bins in the box, capacity used up."""
+    from histbook_b200 import fillable
+    x = numpy.arange(103)
+    narrow = numpy.exp(-0.5 * ((x - 40.0) / 4.0) ** 2)
+    wide = numpy.exp(-0.5 * ((x - 60.0) / 12.0) ** 2)
+    lo, n, coverage = fillable.choose_box([narrow, wide, narrow], 14000)
+    assert numpy.prod(n) <= 14000 and numpy.prod(n) > 0.8 * 14000
+    assert lo[0] <= 40 < lo[0] + n[0] and lo[1] <= 60 < lo[1] + n[1] and n[1] > n[0]      # the wide axis takes more bins
+    exact = numpy.prod([m[a:a + k].sum() / m.sum() for m, a, k in zip([narrow, wide, narrow], lo, n)])
+    assert abs(coverage - exact) < 1e-12 and coverage > 0.5
+    assert fillable.choose_box([narrow, wide * 0.0], 100) == ([0, 0], [0, 0], 0.0)        # an empty marginal: no box
+    lo, n, coverage = fillable.choose_box([narrow], 1000)                                   # room for everything
+    assert lo == [0] and n == [103] and abs(coverage - 1.0) < 1e-12
