@@ -1316,6 +1316,8 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     threads, ept, tile, lanes = layout["threads"], layout["ept"], layout["tile"], layout["lanes"]
     G = len(groups)
     assert threads % lanes == 0
+    split = int(options.get("sort_split", 2))              # lanes per bin in the summing phase (a power of two, at most 32; c4: 10.9 / 11.4 / 10.8 / 9.0 Gev/s for 1 / 2 / 4 / 8)
+    assert split in (1, 2, 4, 8, 16, 32)
     nwg = min(threads // lanes, 15)                        # warp-groups that take sort groups (named barriers 1..15)
     src = []
     src.append('#include "hb_template.cuh"')
@@ -1412,13 +1414,20 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
         src.append("            const hb_u32* const st = reinterpret_cast<const hb_u32*>(hb_smem + %d);" % g.off["tick"])
         src.append("            const unsigned short* const so = reinterpret_cast<const unsigned short*>(hb_smem + %d);" % g.off["sorted"])
         src.append("            double* const acc = reinterpret_cast<double*>(hb_smem + %d);" % g.off["acc"])
-        src.append("            for (int b = hb_l; b < %d; b += HB_LANES) {" % g.nbins)
-        src.append("                hb_u32 pos = st[b];")
-        src.append("                const hb_u32 end = st[b + 1];")
-        src.append("                if (pos == end) continue;")
+        # HB_SPLIT lanes share a bin: lane q of them takes the events q, q + HB_SPLIT, ... of the bin's run, a butterfly of
+        # shuffles adds the partial sums, lane 0 adds them to the table.  One lane per bin left the warp that holds the
+        # fullest bin working alone while the block waited at the barrier (x*y of c4: 11 % of a tile in one bin, the
+        # barrier the top stall reason at 5 warps per issue -- profiles/r02_c4_ncu.txt).
+        src.append("            for (int w0 = 0; w0 < %d; w0 += HB_LANES) {" % (g.nbins * split))
+        src.append("                const int w = w0 + hb_l;")
+        src.append("                const bool mine = w < %d;" % (g.nbins * split))
+        src.append("                const int b = mine ? (w / %d) : 0;" % split)
+        src.append("                const hb_u32 end = mine ? st[b + 1] : 0u;")
+        src.append("                hb_u32 pos = mine ? st[b] + (hb_u32)(w %% %d) : 0u;" % split)
+        src.append("                const bool any = mine && st[b] != end;")
         src.append("                " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
-        src.append("                for (; pos + 1u < end; pos += 2u) {       // two events per round: their loads are in flight together")
-        src.append("                    const unsigned e0 = so[pos], e1 = so[pos + 1u];")
+        src.append("                for (; pos + %du < end; pos += %du) {       // two events per round: their loads are in flight together" % (split, 2 * split))
+        src.append("                    const unsigned e0 = so[pos], e1 = so[pos + %du];" % split)
         src.extend(element("                    ", "e0"))
         src.extend(element("                    ", "e1"))
         src.extend(adds("                    ", "e0"))
@@ -1429,7 +1438,11 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
         src.extend(element("                    ", "e0"))
         src.extend(adds("                    ", "e0"))
         src.append("                }")
-        src.append("                " + " ".join("acc[%d + b] += a%d;" % (j * g.nbins, j) for j in range(nv)) + "      // this lane alone adds to bin b")
+        d = 1
+        while d < split:
+            src.append("                " + " ".join("a%d += __shfl_xor_sync(0xffffffffu, a%d, %d);" % (j, j, d) for j in range(nv)))
+            d *= 2
+        src.append("                if (any && (w %% %d) == 0) { %s }      // this lane alone adds to bin b" % (split, " ".join("acc[%d + b] += a%d;" % (j * g.nbins, j) for j in range(nv))))
         src.append("            }")
         src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))
         src.append("            for (int b = hb_l; b <= %d; b += HB_LANES) reinterpret_cast<hb_u32*>(hb_smem + %d)[b] = 0u;" % (g.nbins, g.off["tick"]))

@@ -29,7 +29,7 @@ def set_options(**kwargs):
     "smem" | "global" | "window"}), ``smem_budget``, ``window`` / ``win_dense`` / ``win_pair`` / ``win_smem`` /
     ``win_threads`` / ``win_min_blocks`` / ``win_table32`` / ``win_max_rows`` / ``win_max_hist_bytes``, ``merge_pair``,
     ``pair_red``, ``group_slots``, ``replicas``, ``f64_atomic`` ("cas" | "exch"), ``sort`` ("auto" | True | False: the sorted
-    strategy of big books, codegen.SortGroup) with ``sort_lanes`` / ``sort_ept`` / ``sort_threads`` / ``sort_max_groups`` / ``sort_smem``.
+    strategy of big books, codegen.SortGroup) with ``sort_lanes`` / ``sort_split`` / ``sort_ept`` / ``sort_threads`` / ``sort_max_groups`` / ``sort_smem``, ``parts``, ``box``.
     Launch shape and loop: ``threads``, ``min_blocks``, ``unroll`` (4 | 1 | 0), ``prefetch``, ``dynamic`` (False | "tail" |
     True), ``evict_first``, ``red_evict_last``.  Measurement: ``block_times``.
     Defaults are the measured best (profiles/r01_sweeps.txt); tests/test_gpu_parity.py checks that none of them changes a
@@ -127,7 +127,8 @@ class Plan(object):
                     kern = None
                 if kern is not None and kern.sorted and len(kern.sorted["groups"]) >= int(options.get("parts_min_groups", 4)):
                     k = int(want) if want != "auto" else 2
-                    extra = {"sort_threads": 512, "sort_min_blocks": 2, "sort": True}
+                    extra = {"sort_threads": int(options.get("parts_threads", 512)), "sort_min_blocks": int(options.get("parts_min_blocks", 2)),
+                             "sort_ept": int(options.get("parts_ept", codegen.SORT_EPT)), "sort": True}
             if k <= 1:
                 self.parts[sig] = None
             else:

@@ -202,7 +202,7 @@ OPTION_SETS = [
     {"win_table32": False}, {"pair_red": False}, {"prefetch": True}, {"replicas": 2}, {"f64_atomic": "exch"}, {"unroll": 1},
     {"unroll": 0}, {"evict_first": False}, {"red_evict_last": True}, {"group_slots": 2}, {"threads": 256, "min_blocks": 4},
     {"smem_budget": 16384}, {"block_times": True}, {"sort": True}, {"sort": True, "sort_lanes": 256}, {"sort": True, "sort_lanes": 32},
-    {"sort": True, "sort_ept": 1}, {"sort": False},
+    {"sort": True, "sort_ept": 1}, {"sort": True, "sort_split": 1}, {"sort": True, "sort_split": 16}, {"sort": False},
 ]
 
 
