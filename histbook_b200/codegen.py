@@ -683,6 +683,8 @@ def hist_index(hp):
 
 SORT_THREADS = 1024        # one block per SM
 SORT_EPT = 2               # events per thread and tile
+SORT_SUM = "chunks"        # how the sorted events of a tile are summed: "chunks" (balanced: a contiguous chunk per lane) | "bins" (sort_split lanes per bin);
+                           # c4, one GPU, 1e9 events: chunks of 64 lanes per group 12.1 Gev/s, of 128 lanes 11.9, bins 11.75 (profiles/r02_sweeps.txt)
 SORT_MAX_BINS = 8192
 SORT_MAX_GROUPS = 12       # (key, rank) tickets of a tile live in registers: SORT_EPT x groups of them per thread
 SMEM_MAX = 227 * 1024
@@ -727,9 +729,10 @@ class SortGroup(object):
             hp.sslot[t] = j
             self.dests[j].extend((hp.hid, col, hp.ncol) for col in hp.dest[t])
 
-    def smem_bytes(self, tile, lanes):
+    def smem_bytes(self, tile, lanes, chunks=False):
         nv = len(self.values)
-        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + 64) // 16 * 16 + 16
+        tails = (4 * lanes + 4 * lanes + lanes * 8 * max(nv, 1)) if chunks else 0      # padding of the sorted array, tail keys, tail values
+        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + tails + 64) // 16 * 16 + 16
 
 
 def sort_groups(plans, options):
@@ -829,14 +832,15 @@ def choose_strategies(plans, options, prog=None, layout=None):
             sgroups = sgroups[:int(options.get("sort_max_groups", SORT_MAX_GROUPS))]
             staged = stage_values(prog, sgroups)
             # the block's warps are dealt out to the groups (4 warps = 128 lanes per group for c4's 8 groups)
+            sort_chunks = options.get("sort_sum", SORT_SUM) == "chunks"
             if sort_lanes == "auto":
                 lanes = 32
-                while lanes * 2 <= min(256, int(options.get("sort_threads", SORT_THREADS)) // len(sgroups)):
+                while lanes * 2 <= min(64 if sort_chunks else 256, int(options.get("sort_threads", SORT_THREADS)) // len(sgroups)):
                     lanes *= 2
             else:
                 lanes = int(sort_lanes)
             for slots in (group_slots, min(group_slots, 8)):
-                sort_bytes = sum(g.smem_bytes(sort_tile, lanes) for g in sgroups) + 8 * len(staged) * sort_tile + 64
+                sort_bytes = sum(g.smem_bytes(sort_tile, lanes, sort_chunks) for g in sgroups) + 8 * len(staged) * sort_tile + 64
                 if sort_bytes + direct_need(slots) <= sort_cap:
                     break
             if sort_bytes + 16 * 1024 <= sort_cap:
@@ -1003,10 +1007,16 @@ def choose_strategies(plans, options, prog=None, layout=None):
         for g in sgroups:
             g.off["sorted"] = used
             used += (2 * sort_tile + 15) // 16 * 16
+            if options.get("sort_sum", SORT_SUM) == "chunks":
+                used += (4 * sort_lanes + 15) // 16 * 16                  # every lane's chunk is followed by 4 bytes of padding (HB_SPOS)
+                g.off["tkey"] = used
+                used += (4 * sort_lanes + 15) // 16 * 16
+                g.off["tval"] = used
+                used += 8 * sort_lanes * max(len(g.values), 1)
         e_off = used
         used += 8 * len(staged) * sort_tile
         sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "e_off": e_off, "tile": sort_tile,
-                       "lanes": sort_lanes, "threads": int(options.get("sort_threads", SORT_THREADS)),
+                       "lanes": sort_lanes, "chunks": options.get("sort_sum", SORT_SUM) == "chunks", "threads": int(options.get("sort_threads", SORT_THREADS)),
                        "ept": int(options.get("sort_ept", SORT_EPT))}
         if layout is not None:
             layout.update(sort_layout)
@@ -1327,6 +1337,16 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("#define HB_LANES %d" % lanes)
     src.append("#define HB_NSG %d" % G)
     src.append("#define HB_FXMISS (reinterpret_cast<hb_u32*>(hb_smem))")
+    chunks = bool(layout.get("chunks"))
+    chunk = tile // lanes
+    if chunks:
+        # where sorted position `pos` lives in a group's array of event numbers: the chunks of consecutive lanes are an odd
+        # number of 32-bit words apart, so the 32 lanes of a warp, each reading its own chunk, hit 32 different banks
+        # (unpadded: 16-way conflicts, a quarter of the kernel's shared-memory wavefronts)
+        assert chunk * lanes == tile
+        src.append("#define HB_SPOS(pos) ((pos) + (((pos) / %du) << 1))" % chunk)
+    else:
+        src.append("#define HB_SPOS(pos) (pos)")
     src.extend(prog.consts)
     src.append("")
     sig = ["const HbParams& p", "unsigned char* hb_smem", "const bool live", "const int eid", "hb_u32 (&kr)[HB_NSG]"]
@@ -1387,11 +1407,61 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("        // 3. scatter the event numbers to start[bin] + rank")
     for k in range(ept):
         for g in groups:
-            src.append("        if (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[sp] = (unsigned short)(%d * HB_THREADS + threadIdx.x); }" % (
+            src.append("        if (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[HB_SPOS(sp)] = (unsigned short)(%d * HB_THREADS + threadIdx.x); }" % (
                 k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
     src.append("        __syncthreads();")
+    if chunks:
+        # the balanced variant: every lane walks a contiguous chunk of the sorted events; a run that ends inside the chunk is
+        # flushed on the spot (it ends in no other lane's chunk), a run that goes on in the next lane is a "tail", added
+        # after the group's barrier by the first lane that holds a tail of that bin
+        src.append("        // 4. chunked sums over the sorted events")
+        for g in groups:
+            nv = len(g.values)
+            wg = g.gid % nwg
+            used_slots = sorted(set(k for kind, k in g.stage))
+            src.append("        if (hb_wg == %d) {   // sort group %d" % (wg, g.gid))
+            src.append("            const hb_u32* const st = reinterpret_cast<const hb_u32*>(hb_smem + %d);" % g.off["tick"])
+            src.append("            const unsigned short* const so = reinterpret_cast<const unsigned short*>(hb_smem + %d);" % g.off["sorted"])
+            src.append("            double* const acc = reinterpret_cast<double*>(hb_smem + %d);" % g.off["acc"])
+            src.append("            int* const tkeys = reinterpret_cast<int*>(hb_smem + %d);" % g.off["tkey"])
+            src.append("            double* const tvals = reinterpret_cast<double*>(hb_smem + %d);" % g.off["tval"])
+            src.append("            const hb_u32 ng = st[%d];" % g.nbins)
+            src.append("            const hb_u32 p0 = (hb_u32)hb_l * %du, p1 = min(p0 + %du, ng);" % (chunk, chunk))
+            src.append("            " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
+            src.append("            int tkey = -1;")
+            flush = " ".join("acc[%d + key] += a%d; a%d = 0.0;" % (j * g.nbins, j, j) for j in range(nv))
+            src.append("            if (p0 < ng) {")
+            src.append("                int key = hb_sort_find(st, %d, p0);" % g.nbins)
+            src.append("                hb_u32 runend = st[key + 1];")
+            src.append("                for (hb_u32 pos = p0; pos < p1; ++pos) {")
+            src.append("                    if (pos >= runend) {       // the run of `key` ends in this lane's chunk, and in no other lane's")
+            src.append("                        " + flush)
+            src.append("                        do { ++key; runend = st[key + 1]; } while (pos >= runend);")
+            src.append("                    }")
+            src.append("                    const unsigned e = so[HB_SPOS(pos)];")
+            for k in used_slots:
+                src.append("                    const double v%d = reinterpret_cast<const double*>(hb_smem + %d)[e];" % (k, layout["e_off"] + 8 * k * tile))
+            for j, (kind, k) in enumerate(g.stage):
+                if kind == "E":
+                    src.append("                    a%d += v%d;" % (j, k))
+                else:
+                    src.append("                    a%d += hb_mul<double>(v%d, v%d);" % (j, k, k))
+            src.append("                }")
+            src.append("                if (runend > p1) tkey = key;       // the run goes on in the next lane: a tail")
+            src.append("                else { %s }" % flush)
+            src.append("            }")
+            src.append("            tkeys[hb_l] = tkey;")
+            src.append("            if (tkey >= 0) { %s }" % " ".join("tvals[%d + hb_l] = a%d;" % (j * lanes, j) for j in range(nv)))
+            src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))
+            src.append("            for (int b = hb_l; b <= %d; b += HB_LANES) reinterpret_cast<hb_u32*>(hb_smem + %d)[b] = 0u;" % (g.nbins, g.off["tick"]))
+            src.append("            if (tkey >= 0 && (hb_l == 0 || tkeys[hb_l - 1] != tkey)) {")
+            src.append("                const int key = tkey;")
+            src.append("                for (int m = hb_l + 1; m < HB_LANES && tkeys[m] == key; ++m) { %s }" % " ".join("a%d += tvals[%d + m];" % (j, j * lanes) for j in range(nv)))
+            src.append("                " + flush)
+            src.append("            }")
+            src.append("        }")
     src.append("        // 4. every lane of a group's warps sums the runs of its bins")
-    for g in groups:
+    for g in ([] if chunks else groups):
         nv = len(g.values)
         wg = g.gid % nwg
         used_slots = sorted(set(k for kind, k in g.stage))

@@ -302,9 +302,13 @@ class Arena(object):
         return {"shape": (int(self.size),), "typestr": "<f8", "data": (int(self.ptr or 0), False), "version": 3, "strides": None}
 
     def as_tensor(self):
-        """Zero-copy torch view (for torch.distributed collectives over NCCL)."""
+        """Zero-copy torch view (for torch.distributed collectives over NCCL); cached until the arena moves or grows."""
         import torch
-        return torch.as_tensor(self, device="cuda:%d" % init())
+        ptr, size = self.ptr, self.size
+        cached = getattr(self, "_view", None)
+        if cached is None or cached[0] != ptr or cached[1] != size:
+            cached = self._view = (ptr, size, torch.as_tensor(self, device="cuda:%d" % init()))
+        return cached[2]
 
 
 class KeySet(object):

@@ -18,6 +18,7 @@ from histbook_b200.store import GroupInfo, Store
 _options = dict(json.loads(os.environ.get("HB_OPTIONS", "") or "{}"))
 _lock = threading.RLock()
 last_stats = {}
+TIMED = False                   # measurement: bracket every fill's launches with CUDA events (last_stats["ms_kernel"]); costs a device sync
 
 
 def set_options(**kwargs):
@@ -103,11 +104,11 @@ class Plan(object):
     def parts_for(self, cols):
         """None, or the parts this book is filled in: [(Plan, histogram indices)].  A book is split
         * when it has more histograms than one kernel's parameter block takes (each part at most PART_MAX_HISTS), or
-        * when it is a big book with at least ``parts_min_groups`` sort groups: two half-books, each filled by 512-thread
-          blocks, two per SM with their own tiles, so that one block's arithmetic (evaluate, index, tickets) overlaps the
-          other's shared-memory traffic (the sums over the sorted events) -- one 1024-thread block runs its phases one
-          after the other and waits at every barrier (kernels only, 1e8 events: 9.4 ms whole, 2 x 4.15 ms in halves;
-          tools/parts_probe.py).
+        * when asked to (option ``parts`` = 2, 4): a big book with at least ``parts_min_groups`` sort groups as half-books,
+          each filled by 512-thread blocks, two per SM with their own tiles, so that one block's arithmetic (evaluate,
+          index, tickets) overlaps the other's shared-memory traffic (the sums over the sorted events) -- the one
+          1024-thread block runs its phases one after the other and waits at every barrier (kernels only, 1e8 events:
+          9.4 ms whole, 2 x 4.15 ms in halves; tools/parts_probe.py).  Not the default: the parts re-read the columns.
         All parts are filled in ONE pass over the columns (engine.fill_multi): every chunk is staged once."""
         self._fresh()
         sig = tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields)
@@ -119,14 +120,17 @@ class Plan(object):
                 k = 1
             elif self.nhists > PART_MAX_HISTS:
                 k = -(-self.nhists // PART_MAX_HISTS)
-            if k == 1 and not self.options.get("_part") and want not in (1, False) and not options.get("deterministic", False):
+            if k == 1 and not self.options.get("_part") and want not in (1, False, "auto") and not options.get("deterministic", False):
+                # asked for (parts=2): a big book as half-books of 512-thread blocks, two per SM.  Measured on c4: 11.4 against
+                # 10.9 Gev/s for the one 1024-thread kernel -- but every part reads the columns again (2.0x the DRAM traffic
+                # of the single pass), so the default stays ONE fused pass over the columns.
                 coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in self.fields)
                 try:
                     kern = codegen.generate(self.spec, coltypes, options)
                 except codegen.UnsupportedError:
                     kern = None
                 if kern is not None and kern.sorted and len(kern.sorted["groups"]) >= int(options.get("parts_min_groups", 4)):
-                    k = int(want) if want != "auto" else 2
+                    k = int(want)
                     extra = {"sort_threads": int(options.get("parts_threads", 512)), "sort_min_blocks": int(options.get("parts_min_blocks", 2)),
                              "sort_ept": int(options.get("parts_ept", codegen.SORT_EPT)), "sort": True}
             if k <= 1:
@@ -479,6 +483,7 @@ def _fill_parts(plan, parts, hists, cols, length, timed):
 def fill_hists(plan, hists, arrays, timed=False):
     """One pass over ``arrays`` filling every histogram in ``hists`` (deduplicated, in plan order)."""
     with _lock:
+        timed = timed or TIMED
         arrays = _encode_strings(plan, arrays)
         cols, length = columns.bind_all(plan.fields, arrays)
         parts = plan.parts_for(cols)

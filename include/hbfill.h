@@ -152,7 +152,7 @@ typedef struct {
     const int32_t* win;
 } hb_launch;
 int hb_fill_multi(int nlaunch, const hb_launch* launches, int ncols, const hb_column* cols, int64_t n, int flags, hb_stats* stats);
-/* worker threads that copy pageable host columns into the page-locked bounce ring (default: min(8, cores / 2);
+/* worker threads that copy pageable host columns into the page-locked bounce ring (default: 12, or 3/4 of the cores on small hosts;
  * environment HB_COPY_THREADS) */
 int hb_set_copy_threads(int n);
 

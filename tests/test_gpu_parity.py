@@ -201,8 +201,8 @@ OPTION_SETS = [
     {"fx": False}, {"fx": True}, {"fx": "mix"}, {"window": False}, {"win_dense": True}, {"win_pair": False}, {"merge_pair": False},
     {"win_table32": False}, {"pair_red": False}, {"prefetch": True}, {"replicas": 2}, {"f64_atomic": "exch"}, {"unroll": 1},
     {"unroll": 0}, {"evict_first": False}, {"red_evict_last": True}, {"group_slots": 2}, {"threads": 256, "min_blocks": 4},
-    {"smem_budget": 16384}, {"block_times": True}, {"sort": True}, {"sort": True, "sort_lanes": 256}, {"sort": True, "sort_lanes": 32},
-    {"sort": True, "sort_ept": 1}, {"sort": True, "sort_split": 1}, {"sort": True, "sort_split": 16}, {"sort": False},
+    {"smem_budget": 16384}, {"block_times": True}, {"sort": True}, {"sort": True, "sort_lanes": 128}, {"sort": True, "sort_lanes": 32},
+    {"sort": True, "sort_ept": 1}, {"sort": True, "sort_sum": "bins", "sort_split": 1}, {"sort": True, "sort_sum": "bins", "sort_split": 16}, {"sort": True, "sort_sum": "bins"}, {"sort": True, "sort_sum": "chunks", "sort_lanes": 32}, {"sort": True, "sort_sum": "bins", "sort_lanes": 256}, {"sort": False},
 ]
 
 
@@ -267,8 +267,8 @@ def test_golden_sorted_strategy(name):
     compare(name, case["spec"], got, golden_util.outputs(case), bound)
 
 
-@pytest.mark.parametrize("lanes", [32, 128])
-def test_sorted_strategy_on_degenerate_distributions(lanes):
+@pytest.mark.parametrize("lanes,summing", [(32, "bins"), (128, "bins"), (64, "chunks"), (128, "chunks")])
+def test_sorted_strategy_on_degenerate_distributions(lanes, summing):
     """Every event in ONE bin, two alternating bins, masked rows, NaN weights, tiles with a single live event, more
     bins than lanes: the counting sort and the bin ownership of codegen.SortGroup."""
     from histbook_b200 import fillable
@@ -276,7 +276,7 @@ def test_sorted_strategy_on_degenerate_distributions(lanes):
     spec = dict(cases["c4"]["spec"], hists=cases["c4"]["spec"]["hists"][:8])
     rs = numpy.random.RandomState(3)
     try:
-        fillable.set_options(sort=True, sort_lanes=lanes)
+        fillable.set_options(sort=True, sort_lanes=lanes, sort_sum=summing)
         for n in (1, 31, 2048, 2049, 4096 + 64, 303104 + 17, 700001):
             variants = []
             const = {"x": numpy.full(n, 0.25), "y": numpy.full(n, -0.75), "z": numpy.full(n, 1.5), "w": numpy.full(n, 1.25), "n": numpy.full(n, 4, dtype=numpy.int64)}
@@ -297,7 +297,7 @@ def test_sorted_strategy_on_degenerate_distributions(lanes):
                     bound = fill_oracle.fill(spec, a, bound, absolute=True)
                 compare("degenerate n=%d" % n, spec, got, [golden_util.flatten(e) for e in exp], bound)
     finally:
-        fillable.set_options(sort=None, sort_lanes=None)
+        fillable.set_options(sort=None, sort_lanes=None, sort_sum=None)
 
 
 def test_book_of_320_histograms_is_split_into_parts():
@@ -320,7 +320,7 @@ def test_book_of_320_histograms_is_split_into_parts():
 
 
 def test_half_books_agree_with_the_single_kernel():
-    """c4 is filled as two half-books side by side (parts="auto"); parts=1 forces the single 1024-thread kernel: same bins."""
+    """parts=2 fills c4 as two half-books (512-thread blocks, two per SM); the default is the single 1024-thread kernel: same bins."""
     from histbook_b200 import fillable
     spec = golden_util.load()["c4"]["spec"]
     rs = numpy.random.RandomState(23)
@@ -329,17 +329,17 @@ def test_half_books_agree_with_the_single_kernel():
             "w": rs.uniform(0.5, 1.5, n), "n": rs.poisson(3, n).astype(numpy.int64)}
     out = {}
     try:
-        for parts in ("auto", 1):
+        for parts in (2, 1):
             fillable.set_options(parts=parts)
             sf = fillable.SpecFill(spec)
             sf.fill(cols)
             sf.fill(dict((k, v[:1000]) for k, v in cols.items()))
-            assert fillable.last_stats.get("parts", 1) == (2 if parts == "auto" else 1)
+            assert fillable.last_stats.get("parts", 1) == parts
             out[parts] = sf.contents()
     finally:
         fillable.set_options(parts=None)
     bound = fill_oracle.fill(spec, cols, absolute=True)
-    for hid, (a, b, bd) in enumerate(zip(out["auto"], out[1], bound)):
+    for hid, (a, b, bd) in enumerate(zip(out[2], out[1], bound)):
         fa, fb, fbd = golden_util.flatten(a), golden_util.flatten(b), golden_util.flatten(bd)
         assert [k for k, _ in fa] == [k for k, _ in fb]
         for (k, x), (_, y), (_, z) in zip(fa, fb, fbd):
