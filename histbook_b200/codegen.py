@@ -445,6 +445,9 @@ class Program(object):
                 vv = self.new("sv")
                 self.body.append("const %s %s = %s;" % (ctype(cmp_t), vv, self.cast(v, cmp_t)))
                 lits = [lit(e, cmp_t) for e in numpy.array(edges).astype(cmp_t).tolist()]
+
+                # (a decision tree of nested selects, one compare per edge and half the instructions on paper, compiles to
+                #  branches: c4 11.2 instead of 12.1 Gev/s)
                 count = " + ".join("(int)(%s <= %s)" % (e, vv) for e in lits)
                 onedge = " || ".join("(%s == %s)" % (e, vv) for e in lits)
                 self.body.append("const int %s = hb_split_index<%s>(%s, %s, %s, %d, %s);" % (
@@ -731,8 +734,8 @@ class SortGroup(object):
 
     def smem_bytes(self, tile, lanes, chunks=False):
         nv = len(self.values)
-        tails = (4 * lanes + 4 * lanes + lanes * 8 * max(nv, 1)) if chunks else 0      # padding of the sorted array, tail keys, tail values
-        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + tails + 64) // 16 * 16 + 16
+        tails = (4 * lanes + lanes * 8 * max(nv, 1)) if chunks else 0      # tail keys, tail values
+        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + 4 * lanes + 32 + tails + 64) // 16 * 16 + 16
 
 
 def sort_groups(plans, options):
@@ -1003,19 +1006,20 @@ def choose_strategies(plans, options, prog=None, layout=None):
         for g in sgroups:
             g.off["tick"] = used
             used += (4 * (g.nbins + 1) + 15) // 16 * 16
+        dump_off = used                                   # where masked rows of count-only histograms and masked tickets add (never read)
+        used += 16
         zero_end = used
         for g in sgroups:
             g.off["sorted"] = used
-            used += (2 * sort_tile + 15) // 16 * 16
+            used += (2 * sort_tile + 15) // 16 * 16 + 4 * sort_lanes + 32     # (+ room for the chunk padding of HB_SPOS and the dump slot of masked events)
             if options.get("sort_sum", SORT_SUM) == "chunks":
-                used += (4 * sort_lanes + 15) // 16 * 16                  # every lane's chunk is followed by 4 bytes of padding (HB_SPOS)
                 g.off["tkey"] = used
                 used += (4 * sort_lanes + 15) // 16 * 16
                 g.off["tval"] = used
                 used += 8 * sort_lanes * max(len(g.values), 1)
         e_off = used
         used += 8 * len(staged) * sort_tile
-        sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "e_off": e_off, "tile": sort_tile,
+        sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "dump_off": dump_off, "e_off": e_off, "tile": sort_tile,
                        "lanes": sort_lanes, "chunks": options.get("sort_sum", SORT_SUM) == "chunks", "threads": int(options.get("sort_threads", SORT_THREADS)),
                        "ept": int(options.get("sort_ept", SORT_EPT))}
         if layout is not None:
@@ -1360,12 +1364,18 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     for g in groups:
         src.append("    // ---- sort group %d: %d bins, %d values, histograms %s" % (g.gid, g.nbins, len(g.values), [hp.hid for hp in g.members]))
         src.append("    {")
-        src.append("        hb_u32 t = 0xffffffffu;")
-        src.append("        if (%s) {" % " && ".join(["live"] + g.conds))
-        src.append("            const int bin = %s;" % g.idx)
-        src.append("            t = ((hb_u32)bin << 16) | atomicAdd(reinterpret_cast<hb_u32*>(hb_smem + %d) + bin, 1u);" % g.off["tick"])
-        src.append("        }")
-        src.append("        kr[%d] = t;" % g.gid)
+        if options.get("sort_branchfree", True):
+            src.append("        const bool okr = %s;" % " && ".join(["live"] + g.conds))
+            src.append("        const int bin = okr ? (%s) : 0;" % g.idx)
+            src.append("        const hb_u32 rank = atomicAdd(reinterpret_cast<hb_u32*>(hb_smem + (okr ? %d + 4 * bin : %d)), 1u);" % (g.off["tick"], layout["dump_off"]))
+            src.append("        kr[%d] = okr ? (((hb_u32)bin << 16) | rank) : 0xffffffffu;" % g.gid)
+        else:
+            src.append("        hb_u32 t = 0xffffffffu;")
+            src.append("        if (%s) {" % " && ".join(["live"] + g.conds))
+            src.append("            const int bin = %s;" % g.idx)
+            src.append("            t = ((hb_u32)bin << 16) | atomicAdd(reinterpret_cast<hb_u32*>(hb_smem + %d) + bin, 1u);" % g.off["tick"])
+            src.append("        }")
+            src.append("        kr[%d] = t;" % g.gid)
         src.append("    }")
     src.append("}\n")
 
@@ -1407,8 +1417,13 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("        // 3. scatter the event numbers to start[bin] + rank")
     for k in range(ept):
         for g in groups:
-            src.append("        if (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[HB_SPOS(sp)] = (unsigned short)(%d * HB_THREADS + threadIdx.x); }" % (
-                k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
+            if options.get("sort_branchfree", True):
+                # (an event that is masked for this group writes its number to a dump slot behind the array)
+                src.append("        { const bool v = kr%d[%d] != 0xffffffffu; const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[v ? (kr%d[%d] >> 16) : 0u] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[v ? HB_SPOS(sp) : %du] = (unsigned short)(%d * HB_THREADS + threadIdx.x); }" % (
+                    k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], tile + 2 * lanes + 4, k))
+            else:
+                src.append("        if (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[HB_SPOS(sp)] = (unsigned short)(%d * HB_THREADS + threadIdx.x); }" % (
+                    k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
     src.append("        __syncthreads();")
     if chunks:
         # the balanced variant: every lane walks a contiguous chunk of the sorted events; a run that ends inside the chunk is
@@ -1850,6 +1865,28 @@ def generate(spec, coltypes, options=None):
             nz = ["(%s != 0.0)" % e for e in hp.terms if e is not None]
             if nz and len(nz) == len(hp.terms):
                 conds = conds + ["(%s)" % " || ".join(nz)]
+        if (layout and hp.strategy == "smem" and not hp.groups and not hp.f64_terms and hp.count_term is not None and hp.replicas == 1
+                and options.get("sort_branchfree", True)):
+            # big books: a count-only histogram is ONE unconditional native atomic -- a masked row adds to a dump word -- instead
+            # of a branch around it (BSSY / BRA / BSYNC were 13 % of the instructions of the event phase, profiles/r02_c4_ncu.txt)
+            ev.append("    hb_sadd_u32(reinterpret_cast<hb_u32*>(hb_smem + ((%s) ? %d + 4 * (%s) : %d)), 1u);" % (
+                " && ".join(conds), hp.smem_f64_off, idx, layout["dump_off"]))
+            ev.append("}")
+            continue
+        if (layout and hp.strategy == "smem" and hp.groups and not hp.f64_terms and hp.count_term is not None
+                and options.get("sort_branchfree", True)):
+            # the same for a count-only histogram with group axes: slots below the privatised ones take the unconditional atomic,
+            # the (rare) rest the global path
+            ev.append("    const bool okr = %s;" % " && ".join(conds))
+            ev.append("    const bool insm = okr && slot < %d;" % hp.gcap)
+            ev.append("    hb_sadd_u32(reinterpret_cast<hb_u32*>(hb_smem + (insm ? %d + 4 * (slot * %d + (%s)) : %d)), 1u);" % (
+                hp.smem_f64_off, hp.nbins, idx, layout["dump_off"]))
+            ev.append("    if (okr && !insm) {")
+            ev.append("        const int bin = %s;" % idx)
+            ev.extend(_emit_global_adds(hp, options, "(hb_i64)slot * %d + bin" % hp.nbins, "        "))
+            ev.append("    }")
+            ev.append("}")
+            continue
         ev.append("    if (%s) {" % (" && ".join(conds) if conds else "true"))
         ev.append("        const int bin = %s;" % idx)
         if hp.strategy == "smem":
