@@ -128,6 +128,8 @@ extern "C" int hb_init(int device) {
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(HB_ERR_ARG, "no such CUDA device");
+    if (g_device >= 0 && g_device != device)
+        return fail(HB_ERR_ARG, "the engine is bound to cuda:" + std::to_string(g_device) + " (one process per GPU: streams, staging and arenas live there)");
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaFree(0));                        // make the primary context current
     if (g_device != device) {

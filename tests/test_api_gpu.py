@@ -506,3 +506,64 @@ def test_serialisation_keeps_the_device_copy():               # Hist.tojson / __
     assert sorted(j["content"]) == ["a", "b", "c"] and sum(sum(r[0] for r in v) for v in j["content"].values()) == 4.0
     h.fill(**cols)                                                # no upload in between: still the same arena, twice the weight
     assert h.__dict__["_hb"] is st and abs(h._content[..., 0].sum() - 2 * cols["w"].sum()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# the behaviours DESIGN.md section 8 lists as chosen where the reference has none (or a different one): pinned here
+
+def test_chosen_behaviours_where_the_reference_differs():
+    # profile axis + masked rows: the reference raises (weight compressed, sumx not; hist.py:429-440); here masked rows are skipped
+    h = Hist(bin("x", 2, 0, 1, underflow=False, overflow=False, nanflow=False), profile("y"))
+    cols = {"x": numpy.array([-1.0, 0.2, 0.7, 5.0, numpy.nan]), "y": numpy.array([1.0, 2.0, 3.0, 4.0, 5.0])}
+    h.fill(**cols)
+    assert h._content.tolist() == [[2.0, 4.0, 1.0], [3.0, 9.0, 1.0]]
+    with histbook_b200.reference_path() as hb:
+        r = hb.Hist(hb.bin("x", 2, 0, 1, underflow=False, overflow=False, nanflow=False), hb.profile("y"))
+        with pytest.raises(ValueError):
+            r.fill(**cols)
+    # groupby on a float key that holds NaN: ONE NaN key however many fills (the reference adds a key per fill: nan != nan)
+    g = Hist(groupby("k"), bin("x", 2, 0, 1))
+    for _ in range(3):
+        g.fill(k=numpy.array([1.5, numpy.nan, numpy.nan]), x=numpy.array([0.1, 0.6, 0.7]))
+    keys = list(g._content)
+    assert len(keys) == 2 and sum(1 for k in keys if k != k) == 1
+    nan_key = [k for k in keys if k != k][0]
+    assert g._content[nan_key][:, 0].tolist() == [0.0, 0.0, 6.0, 0.0, 0.0]
+    # cut on a non-boolean column: values outside {0, 1} are masked (the reference indexes outside the axis)
+    c = Hist(cut("p"))
+    c.fill(p=numpy.array([0, 1, 1, 2, -1, 7], dtype=numpy.int64))
+    assert c._content.tolist() == [[1.0], [2.0]]
+    # Book.fill honours copy-on-fill (the reference's Book.fill writes into the shared content, book.py:582-586)
+    a = Hist(bin("x", 2, 0, 1))
+    a.fill(x=[0.1])
+    b = a.copyonfill()
+    book = Book(b=b)
+    book.fill(x=[0.7, 0.8])
+    assert a._content[:, 0].tolist() == [0.0, 1.0, 0.0, 0.0, 0.0] and b._content[:, 0].tolist() == [0.0, 1.0, 2.0, 0.0, 0.0]
+    # one Hist under two names of a Book is filled once
+    one = Hist(bin("x", 2, 0, 1))
+    twice = Book(first=one, second=one)
+    twice.fill(x=[0.2, 0.3])
+    assert one._content[:, 0].sum() == 2.0
+
+
+@pytest.mark.parametrize("expr,lo,hi", [("sin(x)", -1, 1), ("cos(x)", -1, 1), ("tan(x)", -5, 5), ("exp(x)", 0, 20), ("log(abs(x) + 0.001)", -7, 2),
+                                        ("log10(abs(x) + 0.001)", -3, 1), ("tanh(x)", -1, 1), ("arctan2(x, y)", -3.2, 3.2), ("hypot(x, y)", 0, 5),
+                                        ("pow(abs(x), 2.5)", 0, 10), ("erf(x)", -1, 1), ("sinh(x)", -5, 5), ("arcsin(x / 5)", -1.6, 1.6)])
+def test_libm_class_functions_at_ten_million_events(expr, lo, hi):
+    """sin, exp, log, pow, hypot, arctan2 ... are CUDA's libm on the device and numpy's SIMD loops in the reference:
+    both are accurate to 1-2 ulp but not identical, so an event whose value lies within ~2 ulp of a bin edge may land
+    in the neighbouring bin.  With 100 bins that is ~1e-13 of the events: at 1e7 events the histograms must have equal
+    totals and differ by at most 2 moved events (4 units of |difference|) -- stated per function, measured here."""
+    rs = numpy.random.RandomState(77)
+    n = 10**7
+    cols = {"x": rs.normal(0, 1.5, n), "y": rs.normal(0, 1.5, n)}
+    h = Hist(bin(expr, 100, lo, hi))
+    h.fill(**cols)
+    with histbook_b200.reference_path() as hb:
+        r = hb.Hist(hb.bin(expr, 100, lo, hi))
+        r.fill(**cols)
+        exp = r._content
+    got = h._content
+    assert got.sum() == exp.sum() == n
+    assert numpy.abs(got - exp).sum() <= 4, (expr, float(numpy.abs(got - exp).sum()))

@@ -144,35 +144,54 @@ def test_c5_full_size():
 
 
 def test_c4_full_size_book():
+    """All 64 histograms of the north-star book at 1e9 events against plain torch: every count bit-exact (bin, split,
+    bin x intbin, bin x cut, groupbin x bin), every weighted, filtered and profile column within 1e-12 of the per-bin sum
+    of |term|.  The eight axis expressions are evaluated as histbook's normal form orders them."""
     torch = _torch()
     n = 10**9
     spec = golden_util.load()["c4"]["spec"]
     assert len(spec["hists"]) == 64
     cols = _columns(["n", "w", "x", "y", "z"], n, 12345)
     got = _fill(spec, cols)
-    checked = 0
-    for h, content in zip(spec["hists"], got):
-        if h["weight"] is not None or h["profile"]:
-            continue
-        if h["group"]:
-            # groupbin("n", 2) x bin: every event has exactly one key and one bin
-            assert isinstance(content, dict) and len(content) >= 5
-            assert sum(float(v.sum()) for v in content.values()) == n
-            checked += 1
-            continue
-        # unweighted, all flow bins on: the counts add up to the number of events, exactly
-        assert float(content.sum()) == n
-        checked += 1
-        fixed = h["fixed"]
-        if len(fixed) == 1 and fixed[0]["kind"] == "bin" and fixed[0]["goal"][2][0] == "name":
-            name = fixed[0]["goal"][2][1]
-            numbins, low, high = (fixed[0]["goal"][k][1] for k in (3, 4, 5))
-            exp = torch.bincount(_bin(cols[name], numbins, low, high), minlength=numbins + 3).cpu().numpy()
-            assert numpy.array_equal(content[:, 0], exp.astype(numpy.float64))
-    assert checked >= 30
-    # a weighted member of the book against torch: Hist(bin("x",100,-5,5), weight="w")
-    h1 = spec["hists"][1]
-    assert h1["weight"] is not None and h1["fixed"][0]["goal"][2] == ["name", "x"]
-    idx = _bin(cols["x"], 100, -5, 5)
-    _check_sum(got[1][:, 0], idx, cols["w"], 103)
-    _check_sum(got[1][:, 1], idx, cols["w"] * cols["w"], 103)
+    x, y, z, w, nn = cols["x"], cols["y"], cols["z"], cols["w"], cols["n"]
+    edges = torch.tensor([-2, -1, -0.5, 0, 0.5, 1, 2], dtype=torch.float64, device="cuda")
+    nbin = (nn + 1).clamp_(0, 11)                            # intbin("n", 0, 9): [under][0..9][over]
+    zpos = (z > 0).to(torch.int64)
+    gkey = torch.floor(nn.to(torch.float64) * 0.5) * 2.0     # groupbin("n", 2)
+    keys = sorted(float(k) for k in torch.unique(gkey).cpu().numpy())
+    fw = torch.where(nn >= 3, w, torch.zeros_like(w))        # where(n >= 3, 1, 0) * w
+    exprs = [lambda: x, lambda: y, lambda: z, lambda: x + y, lambda: x - y, lambda: x * y,
+             lambda: torch.sqrt(x * x + y * y), lambda: torch.sqrt(x * x + (y * y + z * z))]
+    for e, make in enumerate(exprs):
+        v = make()
+        i100, i50 = _bin(v, 100, -5, 5), _bin(v, 50, -5, 5)
+        h = got[8 * e: 8 * e + 8]
+        # 0: Hist(bin(e, 100, -5, 5))
+        c100 = torch.bincount(i100, minlength=103).cpu().numpy().astype(numpy.float64)
+        assert numpy.array_equal(h[0][:, 0], c100) and h[0].sum() == n, e
+        # 1: weight="w"
+        _check_sum(h[1][:, 0], i100, w, 103)
+        _check_sum(h[1][:, 1], i100, w * w, 103)
+        # 2: split(e, (-2, -1, -0.5, 0, 0.5, 1, 2)): [under][6 finite][over][nan]
+        isplit = torch.bucketize(v, edges, right=True)
+        assert numpy.array_equal(h[2][:, 0], torch.bincount(isplit, minlength=9).cpu().numpy().astype(numpy.float64)), e
+        del isplit
+        # 3: bin(e, 50) x intbin("n", 0, 9)
+        assert numpy.array_equal(h[3].reshape(-1), torch.bincount(i50 * 12 + nbin, minlength=53 * 12).cpu().numpy().astype(numpy.float64)), e
+        # 4: bin(e, 50) x cut("z > 0")
+        assert numpy.array_equal(h[4].reshape(-1), torch.bincount(i50 * 2 + zpos, minlength=106).cpu().numpy().astype(numpy.float64)), e
+        # 5: bin(e, 100), profile("z"): [sum z, sum z^2, count]
+        _check_sum(h[5][:, 0], i100, z, 103)
+        _check_sum(h[5][:, 1], i100, z * z, 103)
+        assert numpy.array_equal(h[5][:, 2], c100), e
+        # 6: groupbin("n", 2) x bin(e, 50): one block per key, keys as the reference spells them
+        assert sorted(float(k) for k in h[6]) == keys, e
+        for k, block in h[6].items():
+            sel = gkey == float(k)
+            assert numpy.array_equal(block[:, 0], torch.bincount(i50[sel], minlength=53).cpu().numpy().astype(numpy.float64)), (e, k)
+            del sel
+        # 7: bin(e, 100), filter="n >= 3", weight="w"
+        _check_sum(h[7][:, 0], i100, fw, 103)
+        _check_sum(h[7][:, 1], i100, fw * fw, 103)
+        del v, i100, i50
+        torch.cuda.empty_cache()
