@@ -100,12 +100,21 @@ def _book_fill(self, arrays=None, **more):
         pass
     else:
         arrays = hb.util.ChainedDict(arrays, more)
-    hists = _book_hists(self)
-    ids = tuple(id(h) for h in hists)
     cached = self.__dict__.get("_hb_plan")
-    if cached is None or cached[0] != ids:
-        cached = self.__dict__["_hb_plan"] = (ids, fillable.Plan(hists), hists)
-    fillable.fill_hists(cached[1], hists, arrays)
+    if cached is None or type(self).__dict__.get("_changed") is not _book_changed:
+        # (Book._changed drops the cached plan whenever an entry is set or deleted; book classes with their own
+        #  _changed -- SystematicsBook -- are walked at every fill instead)
+        hists = _book_hists(self)
+        ids = tuple(id(h) for h in hists)
+        if cached is None or cached[0] != ids:
+            cached = self.__dict__["_hb_plan"] = (ids, fillable.Plan(hists), hists)
+    fillable.fill_hists(cached[1], cached[2], arrays)
+
+
+def _book_changed(self):
+    """``Book._changed`` (histbook/book.py:526-527: invalidates the instruction program) + the cached device plan."""
+    self._fields = None
+    self.__dict__.pop("_hb_plan", None)
 
 
 def _hist_copy(self):
@@ -332,6 +341,7 @@ def install():
         "Hist.__add__": Hist.__dict__["__add__"], "Hist.__iadd__": Hist.__dict__["__iadd__"],
         "Hist.__mul__": Hist.__dict__["__mul__"], "Hist.__imul__": Hist.__dict__["__imul__"],
         "Hist.tojson": Hist.__dict__["tojson"], "Hist.__getstate__": Hist.__dict__["__getstate__"],
+        "Book._changed": Book.__dict__["_changed"],
     })
     Hist._content = property(_content_get, _content_set)
     Hist.fill = _hist_fill
@@ -341,6 +351,7 @@ def install():
     Hist.project = _hist_project
     Hist.__add__, Hist.__iadd__, Hist.__mul__, Hist.__imul__ = _hist_add, _hist_iadd, _hist_mul, _hist_imul
     Hist.tojson, Hist.__getstate__ = _hist_tojson, _hist_getstate
+    Book._changed = _book_changed
     _installed = True
 
 
@@ -360,6 +371,7 @@ def uninstall():
     del Hist.project                      # falls back to the inherited Projectable.project
     for name in ("__add__", "__iadd__", "__mul__", "__imul__", "tojson", "__getstate__"):
         setattr(Hist, name, _originals["Hist." + name])
+    Book._changed = _originals["Book._changed"]
     _installed = False
 
 

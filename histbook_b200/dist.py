@@ -108,6 +108,9 @@ SCATTER_BYTES = 8 << 20     # contents at least this large are reduce-scattered,
 def _hists_of(target):
     if isinstance(target, (list, tuple)):
         return list(target)
+    plan = getattr(target, "__dict__", {}).get("_hb_plan")
+    if isinstance(plan, tuple) and len(plan) == 3 and hasattr(target, "itervalues"):
+        return plan[2]                                         # a Book that has been filled: the histogram list of its plan (no walk)
     if hasattr(target, "hists"):                               # fillable.SpecFill
         return list(target.hists)
     if hasattr(target, "itervalues"):                          # Book: one Hist stored under several names counts once
@@ -196,6 +199,10 @@ class Merger(object):
         self.done = None
         self.device = device            # None: decided at the first start() (NCCL -> device, anything else -> host)
         self.layout = None              # [(hist, store, kind, offset, size, union order)] of the last start()
+        self._sig = None                # what the last start() saw (stores, arenas, key counts): reuse of its layout
+        self._entries = None
+        self._unions = None
+        self._fixed = None
         self.collectives = 0            # collectives issued so far
         self.collectives_last = 0       # ... by the last start()
         self._maps = {}
@@ -274,11 +281,16 @@ class Merger(object):
         hists = _hists_of(self.target)
         stores = [_store(h) for h in hists]
         before = self.collectives
+        # repeated merges of a book that is being filled: the stores, their arenas and key lists are usually the same as
+        # last time -- then everything below except the key exchange, the copies and the collective is reused
+        sig = tuple((id(st), st.dev_valid, st.host_valid, None if st.arena is None else st.arena.ptr, len(st.tuples)) for st in stores) if device else None
+        reuse = device and sig is not None and sig == self._sig
+        self._sig = sig
 
         # 1. what every histogram holds here: fixed-size blocks, or (pattern tuple -> block) for group axes
-        entries = []
-        group_entries = []
-        for h, st in zip(hists, stores):
+        entries = self._entries[0] if reuse else []
+        group_entries = self._entries[1] if reuse else []
+        for h, st in ([] if reuse else zip(hists, stores)):
             ngroup = _static_groups(h, st)
             if ngroup == 0:
                 if device:
@@ -315,6 +327,11 @@ class Merger(object):
                     st = entries[i][1]
                     unions[i] = [tuple(g.from_wire(w) for g, w in zip(st.groups, tup)) for tup in order] if st.groups else list(order)
 
+        if not reuse:
+            self._entries = (entries, group_entries)
+        reuse = reuse and unions == self._unions and self.flat is not None
+        self._unions = unions
+
         # 3. flat layout: [fixed blocks ...][group slabs in union order ...]
         off = 0
         layout = []
@@ -337,13 +354,19 @@ class Merger(object):
             dev = torch.device("cuda", engine.init())
             if self.flat is None or self.flat.numel() != padded or not self.flat.is_cuda:
                 self.flat = torch.empty(padded, device=dev, dtype=torch.float64)
+                self._fixed, reuse = None, False
             cur = torch.cuda.current_stream(dev)
             if self.done is not None:
                 cur.wait_event(self.done)                  # the previous collective has read the buffer
-            fixed = [(off_, st.arena.as_tensor()) for (h, st, kind, off_, size, order, tuples, blocks) in layout if kind == "fixed"]
-            if fixed:
-                first, last = fixed[0][0], fixed[-1][0] + fixed[-1][1].numel()
-                torch.cat([t for o, t in fixed], out=self.flat[first:last])
+            if reuse and self._fixed is not None:
+                tensors, target_slice = self._fixed
+            else:
+                fixed = [(off_, st.arena.as_tensor()) for (h, st, kind, off_, size, order, tuples, blocks) in layout if kind == "fixed"]
+                tensors = [t for o, t in fixed]
+                target_slice = self.flat[fixed[0][0]:fixed[-1][0] + fixed[-1][1].numel()] if fixed else None
+                self._fixed = (tensors, target_slice)
+            if tensors:
+                torch.cat(tensors, out=target_slice)
             for (h, st, kind, off_, size, order, tuples, blocks) in layout:
                 if kind != "group" or size == 0:
                     continue

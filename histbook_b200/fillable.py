@@ -63,6 +63,7 @@ class Plan(object):
                 g = a["goal"]
                 if a["kind"] == "groupby" and g[0] == "call" and g[1] == "histbook.groupby" and g[2][0] == "name":
                     self.groupby_fields[g[2][1]] = hbspec.tree_key(g)
+        self.goalkeys = [[hbspec.tree_key(a["goal"]) for a in h["group"]] for h in self.spec["hists"]]      # per histogram, per group axis
         self.string_codes = {}      # field name -> columns.StringCodes (created at the first string-valued fill)
         self.fx_scales = {}         # dtype signature -> fixed-point scale per term (from the pilot), see _fx_scales
         self.fx_sample = {}         # dtype signature -> events the pilot of fx_scales[signature] looked at
@@ -414,8 +415,7 @@ def _bind_stores(plan, kern, hists, discovered):
         if hspec["group"]:
             infos = []
             fill_keys = []
-            for a in hspec["group"]:
-                goalkey = hbspec.tree_key(a["goal"])
+            for a, goalkey in zip(hspec["group"], plan.goalkeys[hid]):
                 patterns, info = discovered[goalkey]
                 codes = None
                 for field, gk in plan.groupby_fields.items():

@@ -105,6 +105,7 @@ class Store(object):
         self.window = None            # {"table": DeviceBuffer, "bins", "rows"}
         self.window_key = None        # (rows, trail, wmax) of the kernel the window was placed for
         self.window_coverage = None
+        self._admitted = None         # the key lists of the last fill (admit)
         self.exact = None             # deterministic mode: engine.Arena of 128-bit accumulators (zero between fills)
         self.nonempty = False                         # the device copy holds at least one fill / uploaded content
 
@@ -220,6 +221,8 @@ class Store(object):
         hist.py:458-499: the reference loops over *all* uniques of every axis at every nesting level and
         creates missing entries, i.e. after a fill the dict holds the cross product of this fill's per-axis
         key sets (zero blocks where no row landed).  Insertion order = numpy.unique order per axis."""
+        if self.table is not None and self.arena is not None and self._admitted == fill_keys:
+            return                                   # the same keys as the last fill: slots, slab and slot map stand
         if self.skeleton is None:
             self.skeleton = collections.OrderedDict()
         ordered = [g.sort_patterns(k) for g, k in zip(self.groups, fill_keys)]
@@ -242,6 +245,7 @@ class Store(object):
             grow = max(need, 2 * self.arena.size)
             self.arena.resize(grow)
         self._slot_map(ordered)
+        self._admitted = [list(k) for k in fill_keys]
 
     def _slot_map(self, ordered):
         """Dense map for the fill kernel (codegen._group_lookup): position of the event's key on every axis among THIS
