@@ -375,3 +375,54 @@ def test_box_window_on_a_large_histogram():
 def torch_or_numpy(v):
     import torch
     return torch.from_numpy(numpy.ascontiguousarray(v)).cuda()
+
+
+def test_file_backed_columns_stream_through_the_bounce_ring(tmp_path):
+    """Columns that live in files (numpy.memmap: pageable, faulted in from disk as they are read) are filled like any
+    other host array -- in chunks through the page-locked bounce ring, never materialised as a whole."""
+    from histbook_b200 import engine, fillable
+    spec = golden_util.load()["c2"]["spec"]
+    rs = numpy.random.RandomState(31)
+    n = 3000017
+    data = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n), "w": rs.uniform(0.5, 1.5, n)}
+    maps = {}
+    for k, v in data.items():
+        path = str(tmp_path / (k + ".f64"))
+        v.tofile(path)
+        maps[k] = numpy.memmap(path, dtype=numpy.float64, mode="r", shape=(n,))
+    engine.lib().hb_set_chunk_events(1 << 19)                  # several chunks: 3 ring slots and 2 device buffers all get reused
+    try:
+        sf = fillable.SpecFill(spec)
+        sf.fill(maps)
+        sf.fill(dict((k, v[: n // 3]) for k, v in maps.items()))
+    finally:
+        engine.lib().hb_set_chunk_events(1 << 24)
+    exp = bound = None
+    for a in (data, dict((k, v[: n // 3]) for k, v in data.items())):
+        exp = fill_oracle.fill(spec, a, exp)
+        bound = fill_oracle.fill(spec, a, bound, absolute=True)
+    compare("c2 memmap", spec, sf.contents(), [golden_util.flatten(e) for e in exp], bound)
+
+
+def test_back_to_back_host_fills_do_not_race_on_the_staging_buffers():
+    """Two fills from DIFFERENT host arrays with a slow book and no read in between (the advisor's round-1 finding: the
+    second call's first copy could overwrite a staging buffer the first call's last kernel was still reading)."""
+    from histbook_b200 import fillable
+    spec = golden_util.load()["c4"]["spec"]
+    rs = numpy.random.RandomState(37)
+    n = 600011
+
+    def cols(seed_shift):
+        r = numpy.random.RandomState(37 + seed_shift)
+        return {"x": r.normal(0, 1, n), "y": r.normal(0, 1, n), "z": r.normal(0, 1, n), "w": r.uniform(0.5, 1.5, n),
+                "n": r.poisson(3, n).astype(numpy.int64)}
+    a, b, c = cols(0), cols(1), cols(2)
+    sf = fillable.SpecFill(spec)
+    sf.fill(a)
+    sf.fill(b)
+    sf.fill(c)                                                # nothing is read until here
+    exp = bound = None
+    for arrays in (a, b, c):
+        exp = fill_oracle.fill(spec, arrays, exp)
+        bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+    compare("c4 back to back", spec, sf.contents(), [golden_util.flatten(e) for e in exp], bound)
