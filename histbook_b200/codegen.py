@@ -734,8 +734,9 @@ class SortGroup(object):
 
     def smem_bytes(self, tile, lanes, chunks=False):
         nv = len(self.values)
-        tails = (4 * lanes + lanes * 8 * max(nv, 1)) if chunks else 0      # tail keys, tail values
-        return (8 * nv * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + 4 * lanes + 32 + tails + 64) // 16 * 16 + 16
+        nvp = (nv + 1) // 2 * 2 if chunks else nv                         # chunks: rows of the table are [bin][values], padded to 16 bytes
+        tails = (4 * lanes + lanes * 8 * max(nvp, 2)) if chunks else 0      # tail keys, tail values
+        return (8 * nvp * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + 4 * lanes + 32 + tails + 64) // 16 * 16 + 16
 
 
 def sort_groups(plans, options):
@@ -999,7 +1000,8 @@ def choose_strategies(plans, options, prog=None, layout=None):
         used = (used + 15) // 16 * 16
         for g in sgroups:
             g.off["acc"] = used
-            used += (8 * len(g.values) * g.nbins + 15) // 16 * 16
+            nvp = (len(g.values) + 1) // 2 * 2 if options.get("sort_sum", SORT_SUM) == "chunks" else len(g.values)
+            used += (8 * nvp * g.nbins + 15) // 16 * 16
         for g in sgroups:
             g.off["cnt"] = used
             used += (4 * g.nbins + 15) // 16 * 16
@@ -1016,7 +1018,7 @@ def choose_strategies(plans, options, prog=None, layout=None):
                 g.off["tkey"] = used
                 used += (4 * sort_lanes + 15) // 16 * 16
                 g.off["tval"] = used
-                used += 8 * sort_lanes * max(len(g.values), 1)
+                used += 8 * sort_lanes * max((len(g.values) + 1) // 2 * 2, 2)
         e_off = used
         used += 8 * len(staged) * sort_tile
         sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "dump_off": dump_off, "e_off": e_off, "tile": sort_tile,
@@ -1359,8 +1361,31 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("__device__ __forceinline__ void hb_event(%s)\n{" % ", ".join(sig))
     src.extend("    " + line for line in event_lines)
     src.append("    // ---- values the sort groups accumulate, staged for this tile")
-    for k, e in enumerate(staged):
-        src.append("    reinterpret_cast<double*>(hb_smem + %d)[eid] = %s;" % (layout["e_off"] + 8 * k * tile, e))
+    # staged values travel in pairs: slots 2h and 2h + 1 are one 16-byte record per event (one STS.128 here, one LDS.128 per
+    # gather in the summing phase: a random 16-byte gather costs ~9 wavefronts per warp, two 8-byte ones ~12); an odd last slot
+    # is an array of doubles
+    def e_pair_off(h):
+        return layout["e_off"] + 16 * h * tile
+
+    def e_single_off():
+        return layout["e_off"] + 16 * (len(staged) // 2) * tile
+    for h in range(len(staged) // 2):
+        src.append("    reinterpret_cast<double2*>(hb_smem + %d)[eid] = make_double2(%s, %s);" % (e_pair_off(h), staged[2 * h], staged[2 * h + 1]))
+    if len(staged) % 2:
+        src.append("    reinterpret_cast<double*>(hb_smem + %d)[eid] = %s;" % (e_single_off(), staged[-1]))
+
+    def gather(ind, used, e, suffix=""):
+        """C lines loading the staged slots ``used`` of event ``e`` into v<k><suffix>"""
+        out = []
+        for h in range(len(staged) // 2):
+            if 2 * h in used or 2 * h + 1 in used:
+                out.append("%sconst double2 vp%d%s = reinterpret_cast<const double2*>(hb_smem + %d)[%s];" % (ind, h, suffix, e_pair_off(h), e))
+                for k, part in ((2 * h, "x"), (2 * h + 1, "y")):
+                    if k in used:
+                        out.append("%sconst double v%d%s = vp%d%s.%s;" % (ind, k, suffix, h, suffix, part))
+        if len(staged) % 2 and len(staged) - 1 in used:
+            out.append("%sconst double v%d%s = reinterpret_cast<const double*>(hb_smem + %d)[%s];" % (ind, len(staged) - 1, suffix, e_single_off(), e))
+        return out
     for g in groups:
         src.append("    // ---- sort group %d: %d bins, %d values, histograms %s" % (g.gid, g.nbins, len(g.values), [hp.hid for hp in g.members]))
         src.append("    {")
@@ -1444,7 +1469,17 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("            const hb_u32 p0 = (hb_u32)hb_l * %du, p1 = min(p0 + %du, ng);" % (chunk, chunk))
             src.append("            " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
             src.append("            int tkey = -1;")
-            flush = " ".join("acc[%d + key] += a%d; a%d = 0.0;" % (j * g.nbins, j, j) for j in range(nv))
+            nvp = (nv + 1) // 2 * 2
+
+            def rowop(ptr, fmt_pair, fmt_single):
+                """statements over the 16-byte pairs of one [values] row at ``ptr`` (a double*)"""
+                out = ["double2* const r = reinterpret_cast<double2*>(%s); double2 q;" % ptr]
+                for h in range(nvp // 2):
+                    out.append((fmt_pair if 2 * h + 1 < nv else fmt_single).format(h=h, a=2 * h, b=2 * h + 1))
+                return " ".join(out)
+            # (rows of the block's table are [bin][values]: a flush is 3 LDS.128 + 3 STS.128 for c4's six sums instead of 6 + 6
+            #  64-bit ones -- the flush path is walked by the whole warp whenever one lane's run ends, which is most iterations)
+            flush = "{ " + rowop("acc + key * %d" % nvp, "q = r[{h}]; q.x += a{a}; q.y += a{b}; r[{h}] = q;", "q = r[{h}]; q.x += a{a}; r[{h}] = q;") + " " + " ".join("a%d = 0.0;" % j for j in range(nv)) + " }"
             src.append("            if (p0 < ng) {")
             src.append("                int key = hb_sort_find(st, %d, p0);" % g.nbins)
             src.append("                hb_u32 runend = st[key + 1];")
@@ -1454,8 +1489,7 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("                        do { ++key; runend = st[key + 1]; } while (pos >= runend);")
             src.append("                    }")
             src.append("                    const unsigned e = so[HB_SPOS(pos)];")
-            for k in used_slots:
-                src.append("                    const double v%d = reinterpret_cast<const double*>(hb_smem + %d)[e];" % (k, layout["e_off"] + 8 * k * tile))
+            src.extend(gather("                    ", used_slots, "e"))
             for j, (kind, k) in enumerate(g.stage):
                 if kind == "E":
                     src.append("                    a%d += v%d;" % (j, k))
@@ -1466,12 +1500,12 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("                else { %s }" % flush)
             src.append("            }")
             src.append("            tkeys[hb_l] = tkey;")
-            src.append("            if (tkey >= 0) { %s }" % " ".join("tvals[%d + hb_l] = a%d;" % (j * lanes, j) for j in range(nv)))
+            src.append("            if (tkey >= 0) { %s }" % rowop("tvals + hb_l * %d" % nvp, "r[{h}] = make_double2(a{a}, a{b});", "r[{h}] = make_double2(a{a}, 0.0);"))
             src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))
             src.append("            for (int b = hb_l; b <= %d; b += HB_LANES) reinterpret_cast<hb_u32*>(hb_smem + %d)[b] = 0u;" % (g.nbins, g.off["tick"]))
             src.append("            if (tkey >= 0 && (hb_l == 0 || tkeys[hb_l - 1] != tkey)) {")
             src.append("                const int key = tkey;")
-            src.append("                for (int m = hb_l + 1; m < HB_LANES && tkeys[m] == key; ++m) { %s }" % " ".join("a%d += tvals[%d + m];" % (j, j * lanes) for j in range(nv)))
+            src.append("                for (int m = hb_l + 1; m < HB_LANES && tkeys[m] == key; ++m) { %s }" % rowop("tvals + m * %d" % nvp, "q = r[{h}]; a{a} += q.x; a{b} += q.y;", "q = r[{h}]; a{a} += q.x;"))
             src.append("                " + flush)
             src.append("            }")
             src.append("        }")
@@ -1482,10 +1516,7 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
         used_slots = sorted(set(k for kind, k in g.stage))
 
         def element(ind, e):
-            out = []
-            for k in used_slots:
-                out.append("%sconst double v%d_%s = reinterpret_cast<const double*>(hb_smem + %d)[%s];" % (ind, k, e, layout["e_off"] + 8 * k * tile, e))
-            return out
+            return gather(ind, used_slots, e, "_" + e)
 
         def adds(ind, e):
             out = []
@@ -1540,7 +1571,10 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
         src.append("    // merge sort group %d" % g.gid)
         src.append("    for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % g.nbins)
         for j, dests in enumerate(g.dests):
-            src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b];" % (g.off["acc"] + 8 * j * g.nbins))
+            if chunks:
+                src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b * %d + %d];" % (g.off["acc"], (len(g.values) + 1) // 2 * 2, j))
+            else:
+                src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b];" % (g.off["acc"] + 8 * j * g.nbins))
             src.append("          if (v != 0.0) { %s } }" % " ".join("hb_red_f64(p.hist[%d] + (hb_i64)b * %d + %d, v);" % (hid, ncol, col) for hid, col, ncol in dests))
         if g.count_dests:
             src.append("        { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d)[b];" % g.off["cnt"])
