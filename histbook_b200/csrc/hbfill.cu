@@ -428,6 +428,13 @@ static CopyPool* copy_pool() {
             // measured on a 16-core B200 host, c4 from pageable numpy columns: 4 threads 23.9 GB/s, 8: 32.1, 12: 36.3, 16: 35.8
             // (page-locked columns: 44.8 GB/s) -- tools/gpu/e2e_threads.sh
             g_copy_threads = env ? atoi(env) : (int)(hw >= 16 ? 12 : (hw >= 4 ? hw * 3 / 4 : 1));
+            // one process per GPU: the ranks of a box share its cores (8 ranks on 32 cores: 3 threads each, not 12)
+            const char* lws = getenv("LOCAL_WORLD_SIZE");
+            const int ranks = lws ? atoi(lws) : 1;
+            if (!env && ranks > 1) {
+                const int share = (int)(hw * 3 / 4) / ranks;
+                if (g_copy_threads > share) g_copy_threads = share < 2 ? 2 : share;
+            }
             if (g_copy_threads < 1) g_copy_threads = 1;
         }
         g_pool = new CopyPool();

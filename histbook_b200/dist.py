@@ -196,6 +196,7 @@ class Merger(object):
         self.shard = None
         self.sharded = False
         self.side = None
+        self.kstream = None             # stream of the key exchange
         self.done = None
         self.device = device            # None: decided at the first start() (NCCL -> device, anything else -> host)
         self.layout = None              # [(hist, store, kind, offset, size, union order)] of the last start()
@@ -235,11 +236,23 @@ class Merger(object):
                 buf[1:need] = numpy.array(words, dtype=numpy.uint64)
             t = torch.from_numpy(buf.view(numpy.int64))
             if self._use_device():
-                t = t.cuda()
-            gathered = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(gathered, t, group=self.group)
+                # on a stream of its own: the exchange must not queue behind the fill kernel that is still running on the
+                # compute stream -- the host would wait for it and do the rest of the merge's host work with the GPU idle
+                # (c4 at 8 GPUs: 10.5 ms per step against 8.8 ms of kernel before this)
+                if self.kstream is None:
+                    self.kstream = torch.cuda.Stream()
+                with torch.cuda.stream(self.kstream):
+                    td = t.pin_memory().to("cuda", non_blocking=True)
+                    out = torch.empty(world * td.numel(), dtype=td.dtype, device=td.device)
+                    dist.all_gather_into_tensor(out, td, group=self.group)
+                    host = out.to("cpu", non_blocking=True)
+                self.kstream.synchronize()
+                rows = [r.view(numpy.uint64) for r in host.numpy().reshape(world, -1)]
+            else:
+                gathered = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(gathered, t, group=self.group)
+                rows = [g.numpy().view(numpy.uint64) for g in gathered]
             self.collectives += 1
-            rows = [g.cpu().numpy().view(numpy.uint64) for g in gathered]
             most = max(int(r[0]) for r in rows)
             if most > self.keycap:                       # every rank sees the same numbers and grows alike
                 while self.keycap < most:
