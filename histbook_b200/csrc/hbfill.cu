@@ -633,6 +633,49 @@ extern "C" int hb_arena_axpy_at(hb_arena* dst, int64_t dst_off, const hb_arena* 
     return HB_OK;
 }
 
+// Snapshot of many arenas (or slab slots) into one flat buffer with ONE launch: the rank merge copies every histogram of a
+// book into the buffer its collective reduces (dist.Merger).  64 small torch copies cost ~0.4 ms of launches per merge.
+#define HB_SNAP_MAX 128
+struct HbSnapshot {
+    const double* src[HB_SNAP_MAX];
+    long long dst[HB_SNAP_MAX];
+    long long count[HB_SNAP_MAX];
+};
+__global__ void hb_snapshot_kernel(const HbSnapshot s, double* __restrict__ out) {
+    const int seg = blockIdx.y;
+    const double* __restrict__ src = s.src[seg];
+    double* __restrict__ dst = out + s.dst[seg];
+    const long long n = s.count[seg];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+extern "C" int hb_arena_snapshot(int nseg, hb_arena* const* src, const int64_t* src_off, const int64_t* dst_off, const int64_t* count, void* dst) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (nseg < 0 || (nseg > 0 && (!src || !src_off || !dst_off || !count || !dst))) return fail(HB_ERR_ARG, "bad hb_arena_snapshot arguments");
+    for (int base = 0; base < nseg; base += HB_SNAP_MAX) {
+        HbSnapshot s;
+        memset(&s, 0, sizeof(s));
+        const int m = nseg - base < HB_SNAP_MAX ? nseg - base : HB_SNAP_MAX;
+        long long most = 0;
+        for (int i = 0; i < m; ++i) {
+            const hb_arena* a = src[base + i];
+            if (!a || src_off[base + i] < 0 || count[base + i] < 0 || src_off[base + i] + count[base + i] > a->n)
+                return fail(HB_ERR_ARG, "hb_arena_snapshot: segment out of range");
+            s.src[i] = a->ptr + src_off[base + i];
+            s.dst[i] = dst_off[base + i];
+            s.count[i] = count[base + i];
+            if (count[base + i] > most) most = count[base + i];
+        }
+        if (most == 0) continue;
+        long long gx = (most + 1023) / 1024;
+        if (gx > 1024) gx = 1024;
+        hb_snapshot_kernel<<<dim3((unsigned)gx, (unsigned)m, 1), 256, 0, g_stream>>>(s, (double*)dst);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return HB_OK;
+}
+
 extern "C" int hb_arena_scale(hb_arena* dst, double alpha) {
     int rc = ensure_device();
     if (rc) return rc;

@@ -76,6 +76,7 @@ SYMBOLS = {
     "hb_arena_axpy": (_I, [_P, _P, ctypes.c_double]),
     "hb_arena_axpy_at": (_I, [_P, _I64, _P, _I64, _I64, ctypes.c_double]),
     "hb_arena_scale": (_I, [_P, ctypes.c_double]),
+    "hb_arena_snapshot": (_I, [_I, _PP, ctypes.POINTER(_I64), ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P]),
     "hb_arena_project": (_I, [_P, _I, ctypes.POINTER(_I64), _I, ctypes.POINTER(ctypes.c_int32), _PP]),
     "hb_arena_ptr": (_P, [_P]),
     "hb_arena_size": (_I64, [_P]),
@@ -467,3 +468,20 @@ def fill_multi(parts, columns, n, timed=False, offset=0):
     check(lib().hb_fill_multi(len(parts), launches, ncols, cols, int(n), HB_FILL_TIMED if timed else 0, ctypes.byref(stats)))
     return {"events": stats.events, "h2d_bytes": stats.h2d_bytes, "launches": stats.launches, "grid": stats.grid,
             "blocks_per_sm": stats.blocks_per_sm, "ms_kernel": stats.ms_kernel}
+
+
+class Snapshot(object):
+    """A prepared hb_arena_snapshot call: [(arena, source offset, destination offset, count)] -> one launch."""
+
+    def __init__(self, segments):
+        n = len(segments)
+        self.n = n
+        self.keep = [a for a, so, do, c in segments]
+        self.src = (ctypes.c_void_p * max(n, 1))(*[a._h for a, so, do, c in segments])
+        self.src_off = (ctypes.c_int64 * max(n, 1))(*[int(so) for a, so, do, c in segments])
+        self.dst_off = (ctypes.c_int64 * max(n, 1))(*[int(do) for a, so, do, c in segments])
+        self.count = (ctypes.c_int64 * max(n, 1))(*[int(c) for a, so, do, c in segments])
+
+    def run(self, dst_ptr):
+        if self.n:
+            check(lib().hb_arena_snapshot(self.n, self.src, self.src_off, self.dst_off, self.count, ctypes.c_void_p(int(dst_ptr))))

@@ -117,7 +117,11 @@ int hb_arena_write(hb_arena* a, int64_t offset, int64_t count, const double* hos
 int hb_arena_axpy(hb_arena* dst, const hb_arena* src, double alpha);   /* dst += alpha * src */
 /* dst[dst_off, dst_off + count) += alpha * src[src_off, src_off + count): slab slots of group-axis histograms */
 int hb_arena_axpy_at(hb_arena* dst, int64_t dst_off, const hb_arena* src, int64_t src_off, int64_t count, double alpha);
-int hb_arena_scale(hb_arena* dst, double alpha);                       /* dst *= alpha */
+int hb_arena_scale(hb_arena* dst, double alpha);
+/* ONE launch copying nseg ranges src[i][src_off[i] .. + count[i]) to dst + dst_off[i] (doubles; dst = device memory): the
+ * snapshot of all histograms of a book -- group-axis slabs slot by slot, in the merged key order -- that the rank merge
+ * reduces (Hist.__add__ across ranks, histbook/hist.py:506-542) */
+int hb_arena_snapshot(int nseg, hb_arena* const* src, const int64_t* src_off, const int64_t* dst_off, const int64_t* count, void* dst);                       /* dst *= alpha */
 /* Hist.project (histbook/proj.py:227-296) on the device: sum the content over the fixed axes with keep[k] == 0.
  * `shape` = bins per fixed axis (ndim <= 8), ncol = size of the last (column) dimension, which is always kept.
  * *out is a new arena of prod(kept shape) * ncol doubles. */
