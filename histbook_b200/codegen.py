@@ -689,6 +689,7 @@ SORT_EPT = 2               # events per thread and tile
 SORT_SUM = "chunks"        # how the sorted events of a tile are summed: "chunks" (balanced: a contiguous chunk per lane) | "bins" (sort_split lanes per bin);
                            # c4, one GPU, 1e9 events: chunks of 64 lanes per group 12.1 Gev/s, of 128 lanes 11.9, bins 11.75 (profiles/r02_sweeps.txt)
 SORT_MAX_BINS = 8192
+SORT_PIPE = False          # producer / consumer warps with double-buffered tiles (_emit_kernel_sorted_pipe); "auto" = when it fits
 SORT_MAX_GROUPS = 12       # (key, rank) tickets of a tile live in registers: SORT_EPT x groups of them per thread
 SMEM_MAX = 227 * 1024
 
@@ -805,6 +806,33 @@ def stage_values(prog, groups):
     return staged
 
 
+def _pipe_group_fixed(g):
+    """bytes of a sort group's tables that live for the whole kernel (pipelined variant): [bin][values] sums + counts"""
+    nvp = (len(g.values) + 1) // 2 * 2
+    return (8 * nvp * g.nbins + 15) // 16 * 16 + (4 * g.nbins + 15) // 16 * 16
+
+
+def _pipe_group_tick(g):
+    return (4 * (g.nbins + 1) + 15) // 16 * 16
+
+
+def _pipe_pad(tile):
+    """halfwords of padding behind every lane's chunk of sorted event numbers: a lane's chunk starts 8 x (an odd number)
+    bytes after its neighbour's, so that the summing warp reads four event numbers per lane with ONE conflict-free LDS.64"""
+    chunk = tile // 32
+    pad = 0
+    while (chunk + pad) % 8 != 4:
+        pad += 1
+    return pad
+
+
+def _pipe_sorted_bytes(tile, g):
+    """a group's array of sorted event numbers (padded chunks + the dump slot of masked events); the summing warp re-uses
+    it for the tails of its lanes (32 keys + 32 rows of sums)"""
+    nvp = (len(g.values) + 1) // 2 * 2
+    return (max(2 * (tile + 32 * _pipe_pad(tile) + 8), 128 + 32 * 8 * nvp) + 15) // 16 * 16
+
+
 def _unroll(plans, options):
     """How the four events a thread owns per tile are laid out in code: 4 = vector loads + four inlined copies of the event
     function; 1 = vector loads, one copy in a loop; 0 = one copy, one coalesced scalar load per column and event (big
@@ -819,8 +847,9 @@ def choose_strategies(plans, options, prog=None, layout=None):
     forced = options.get("strategy", {})
     # big books: histograms that share a bin index are summed per tile from events sorted by that index (SortGroup)
     sgroups, staged, sort_bytes = [], [], 0
+    pipe = False
     sort_cap = int(options.get("sort_smem", SMEM_MAX - 1024))
-    sort_tile = int(options.get("sort_threads", SORT_THREADS)) * int(options.get("sort_ept", SORT_EPT))
+    base_tile = sort_tile = int(options.get("sort_threads", SORT_THREADS)) * int(options.get("sort_ept", SORT_EPT))
     sort_lanes = options.get("sort_lanes", "auto")
     group_slots = int(options.get("group_slots", 16))
     if prog is not None:
@@ -843,11 +872,33 @@ def choose_strategies(plans, options, prog=None, layout=None):
                     lanes *= 2
             else:
                 lanes = int(sort_lanes)
-            for slots in (group_slots, min(group_slots, 8)):
-                sort_bytes = sum(g.smem_bytes(sort_tile, lanes, sort_chunks) for g in sgroups) + 8 * len(staged) * sort_tile + 64
-                if sort_bytes + direct_need(slots) <= sort_cap:
+            # pipelined variant: the last len(sgroups) warps of the block sum tile k (one warp per group) while the others
+            # evaluate tile k + 1; tick counters, sorted event numbers and staged values exist twice.  Where that does not fit,
+            # the same groups are tried with one buffer set and phases behind block barriers before a group is given up.
+            want_pipe = bool(options.get("sort_pipe", SORT_PIPE)) and sort_chunks and len(sgroups) <= 12
+            auto_lanes = lanes
+            fits = False
+            for pipe in ([True, False] if want_pipe else [False]):
+                sort_tile, lanes = base_tile, auto_lanes
+                if pipe:
+                    lanes = 32
+                    pipe_threads = int(options.get("sort_threads", SORT_THREADS))
+                    pipe_prod = pipe_threads - 32 * len(sgroups)
+                    sort_tile = pipe_prod * int(options.get("sort_ept", SORT_EPT))
+                    if pipe_prod < 256 or sort_tile > 32768:
+                        continue
+                for slots in (group_slots, min(group_slots, 8)):
+                    if pipe:
+                        sort_bytes = (sum(_pipe_group_fixed(g) for g in sgroups)
+                                      + 2 * (sum(_pipe_group_tick(g) + _pipe_sorted_bytes(sort_tile, g) for g in sgroups) + 16 + 8 * len(staged) * sort_tile) + 64)
+                    else:
+                        sort_bytes = sum(g.smem_bytes(sort_tile, lanes, sort_chunks) for g in sgroups) + 8 * len(staged) * sort_tile + 64
+                    if sort_bytes + direct_need(slots) <= sort_cap:
+                        break
+                if sort_bytes + 16 * 1024 <= sort_cap:
+                    fits = True
                     break
-            if sort_bytes + 16 * 1024 <= sort_cap:
+            if fits:
                 sort_lanes, group_slots = lanes, slots
                 break
             sgroups = sgroups[:-1]                         # does not fit: the last group goes back to the per-event strategies
@@ -860,7 +911,7 @@ def choose_strategies(plans, options, prog=None, layout=None):
             if hp.sgroup is not None:
                 hp.strategy = "sorted"
         if not sgroups:
-            staged, sort_bytes = [], 0
+            staged, sort_bytes, pipe = [], 0, False
     if not sgroups:
         sort_lanes, group_slots = 64, int(options.get("group_slots", 16))
     # Which float64 terms are accumulated as exact fixed point (16 bytes per bin, native u32 atomics, ~55 instructions,
@@ -994,7 +1045,42 @@ def choose_strategies(plans, options, prog=None, layout=None):
         raise UnsupportedError("more than {0} fixed-point terms in one fill".format(MAX_WIN - 2))
     if not any(hp.strategy in ("smem", "window") for hp in plans) and not any(hp.fx for hp in plans):
         used = 0
-    if sgroups:
+    if sgroups and pipe:
+        # pipelined variant: [acc | cnt of every group | tick of every group, buffer 0, + dump word | the same, buffer 1 | dump]
+        # (zeroed at kernel start), then per buffer [sorted event numbers of every group | staged values]
+        used = (used + 15) // 16 * 16
+        for g in sgroups:
+            g.off["acc"] = used
+            used += (8 * ((len(g.values) + 1) // 2 * 2) * g.nbins + 15) // 16 * 16
+        for g in sgroups:
+            g.off["cnt"] = used
+            used += (4 * g.nbins + 15) // 16 * 16
+        tick0 = used
+        for g in sgroups:
+            g.off["tick"] = used
+            used += _pipe_group_tick(g)
+        tick_dump = used                                  # masked tickets of this buffer add here
+        used += 16
+        tick_stride = used - tick0
+        used += tick_stride                               # buffer 1
+        dump_off = used
+        used += 16
+        zero_end = used
+        tile0 = used
+        for g in sgroups:
+            g.off["sorted"] = used
+            used += _pipe_sorted_bytes(sort_tile, g)
+        e_off = used
+        used += 8 * len(staged) * sort_tile
+        tile_stride = used - tile0
+        used += tile_stride                               # buffer 1
+        sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "dump_off": dump_off, "e_off": e_off, "tile": sort_tile,
+                       "lanes": 32, "chunks": True, "threads": pipe_threads, "ept": int(options.get("sort_ept", SORT_EPT)),
+                       "pipe": {"prod": pipe_prod, "tick_stride": tick_stride, "tile_stride": tile_stride, "tick_dump": tick_dump,
+                                "pad": _pipe_pad(sort_tile)}}
+        if layout is not None:
+            layout.update(sort_layout)
+    elif sgroups:
         # layout behind the per-event tables: [acc | cnt | tick of every group] (zeroed at kernel start), then the
         # per-tile scratch [sorted event numbers | tails of every group], then the staged values E[k][event]
         used = (used + 15) // 16 * 16
@@ -1480,7 +1566,8 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             # (rows of the block's table are [bin][values]: a flush is 3 LDS.128 + 3 STS.128 for c4's six sums instead of 6 + 6
             #  64-bit ones -- the flush path is walked by the whole warp whenever one lane's run ends, which is most iterations)
             flush = "{ " + rowop("acc + key * %d" % nvp, "q = r[{h}]; q.x += a{a}; q.y += a{b}; r[{h}] = q;", "q = r[{h}]; q.x += a{a}; r[{h}] = q;") + " " + " ".join("a%d = 0.0;" % j for j in range(nv)) + " }"
-            src.append("            if (p0 < ng) {")
+            # (sort_skip_sum: a measurement aid -- the sums are skipped, the float64 columns stay empty)
+            src.append("            if (p0 < ng%s) {" % (" && p.n < 0" if options.get("sort_skip_sum") else ""))
             src.append("                int key = hb_sort_find(st, %d, p0);" % g.nbins)
             src.append("                hb_u32 runend = st[key + 1];")
             src.append("                for (hb_u32 pos = p0; pos < p1; ++pos) {")
@@ -1575,6 +1662,240 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
                 src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b * %d + %d];" % (g.off["acc"], (len(g.values) + 1) // 2 * 2, j))
             else:
                 src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b];" % (g.off["acc"] + 8 * j * g.nbins))
+            src.append("          if (v != 0.0) { %s } }" % " ".join("hb_red_f64(p.hist[%d] + (hb_i64)b * %d + %d, v);" % (hid, ncol, col) for hid, col, ncol in dests))
+        if g.count_dests:
+            src.append("        { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d)[b];" % g.off["cnt"])
+            src.append("          if (c != 0u) { const double v = (double)c; %s } }" % " ".join(
+                "hb_red_f64(p.hist[%d] + (hb_i64)b * %d + %d, v);" % (hid, ncol, col) for hid, col, ncol in g.count_dests))
+        src.append("    }")
+    src.append("}")
+    return "\n".join(src) + "\n"
+
+
+def _emit_kernel_sorted_pipe(prog, event_lines, merge_lines, layout, options):
+    """The sorted strategy as a two-stage pipeline inside one 1024-thread block (``sort_pipe``).
+
+    In ``_emit_kernel_sorted`` the phases of a tile follow one another behind block barriers: the event phase is bound by the
+    issue slots (56 % of the instructions, a quarter of the shared-memory wavefronts), the summing phase by the shared-memory
+    pipe (a third of the instructions, 63 % of the wavefronts), and half of the warps idle through it -- 44 % of the time
+    (profiles/r02_c4_ncu.txt).  Here the block's warps are split by role: the first HB_PROD threads (*producers*) evaluate
+    tile k + 1 -- stage, tickets, scan, scatter, exactly as before -- while one *consumer* warp per sort group sums tile k.
+    Tick counters, sorted event numbers and staged values exist twice; named barriers hand the buffers over
+    (producers ``bar.arrive`` FULL_b, consumers ``bar.sync`` it, and the other way round for EMPTY_b).  The consumer of a
+    group is ONE warp: every lane walks a chunk of HB_TILE / 32 sorted events, runs that end inside the chunk are flushed
+    on the spot, tails are combined by a segmented reduction over shuffles -- no tail arrays, no barrier inside the group.
+    The count tables belong to the producers (scan), the float64 tables to the consumers: no table has two writers."""
+    groups, staged = layout["groups"], layout["staged"]
+    threads, ept, tile = layout["threads"], layout["ept"], layout["tile"]
+    pp = layout["pipe"]
+    prod, tick_stride, tile_stride, tick_dump, padh = pp["prod"], pp["tick_stride"], pp["tile_stride"], pp["tick_dump"], pp["pad"]
+    G = len(groups)
+    chunk = tile // 32
+    assert chunk * 32 == tile and prod + 32 * G == threads and prod % 32 == 0
+    BAR_PROD, BAR_FULL, BAR_EMPTY = 1, 2, 4
+    src = []
+    src.append('#include "hb_template.cuh"')
+    src.append("#define HB_THREADS %d" % threads)
+    src.append("#define HB_PROD %d" % prod)
+    src.append("#define HB_EPT %d" % ept)
+    src.append("#define HB_TILE (HB_PROD * HB_EPT)")
+    src.append("#define HB_LANES 32")
+    src.append("#define HB_NSG %d" % G)
+    src.append("#define HB_FXMISS (reinterpret_cast<hb_u32*>(hb_smem))")
+    if padh:
+        src.append("#define HB_SPOS(pos) ((pos) + ((pos) / %du) * %du)" % (chunk, padh))
+    else:
+        src.append("#define HB_SPOS(pos) (pos)")
+    src.append("#define HB_BAR_SYNC(id, n) asm volatile(\"bar.sync %0, %1;\" :: \"r\"(id), \"r\"(n) : \"memory\")")
+    src.append("#define HB_BAR_ARRIVE(id, n) asm volatile(\"bar.arrive %0, %1;\" :: \"r\"(id), \"r\"(n) : \"memory\")")
+    src.extend(prog.consts)
+    src.append("// per sort group: tick counters, sorted event numbers (both relative to the buffer), sums, counts (-1: none), bins")
+    src.append("__constant__ int hb_goff[%d][6] = { %s };" % (
+        G, ", ".join("{ %d, %d, %d, %d, %d, 0 }" % (g.off["tick"], g.off["sorted"], g.off["acc"], g.off["cnt"] if g.count_dests else -1, g.nbins) for g in groups)))
+    src.append("")
+    sig = ["const HbParams& p", "unsigned char* hb_smem", "unsigned char* const hb_tk", "unsigned char* const hb_tl", "const bool live", "const int eid",
+           "hb_u32 (&kr)[HB_NSG]"]
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        sig.append("const %s c%d /* %s */" % (ctype(dtype), slot, name))
+    src.append("__device__ __forceinline__ void hb_event(%s)\n{" % ", ".join(sig))
+    src.extend("    " + line for line in event_lines)
+    src.append("    // ---- values the sort groups accumulate, staged for this tile (hb_tl: this tile's buffer)")
+
+    def e_pair_off(h):
+        return layout["e_off"] + 16 * h * tile
+
+    def e_single_off():
+        return layout["e_off"] + 16 * (len(staged) // 2) * tile
+    for h in range(len(staged) // 2):
+        src.append("    reinterpret_cast<double2*>(hb_tl + %d)[eid] = make_double2(%s, %s);" % (e_pair_off(h), staged[2 * h], staged[2 * h + 1]))
+    if len(staged) % 2:
+        src.append("    reinterpret_cast<double*>(hb_tl + %d)[eid] = %s;" % (e_single_off(), staged[-1]))
+
+    def gather(ind, used, e, sfx=""):
+        out = []
+        for h in range(len(staged) // 2):
+            if 2 * h in used or 2 * h + 1 in used:
+                out.append("%sconst double2 vp%d%s = reinterpret_cast<const double2*>(hb_tl + %d)[%s];" % (ind, h, sfx, e_pair_off(h), e))
+                for k, part in ((2 * h, "x"), (2 * h + 1, "y")):
+                    if k in used:
+                        out.append("%sconst double v%d%s = vp%d%s.%s;" % (ind, k, sfx, h, sfx, part))
+        if len(staged) % 2 and len(staged) - 1 in used:
+            out.append("%sconst double v%d%s = reinterpret_cast<const double*>(hb_tl + %d)[%s];" % (ind, len(staged) - 1, sfx, e_single_off(), e))
+        return out
+    for g in groups:
+        src.append("    // ---- sort group %d: %d bins, %d values, histograms %s" % (g.gid, g.nbins, len(g.values), [hp.hid for hp in g.members]))
+        src.append("    {")
+        src.append("        const bool okr = %s;" % " && ".join(["live"] + g.conds))
+        src.append("        const int bin = okr ? (%s) : 0;" % g.idx)
+        src.append("        const hb_u32 rank = atomicAdd(reinterpret_cast<hb_u32*>(hb_tk + (okr ? %d + 4 * bin : %d)), 1u);" % (g.off["tick"], tick_dump))
+        src.append("        kr[%d] = okr ? (((hb_u32)bin << 16) | rank) : 0xffffffffu;" % g.gid)
+        src.append("    }")
+    src.append("}\n")
+
+    src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, 1) hb_fill_kernel(const HbParams p)\n{')
+    src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
+    src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (layout["zero_end"] // 4))
+    src.append("    __syncthreads();")
+    for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+        if is_scalar:
+            src.append("    const %s s%d = hb_scalar<%s>(p.scal[%d]);" % (_loadtype(dtype), slot, _loadtype(dtype), slot))
+    src.append("    const hb_i64 ntiles = (p.n + HB_TILE - 1) / HB_TILE;")
+    src.append("    // tiles blockIdx.x, blockIdx.x + gridDim.x, ...: hb_nk of them; the k-th one goes through buffer k & 1")
+    src.append("    const hb_i64 hb_nk = ntiles > (hb_i64)blockIdx.x ? (ntiles - (hb_i64)blockIdx.x + (hb_i64)gridDim.x - 1) / (hb_i64)gridDim.x : 0;")
+    src.append("    if (threadIdx.x < HB_PROD) {")
+    src.append("        // ===== producers: evaluate, stage, draw tickets; scan; scatter")
+    src.append("        for (hb_i64 k = 0; k < hb_nk; ++k) {")
+    src.append("            const int hb_b = (int)(k & 1);")
+    src.append("            unsigned char* const hb_tk = hb_smem + hb_b * %d;" % tick_stride)
+    src.append("            unsigned char* const hb_tl = hb_smem + hb_b * %d;" % tile_stride)
+    src.append("            const hb_i64 first = ((hb_i64)blockIdx.x + k * (hb_i64)gridDim.x) * HB_TILE;")
+    for q in range(ept):
+        src.append("            hb_u32 kr%d[HB_NSG];" % q)
+    for q in range(ept):
+        src.append("            const hb_i64 i%d = first + %d * HB_PROD + threadIdx.x;" % (q, q))
+        src.append("            const bool live%d = i%d < p.n;" % (q, q))
+        src.append("            const hb_i64 j%d = live%d ? i%d : 0;" % (q, q, q))
+        for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+            if not is_scalar:
+                src.append("            const %s ld%d_%d = hb_load1<%s>(p.cols[%d], j%d);" % (_loadtype(dtype), q, slot, _loadtype(dtype), slot, q))
+    src.append("            if (k >= 2) HB_BAR_SYNC(%d + hb_b, HB_THREADS);      // the consumers are done with this buffer (tile k - 2)" % BAR_EMPTY)
+    for q in range(ept):
+        src.append("            hb_event(p, hb_smem, hb_tk, hb_tl, live%d, %d * HB_PROD + (int)threadIdx.x, kr%d%s);" % (q, q, q, "".join(
+            ", " + _colarg(slot, dtype, is_scalar, "ld%d_%d" % (q, slot))
+            for slot, (name, dtype, is_scalar) in enumerate(prog.cols))))
+    src.append("            HB_BAR_SYNC(%d, HB_PROD);" % BAR_PROD)
+    src.append("            if ((threadIdx.x >> 5) < %du) {        // one warp per group: bin counters -> bin start offsets" % G)
+    src.append("                const int sg = (int)(threadIdx.x >> 5);")
+    src.append("                hb_sort_scan(reinterpret_cast<hb_u32*>(hb_tk + hb_goff[sg][0]), hb_goff[sg][4], hb_goff[sg][3] >= 0 ? reinterpret_cast<hb_u32*>(hb_smem + hb_goff[sg][3]) : nullptr);")
+    src.append("            }")
+    src.append("            HB_BAR_SYNC(%d, HB_PROD);" % BAR_PROD)
+    dump_slot = tile + 32 * padh + 4
+    for q in range(ept):
+        for g in groups:
+            src.append("            { const bool v = kr%d[%d] != 0xffffffffu; const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_tk + %d)[v ? (kr%d[%d] >> 16) : 0u] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_tl + %d)[v ? HB_SPOS(sp) : %du] = (unsigned short)(%d * HB_PROD + threadIdx.x); }" % (
+                q, g.gid, g.off["tick"], q, g.gid, q, g.gid, g.off["sorted"], dump_slot, q))
+    src.append("            __threadfence_block();")
+    src.append("            HB_BAR_ARRIVE(%d + hb_b, HB_THREADS);                 // tile k is ready" % BAR_FULL)
+    src.append("        }")
+    src.append("    } else {")
+    src.append("        // ===== consumers: warp g sums the sorted events of group g")
+    src.append("        const int hb_g = ((int)threadIdx.x - HB_PROD) >> 5, hb_l = (int)(threadIdx.x & 31u);")
+    src.append("        for (hb_i64 k = 0; k < hb_nk; ++k) {")
+    src.append("            const int hb_b = (int)(k & 1);")
+    src.append("            unsigned char* const hb_tk = hb_smem + hb_b * %d;" % tick_stride)
+    src.append("            unsigned char* const hb_tl = hb_smem + hb_b * %d;" % tile_stride)
+    src.append("            HB_BAR_SYNC(%d + hb_b, HB_THREADS);" % BAR_FULL)
+    # groups of one shape (bins, staged slots) share ONE copy of the summing code: a consumer warp keeps its group for the whole
+    # kernel, so the group's offsets are three warp-uniform words from a __constant__ table (c4: eight groups, one copy)
+    classes = {}
+    for g in groups:
+        classes.setdefault((g.nbins, tuple(g.stage)), []).append(g)
+    for (nbins, stage), members in classes.items():
+        nv = len(stage)
+        nvp = (nv + 1) // 2 * 2
+        used_slots = sorted(set(k for kind, k in stage))
+
+        def rowop(ptr, fmt_pair, fmt_single):
+            out = ["double2* const r = reinterpret_cast<double2*>(%s); double2 q;" % ptr]
+            for h in range(nvp // 2):
+                out.append((fmt_pair if 2 * h + 1 < nv else fmt_single).format(h=h, a=2 * h, b=2 * h + 1))
+            return " ".join(out)
+        flush = "{ " + rowop("acc + key * %d" % nvp, "q = r[{h}]; q.x += a{a}; q.y += a{b}; r[{h}] = q;", "q = r[{h}]; q.x += a{a}; r[{h}] = q;") + " " + " ".join("a%d = 0.0;" % j for j in range(nv)) + " }"
+        mask = sum(1 << g.gid for g in members)
+        cond = "true" if len(members) == G else "((%du >> hb_g) & 1u) != 0u" % mask
+        src.append("            if (%s) {   // sort groups %s: %d bins, %d values" % (cond, [g.gid for g in members], nbins, nv))
+        src.append("                hb_u32* const st = reinterpret_cast<hb_u32*>(hb_tk + hb_goff[hb_g][0]);")
+        src.append("                unsigned char* const sob = hb_tl + hb_goff[hb_g][1];")
+        src.append("                const unsigned short* const so = reinterpret_cast<const unsigned short*>(sob);")
+        src.append("                double* const acc = reinterpret_cast<double*>(hb_smem + hb_goff[hb_g][2]);")
+        src.append("                const hb_u32 ng = st[%d];" % nbins)
+        src.append("                const hb_u32 p0 = (hb_u32)hb_l * %du, p1 = min(p0 + %du, ng);" % (chunk, chunk))
+        src.append("                " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
+        src.append("                int tkey = -1;")
+        src.append("                if (p0 < ng%s) {" % (" && p.n < 0" if options.get("sort_skip_sum") else ""))
+        src.append("                    int key = hb_sort_find(st, %d, p0);" % nbins)
+        src.append("                    hb_u32 runend = st[key + 1];")
+        # the event numbers of a lane's chunk are contiguous: four of them per LDS.64, their staged values gathered before the
+        # first add -- the summing warp is alone on its group, so its speed is the latency of this chain (one event at a time
+        # the eight consumer warps were busy 97 % of the kernel and the producers waited a third of theirs,
+        # profiles/r02_c4_pipe_ncu.txt)
+        batch = max(1, min(4, 24 // max(2 * len(used_slots), 1))) if chunk % 4 == 0 else 1
+        src.append("                    const unsigned short* const sol = so + (hb_u32)hb_l * %du;" % (chunk + padh))
+        src.append("                    hb_u32 pos = p0;")
+
+        def one(ind, q, sfx):
+            out = ["%sif (pos + %du >= runend) {       // the run of `key` ends in this lane's chunk, and in no other lane's" % (ind, q)]
+            out.append("%s    %s" % (ind, flush))
+            out.append("%s    do { ++key; runend = st[key + 1]; } while (pos + %du >= runend);" % (ind, q))
+            out.append("%s}" % ind)
+            for j, (kind, k) in enumerate(stage):
+                if kind == "E":
+                    out.append("%sa%d += v%d%s;" % (ind, j, k, sfx))
+                else:
+                    out.append("%sa%d += hb_mul<double>(v%d%s, v%d%s);" % (ind, j, k, sfx, k, sfx))
+            return out
+        if batch == 4:
+            src.append("                    for (; pos + 4u <= p1; pos += 4u) {")
+            src.append("                        const uint2 ev = *reinterpret_cast<const uint2*>(sol + (pos - p0));")
+            src.append("                        const unsigned e_0 = ev.x & 0xffffu, e_1 = ev.x >> 16, e_2 = ev.y & 0xffffu, e_3 = ev.y >> 16;")
+            for q in range(4):
+                src.extend(gather("                        ", used_slots, "e_%d" % q, "_%d" % q))
+            for q in range(4):
+                src.extend(one("                        ", q, "_%d" % q))
+            src.append("                    }")
+        src.append("                    for (; pos < p1; ++pos) {")
+        src.append("                        const unsigned e = sol[pos - p0];")
+        src.extend(gather("                        ", used_slots, "e", ""))
+        src.extend(one("                        ", 0, ""))
+        src.append("                    }")
+        src.append("                    if (runend > p1) tkey = key;       // the run goes on in the next lane: a tail")
+        src.append("                    else { %s }" % flush)
+        src.append("                }")
+        src.append("                __syncwarp();")
+        src.append("                // tails: lanes holding the same bin are neighbours; the first of them adds up the others' sums.  They travel")
+        src.append("                // through the group's array of sorted event numbers, which nobody reads any more")
+        src.append("                int* const tkeys = reinterpret_cast<int*>(sob);")
+        src.append("                double* const tvals = reinterpret_cast<double*>(sob + 128);")
+        src.append("                tkeys[hb_l] = tkey;")
+        src.append("                if (tkey >= 0) { %s }" % rowop("tvals + hb_l * %d" % nvp, "r[{h}] = make_double2(a{a}, a{b});", "r[{h}] = make_double2(a{a}, 0.0);"))
+        src.append("                __syncwarp();")
+        src.append("                if (tkey >= 0 && (hb_l == 0 || tkeys[hb_l - 1] != tkey)) {")
+        src.append("                    const int key = tkey;")
+        src.append("                    for (int m = hb_l + 1; m < 32 && tkeys[m] == key; ++m) { %s }" % rowop("tvals + m * %d" % nvp, "q = r[{h}]; a{a} += q.x; a{b} += q.y;", "q = r[{h}]; a{a} += q.x;"))
+        src.append("                    " + flush)
+        src.append("                }")
+        src.append("                for (int b = hb_l; b <= %d; b += 32) st[b] = 0u;" % nbins)
+        src.append("            }")
+    src.append("            if (k + 2 < hb_nk) { __threadfence_block(); HB_BAR_ARRIVE(%d + hb_b, HB_THREADS); }   // the buffer may be filled again" % BAR_EMPTY)
+    src.append("        }")
+    src.append("    }")
+    src.append("    __syncthreads();")
+    src.extend("    " + line for line in merge_lines)
+    for g in groups:
+        src.append("    // merge sort group %d" % g.gid)
+        src.append("    for (int b = threadIdx.x; b < %d; b += HB_THREADS) {" % g.nbins)
+        for j, dests in enumerate(g.dests):
+            src.append("        { const double v = reinterpret_cast<const double*>(hb_smem + %d)[b * %d + %d];" % (g.off["acc"], (len(g.values) + 1) // 2 * 2, j))
             src.append("          if (v != 0.0) { %s } }" % " ".join("hb_red_f64(p.hist[%d] + (hb_i64)b * %d + %d, v);" % (hid, ncol, col) for hid, col, ncol in dests))
         if g.count_dests:
             src.append("        { const hb_u32 c = reinterpret_cast<const hb_u32*>(hb_smem + %d)[b];" % g.off["cnt"])
@@ -2061,7 +2382,9 @@ def generate(spec, coltypes, options=None):
             if hp.fx:
                 k.exact[hp.hid] = [(hp.fx_index[t], sum(1 << c for c in hp.dest[t])) for t in hp.f64_terms]
     unroll = _unroll(plans, options)
-    if layout:
+    if layout and layout.get("pipe"):
+        k.source = _emit_kernel_sorted_pipe(prog, ev, merge, layout, options)
+    elif layout:
         k.source = _emit_kernel_sorted(prog, ev, merge, layout, options)
     else:
         k.source = _emit_kernel(prog, ev, smem, merge, threads, minblocks, window=winfo, prefetch=bool(options.get("prefetch", False)), unroll=unroll,
@@ -2074,6 +2397,8 @@ def generate(spec, coltypes, options=None):
     k.threads = threads
     k.tile = layout["tile"] if layout else threads * VEC
     k.sorted = dict((key, layout[key]) for key in ("tile", "lanes", "ept")) if layout else None
+    if layout and layout.get("pipe"):
+        k.sorted["pipe"] = {"producers": layout["pipe"]["prod"], "consumer_warps": len(layout["groups"])}
     if layout:
         k.sorted["groups"] = [{"nbins": g.nbins, "values": len(g.values), "hists": [hp.hid for hp in g.members]} for g in layout["groups"]]
         k.sorted["staged"] = len(layout["staged"])

@@ -203,6 +203,8 @@ OPTION_SETS = [
     {"unroll": 0}, {"evict_first": False}, {"red_evict_last": True}, {"group_slots": 2}, {"threads": 256, "min_blocks": 4},
     {"smem_budget": 16384}, {"block_times": True}, {"sort": True}, {"sort": True, "sort_lanes": 128}, {"sort": True, "sort_lanes": 32},
     {"sort": True, "sort_ept": 1}, {"sort": True, "sort_sum": "bins", "sort_split": 1}, {"sort": True, "sort_sum": "bins", "sort_split": 16}, {"sort": True, "sort_sum": "bins"}, {"sort": True, "sort_sum": "chunks", "sort_lanes": 32}, {"sort": True, "sort_sum": "bins", "sort_lanes": 256}, {"sort": False},
+    {"sort": True, "sort_pipe": True}, {"sort": True, "sort_pipe": False}, {"sort": True, "sort_pipe": True, "sort_ept": 1},
+    {"sort": True, "sort_pipe": True, "sort_ept": 4}, {"sort": True, "sort_pipe": True, "sort_threads": 512},
 ]
 
 
@@ -246,28 +248,31 @@ def _sortable(name):
         return False
 
 
+@pytest.mark.parametrize("pipe", [False, True], ids=["phases", "pipe"])
 @pytest.mark.parametrize("name", [n for n in CASES if n not in LIBM_CASES])
-def test_golden_sorted_strategy(name):
+def test_golden_sorted_strategy(name, pipe):
     """Every golden case that has float64 terms on fixed axes, with the sorted strategy of big books forced on
-    (per-tile counting sort by bin index + chunked sums instead of per-event atomics): same bars as everywhere."""
+    (per-tile counting sort by bin index + chunked sums instead of per-event atomics): same bars as everywhere.
+    Both kernels: phases behind block barriers, and the producer / consumer pipeline (``sort_pipe``)."""
     from histbook_b200 import fillable
     if not _sortable(name):
         pytest.skip("no float64 term on a fixed-axis histogram: nothing to sort")
     case = golden_util.load()[name]
     fills = golden_util.fills(case)
     try:
-        fillable.set_options(sort=True)
+        fillable.set_options(sort=True, sort_pipe=pipe)
         got = run_spec(case["spec"], fills)
         assert fillable.last_stats.get("sorted"), name
+        assert pipe or not fillable.last_stats["sorted"].get("pipe"), name      # (a pipeline that does not fit falls back to phases)
     finally:
-        fillable.set_options(sort=None)
+        fillable.set_options(sort=None, sort_pipe=None)
     bound = None
     for arrays in fills:
         bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
     compare(name, case["spec"], got, golden_util.outputs(case), bound)
 
 
-@pytest.mark.parametrize("lanes,summing", [(32, "bins"), (128, "bins"), (64, "chunks"), (128, "chunks")])
+@pytest.mark.parametrize("lanes,summing", [(32, "bins"), (128, "bins"), (64, "chunks"), (128, "chunks"), (32, "pipe")])
 def test_sorted_strategy_on_degenerate_distributions(lanes, summing):
     """Every event in ONE bin, two alternating bins, masked rows, NaN weights, tiles with a single live event, more
     bins than lanes: the counting sort and the bin ownership of codegen.SortGroup."""
@@ -276,8 +281,11 @@ def test_sorted_strategy_on_degenerate_distributions(lanes, summing):
     spec = dict(cases["c4"]["spec"], hists=cases["c4"]["spec"]["hists"][:8])
     rs = numpy.random.RandomState(3)
     try:
-        fillable.set_options(sort=True, sort_lanes=lanes, sort_sum=summing)
-        for n in (1, 31, 2048, 2049, 4096 + 64, 303104 + 17, 700001):
+        if summing == "pipe":
+            fillable.set_options(sort=True, sort_pipe=True)
+        else:
+            fillable.set_options(sort=True, sort_lanes=lanes, sort_sum=summing, sort_pipe=False)
+        for n in (1, 31, 1536, 1537, 2048, 2049, 4096 + 64, 303104 + 17, 454656 + 1, 700001):
             variants = []
             const = {"x": numpy.full(n, 0.25), "y": numpy.full(n, -0.75), "z": numpy.full(n, 1.5), "w": numpy.full(n, 1.25), "n": numpy.full(n, 4, dtype=numpy.int64)}
             variants.append(const)
@@ -297,7 +305,7 @@ def test_sorted_strategy_on_degenerate_distributions(lanes, summing):
                     bound = fill_oracle.fill(spec, a, bound, absolute=True)
                 compare("degenerate n=%d" % n, spec, got, [golden_util.flatten(e) for e in exp], bound)
     finally:
-        fillable.set_options(sort=None, sort_lanes=None, sort_sum=None)
+        fillable.set_options(sort=None, sort_lanes=None, sort_sum=None, sort_pipe=None)
 
 
 def test_book_of_320_histograms_is_split_into_parts():

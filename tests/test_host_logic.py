@@ -67,6 +67,26 @@ def test_generated_kernels_compile_for_sm100a(name):
         assert keys is None
 
 
+def test_pipelined_sorted_kernel_compiles_and_is_laid_out_twice():
+    """sort_pipe: producer warps evaluate tile k + 1 while one consumer warp per sort group sums tile k; tick counters,
+    sorted event numbers and staged values exist twice and everything fits the SM's shared memory."""
+    case = golden_util.load()["c4"]
+    kern = codegen.generate(case["spec"], _coltypes(case), {"sort_pipe": True})
+    pipe = kern.sorted["pipe"]
+    assert pipe["consumer_warps"] == 8 and pipe["producers"] == 1024 - 8 * 32 and kern.tile == pipe["producers"] * kern.sorted["ept"]
+    assert kern.smem_bytes <= 227 * 1024
+    assert "bar.arrive" in kern.source and kern.source.count("hb_sort_find(") == 1          # ONE copy of the summing code for 8 like groups
+    assert engine.compile_source(kern.source)[:4] == b"\x7fELF"
+    # a forced single group (any histogram with a float64 term)
+    case = golden_util.load()["c3"]
+    kern = codegen.generate(case["spec"], _coltypes(case), {"sort": True, "sort_pipe": True})
+    assert kern.sorted["pipe"]["consumer_warps"] == 1 and kern.tile == 992 * 2
+    assert engine.compile_source(kern.source)[:4] == b"\x7fELF"
+    # and the kernel with phases behind block barriers is still there
+    kern = codegen.generate(golden_util.load()["c4"]["spec"], _coltypes(golden_util.load()["c4"]), {"sort_pipe": False})
+    assert "pipe" not in kern.sorted and "bar.arrive" not in kern.source
+
+
 def test_every_golden_spec_lowers():
     for name in golden_util.names():
         case = golden_util.load()[name]
