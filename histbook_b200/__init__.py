@@ -166,6 +166,140 @@ def _hist_project(self, *axis):
     return out
 
 
+def _device_resident(self):
+    """The store of a histogram without group axes whose bins are current on the device only, else None."""
+    st = self.__dict__.get("_hb")
+    if st is None or st.groups or len(self._group) > 0 or st.host_valid or not st.dev_valid or st.arena is None:
+        return None
+    return st
+
+
+def _hist_prefill(self):
+    """``Hist._prefill`` (histbook/hist.py:381-390) asks ``self._content is None`` -- which, for bins that live on the device,
+    would download them and hand the authority to the host copy.  ``table``, ``fraction`` and others call it first: bins on
+    the device are content, nothing to allocate."""
+    st = self.__dict__.get("_hb")
+    if st is not None and st.dev_valid and not st.host_valid and st.arena is not None:
+        return
+    return _originals["Hist._prefill"](self)
+
+
+def _hist_selectaxis(self, cutaxis, newaxis, cutslice, dropnull):
+    """``Hist._selectaxis`` (histbook/proj.py:470-496), the array half of ``Hist.select`` and ``Hist.fraction``: the
+    reference copies ``content[..., cutslice, ...]``.  For device-resident bins that strided copy runs on the device
+    (hb_arena_slice) and the selected histogram stays there; group axes and host-resident bins take the reference's path."""
+    hb = _ref.load()
+    st = _device_resident(self)
+    if st is None or not isinstance(cutslice, slice) or not any(x is cutaxis for x in self._fixed):
+        return _originals["Hist._selectaxis"](self, cutaxis, newaxis, cutslice, dropnull)
+    i = [x is cutaxis for x in self._fixed].index(True)
+    shape = tuple(int(x) for x in self._shape)
+    start, stop, step = cutslice.indices(shape[i])
+    count = len(range(start, stop, step))
+    axis = [newaxis if x is cutaxis else x for x in self._group + self._fixed + self._profile]
+    null = isinstance(newaxis, hb.axis._nullaxis)
+    if dropnull:
+        axis = [x for x in axis if not isinstance(x, hb.axis._nullaxis)]
+    out = self.__class__(*axis, weight=self._weightoriginal, filter=self._filteroriginal, defs=dict(self._defs),
+                         attachment=dict(self._attachment))
+    outer = 1
+    for t in shape[:i]:
+        outer *= t
+    inner = 1
+    for t in shape[i + 1:]:
+        inner *= t
+    newshape = shape[:i] + (() if (dropnull and null) else (count,)) + shape[i + 1:]
+    if count == 0 or (dropnull and null and count != 1) or tuple(int(x) for x in out._shape) != newshape:
+        return _originals["Hist._selectaxis"](self, cutaxis, newaxis, cutslice, dropnull)
+    from histbook_b200.store import Store
+    new = Store(out._shape, [], None)
+    new.arena = st.arena.slice(outer, shape[i], inner, start, step, count)
+    new.host, new.host_valid, new.dev_valid, new.nonempty = None, False, True, True
+    out.__dict__["_hb"] = new
+    return out
+
+
+def _hist_drop(self, *profile):
+    """``Hist.drop`` (histbook/proj.py:182-225).  Dropping EVERY profile of a device-resident histogram -- what ``fraction``
+    does first -- keeps the trailing [sumw, (sumw2)] columns of every bin: a slice on the device.  Anything else takes the
+    reference's path."""
+    hb = _ref.load()
+    st = _device_resident(self)
+    if st is None or len(profile) == 0:
+        return _originals["Hist.drop"](self, *profile)
+    profs = [x if isinstance(x, hb.axis.Axis) else self.axis.profile(x) for x in profile]
+    for prof in profs:
+        if prof not in self._profile:
+            raise IndexError("no such profile axis: {0}".format(prof))
+    if any(prof not in profs for prof in self._profile):
+        return _originals["Hist.drop"](self, *profile)
+    weighted = self._weightoriginal is not None
+    keep = [self._sumwindex] + ([self._sumw2index] if weighted else [])
+    shape = tuple(int(x) for x in self._shape)
+    out = self.__class__(*(self._group + self._fixed), weight=self._weightoriginal, filter=self._filteroriginal, defs=dict(self._defs),
+                         attachment=dict(self._attachment))
+    if keep != list(range(keep[0], keep[0] + len(keep))) or tuple(int(x) for x in out._shape) != shape[:-1] + (len(keep),):
+        return _originals["Hist.drop"](self, *profile)
+    nrows = 1
+    for t in shape[:-1]:
+        nrows *= t
+    from histbook_b200.store import Store
+    new = Store(out._shape, [], None)
+    new.arena = st.arena.slice(nrows, shape[-1], 1, keep[0], 1, len(keep))
+    new.host, new.host_valid, new.dev_valid, new.nonempty = None, False, True, True
+    out.__dict__["_hb"] = new
+    return out
+
+
+def _hist_table(self, *profile, **opts):
+    """``Hist.table`` (histbook/proj.py:498-640).  For device-resident bins without group axes the per-bin columns -- count,
+    its error, effective count, profile means and their errors -- are computed on the device (hb_arena_table, the same IEEE
+    operations in the same order: bit-identical) and only the table is read back; ``normalized=True``, group axes and
+    host-resident bins take the reference's path."""
+    hb = _ref.load()
+    st = _device_resident(self)
+    if st is None or opts.get("normalized", False):
+        return _originals["Hist.table"](self, *profile, **opts)
+    opts = dict(opts)
+    count, effcount, error = opts.pop("count", True), opts.pop("effcount", False), opts.pop("error", True)
+    opts.pop("normalized", None)
+    recarray, showcolumns = opts.pop("recarray", True), opts.pop("columns", False)
+    if len(opts) > 0:
+        raise TypeError("unrecognized options for Hist.table: {0}".format(" ".join(opts)))
+    profs = []
+    for x in profile:
+        prof = x if isinstance(x, hb.axis.Axis) else self.axis.profile(x)
+        if prof not in self._profile:
+            raise IndexError("no such profile axis: {0}".format(prof))
+        profs.append(self._profile[self._profile.index(prof)])
+    columns = []
+    if count:
+        columns.append("count()")
+        if error:
+            columns.append("err(count())")
+    if effcount:
+        columns.append("effcount()")
+    for prof in profs:
+        columns.append(str(prof.expr))
+        if error:
+            columns.append("err({0})".format(str(prof.expr)))
+    if not columns or len(profs) > 16:
+        return _originals["Hist.table"](self, *profile, count=count, effcount=effcount, error=error, recarray=recarray, columns=showcolumns)
+    shape = tuple(int(x) for x in self._shape)
+    nrows = 1
+    for t in shape[:-1]:
+        nrows *= t
+    weighted = self._weightparsed is not None
+    arena = st.arena.table(nrows, shape[-1], self._sumwindex, self._sumw2index if weighted else None, count, error, effcount,
+                           [(prof._sumwxindex, prof._sumwx2index) for prof in profs])
+    flat = arena.read().reshape(nrows, len(columns))
+    if recarray:
+        out = flat.view([(x, flat.dtype) for x in columns]).reshape(shape[:-1])
+    else:
+        out = flat.reshape(shape[:-1] + (len(columns),))
+    return (out, columns) if showcolumns else out
+
+
 # ----------------------------------------------------------------------------- merge algebra on the device
 
 def _device_store(hist):
@@ -341,6 +475,8 @@ def install():
         "Hist.__add__": Hist.__dict__["__add__"], "Hist.__iadd__": Hist.__dict__["__iadd__"],
         "Hist.__mul__": Hist.__dict__["__mul__"], "Hist.__imul__": Hist.__dict__["__imul__"],
         "Hist.tojson": Hist.__dict__["tojson"], "Hist.__getstate__": Hist.__dict__["__getstate__"],
+        "Hist._selectaxis": hb.proj.Projectable.__dict__["_selectaxis"], "Hist.table": hb.proj.Projectable.__dict__["table"],
+        "Hist.drop": hb.proj.Projectable.__dict__["drop"], "Hist._prefill": Hist.__dict__["_prefill"],
         "Book._changed": Book.__dict__["_changed"],
     })
     Hist._content = property(_content_get, _content_set)
@@ -349,6 +485,8 @@ def install():
     Hist.copy = _hist_copy
     Hist.copyonfill = _hist_copyonfill
     Hist.project = _hist_project
+    Hist._selectaxis, Hist.table, Hist.drop = _hist_selectaxis, _hist_table, _hist_drop
+    Hist._prefill = _hist_prefill
     Hist.__add__, Hist.__iadd__, Hist.__mul__, Hist.__imul__ = _hist_add, _hist_iadd, _hist_mul, _hist_imul
     Hist.tojson, Hist.__getstate__ = _hist_tojson, _hist_getstate
     Book._changed = _book_changed
@@ -369,6 +507,8 @@ def uninstall():
     Hist.copy = _originals["Hist.copy"]
     Hist.copyonfill = _originals["Hist.copyonfill"]
     del Hist.project                      # falls back to the inherited Projectable.project
+    del Hist._selectaxis, Hist.table, Hist.drop
+    Hist._prefill = _originals["Hist._prefill"]
     for name in ("__add__", "__iadd__", "__mul__", "__imul__", "tojson", "__getstate__"):
         setattr(Hist, name, _originals["Hist." + name])
     Book._changed = _originals["Book._changed"]

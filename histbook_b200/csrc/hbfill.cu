@@ -751,6 +751,95 @@ extern "C" int hb_arena_project(const hb_arena* src, int ndim, const int64_t* sh
     return HB_OK;
 }
 
+// Hist.select (histbook/proj.py:470-496, `content[slc].copy()` with a slice on ONE axis) on the device: the arena is viewed
+// as [outer][len][inner], element k of the cut axis comes from start + k * step.
+__global__ void hb_slice_kernel(const double* __restrict__ src, double* __restrict__ dst, long long total, long long len,
+                                long long inner, long long start, long long step, long long count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long in = i % inner;
+        const long long rest = i / inner;
+        const long long k = rest % count;
+        const long long o = rest / count;
+        dst[i] = src[(o * len + start + k * step) * inner + in];
+    }
+}
+
+extern "C" int hb_arena_slice(const hb_arena* src, int64_t outer, int64_t len, int64_t inner, int64_t start, int64_t step, int64_t count, hb_arena** out) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!src || !out || outer < 0 || len < 0 || inner < 1 || count < 0 || step == 0) return fail(HB_ERR_ARG, "bad hb_arena_slice arguments");
+    if (outer * len * inner > src->n) return fail(HB_ERR_ARG, "hb_arena_slice: shape larger than the arena");
+    if (count > 0) {
+        const long long last = start + (count - 1) * step;
+        if (start < 0 || start >= len || last < 0 || last >= len) return fail(HB_ERR_ARG, "hb_arena_slice: slice outside the axis");
+    }
+    const long long total = outer * count * inner;
+    rc = hb_arena_create(total, out);
+    if (rc) return rc;
+    if (total == 0) return HB_OK;
+    hb_slice_kernel<<<grid_for(total), 256, 0, g_stream>>>(src->ptr, (*out)->ptr, total, len, inner, start, step, count);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+// Hist.table (histbook/proj.py:577-627, `handlearray`) on the device: per bin the (weighted) count, its error, the effective
+// count and mean / error of the mean of the profiles, operation for operation what numpy does there (IEEE multiply, divide,
+// subtract and square root, no contraction into FMAs), so the columns are bit-identical to the reference's.
+#define HB_TABLE_MAX_PROF 16
+struct HbTable {
+    int ncol, sumw, sumw2, flags, nprof, ncolumns;
+    int sumwx[HB_TABLE_MAX_PROF], sumwx2[HB_TABLE_MAX_PROF];
+};
+__global__ void hb_table_kernel(const double* __restrict__ src, double* __restrict__ dst, long long nrows, const HbTable t) {
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nrows; b += (long long)gridDim.x * blockDim.x) {
+        const double* __restrict__ row = src + b * t.ncol;
+        double* __restrict__ o = dst + b * t.ncolumns;
+        const double sumw = row[t.sumw];
+        const double sumw2 = t.sumw2 >= 0 ? row[t.sumw2] : 0.0;
+        int k = 0;
+        if (t.flags & 1) {
+            o[k++] = sumw;
+            if (t.flags & 2) o[k++] = sqrt(t.sumw2 >= 0 ? sumw2 : sumw);
+        }
+        const bool good = sumw > 0.0;
+        const double effcnt = t.sumw2 >= 0 ? __ddiv_rn(__dmul_rn(sumw, sumw), sumw2) : sumw;
+        if (t.flags & 4) o[k++] = good ? effcnt : 0.0;
+        for (int j = 0; j < t.nprof; ++j) {
+            const double mean = __ddiv_rn(row[t.sumwx[j]], sumw);
+            o[k++] = good ? mean : 0.0;
+            if (t.flags & 2) {
+                const double var = __dsub_rn(__ddiv_rn(row[t.sumwx2[j]], sumw), __dmul_rn(mean, mean));
+                o[k++] = good ? sqrt(__ddiv_rn(var, effcnt)) : 0.0;
+            }
+        }
+    }
+}
+
+extern "C" int hb_arena_table(const hb_arena* src, int64_t nrows, int ncol, int sumw, int sumw2, int flags, int nprof,
+                              const int32_t* sumwx, const int32_t* sumwx2, hb_arena** out) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!src || !out || nrows < 0 || ncol < 1 || sumw < 0 || sumw >= ncol || sumw2 >= ncol || nprof < 0 || nprof > HB_TABLE_MAX_PROF ||
+        (nprof > 0 && (!sumwx || !sumwx2)))
+        return fail(HB_ERR_ARG, "bad hb_arena_table arguments");
+    if (nrows * ncol > src->n) return fail(HB_ERR_ARG, "hb_arena_table: shape larger than the arena");
+    HbTable t;
+    memset(&t, 0, sizeof(t));
+    t.ncol = ncol; t.sumw = sumw; t.sumw2 = sumw2; t.flags = flags; t.nprof = nprof;
+    for (int j = 0; j < nprof; ++j) {
+        if (sumwx[j] < 0 || sumwx[j] >= ncol || sumwx2[j] < 0 || sumwx2[j] >= ncol) return fail(HB_ERR_ARG, "hb_arena_table: profile column outside the row");
+        t.sumwx[j] = sumwx[j]; t.sumwx2[j] = sumwx2[j];
+    }
+    t.ncolumns = ((flags & 1) ? ((flags & 2) ? 2 : 1) : 0) + ((flags & 4) ? 1 : 0) + nprof * ((flags & 2) ? 2 : 1);
+    if (t.ncolumns == 0) return fail(HB_ERR_ARG, "hb_arena_table: no columns asked for");
+    rc = hb_arena_create(nrows * t.ncolumns, out);
+    if (rc) return rc;
+    if (nrows == 0) return HB_OK;
+    hb_table_kernel<<<grid_for(nrows), 256, 0, g_stream>>>(src->ptr, (*out)->ptr, nrows, t);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
 extern "C" void* hb_arena_ptr(const hb_arena* a) { return a ? (void*)a->ptr : nullptr; }
 extern "C" int64_t hb_arena_size(const hb_arena* a) { return a ? a->n : 0; }
 

@@ -78,6 +78,8 @@ SYMBOLS = {
     "hb_arena_scale": (_I, [_P, ctypes.c_double]),
     "hb_arena_snapshot": (_I, [_I, _PP, ctypes.POINTER(_I64), ctypes.POINTER(_I64), ctypes.POINTER(_I64), _P]),
     "hb_arena_project": (_I, [_P, _I, ctypes.POINTER(_I64), _I, ctypes.POINTER(ctypes.c_int32), _PP]),
+    "hb_arena_slice": (_I, [_P, _I64, _I64, _I64, _I64, _I64, _I64, _PP]),
+    "hb_arena_table": (_I, [_P, _I64, _I, _I, _I, _I, _I, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _PP]),
     "hb_arena_ptr": (_P, [_P]),
     "hb_arena_size": (_I64, [_P]),
     "hb_fill": (_I, [_P, _I, ctypes.POINTER(hb_column), _I64, _I, _PP, _I, _PP, _I, ctypes.POINTER(ctypes.c_int32), _I, ctypes.POINTER(hb_stats)]),
@@ -296,6 +298,24 @@ class Arena(object):
         karr = (ctypes.c_int32 * len(shape))(*[1 if k else 0 for k in keep])
         out = ctypes.c_void_p()
         check(lib().hb_arena_project(self._h, len(shape), arr, int(ncol), karr, ctypes.byref(out)))
+        return Arena(_handle=out)
+
+    def slice(self, outer, length, inner, start, step, count):
+        """[outer][length][inner] -> [outer][count][inner], element k of the middle axis from start + k * step (Hist.select on
+        the device); returns a new Arena."""
+        out = ctypes.c_void_p()
+        check(lib().hb_arena_slice(self._h, int(outer), int(length), int(inner), int(start), int(step), int(count), ctypes.byref(out)))
+        return Arena(_handle=out)
+
+    def table(self, nrows, ncol, sumw, sumw2, count, error, effcount, profiles):
+        """Hist.table's columns per bin (histbook/proj.py:577-627) computed on the device; ``profiles`` = [(sumwx column, sumwx2
+        column)]; sumw2 = None for an unweighted histogram.  Returns a new Arena of nrows x ncolumns doubles."""
+        xs = (ctypes.c_int32 * max(len(profiles), 1))(*[int(a) for a, b in profiles])
+        x2s = (ctypes.c_int32 * max(len(profiles), 1))(*[int(b) for a, b in profiles])
+        flags = (1 if count else 0) | (2 if error else 0) | (4 if effcount else 0)
+        out = ctypes.c_void_p()
+        check(lib().hb_arena_table(self._h, int(nrows), int(ncol), int(sumw), -1 if sumw2 is None else int(sumw2), flags, len(profiles), xs, x2s,
+                                   ctypes.byref(out)))
         return Arena(_handle=out)
 
     @property

@@ -126,6 +126,16 @@ int hb_arena_snapshot(int nseg, hb_arena* const* src, const int64_t* src_off, co
  * `shape` = bins per fixed axis (ndim <= 8), ncol = size of the last (column) dimension, which is always kept.
  * *out is a new arena of prod(kept shape) * ncol doubles. */
 int hb_arena_project(const hb_arena* src, int ndim, const int64_t* shape, int ncol, const int32_t* keep, hb_arena** out);
+/* Hist.select on the device (histbook/proj.py:470-496: `content[slc].copy()` with a slice on ONE axis, the only array work
+ * of `_selectaxis`): the arena is viewed as [outer][len][inner]; *out is a new arena [outer][count][inner] whose element k
+ * along the cut axis is element start + k * step of the source. */
+int hb_arena_slice(const hb_arena* src, int64_t outer, int64_t len, int64_t inner, int64_t start, int64_t step, int64_t count, hb_arena** out);
+/* Hist.table on the device (histbook/proj.py:577-627 `handlearray`): *out is a new arena of nrows x ncolumns doubles with, per
+ * bin, [count, err(count)] (flags & 1, & 2), [effcount] (flags & 4) and per profile j [mean, err(mean)] -- the columns in the
+ * reference's order, computed with the same IEEE operations (bit-identical).  sumw / sumw2 / sumwx[j] / sumwx2[j] are column
+ * numbers inside a row of ncol doubles; sumw2 = -1 for an unweighted histogram.  `normalized` tables stay on the host. */
+int hb_arena_table(const hb_arena* src, int64_t nrows, int ncol, int sumw, int sumw2, int flags, int nprof,
+                   const int32_t* sumwx, const int32_t* sumwx2, hb_arena** out);
 void* hb_arena_ptr(const hb_arena* a);                   /* device pointer (for NCCL / DLPack wrapping) */
 int64_t hb_arena_size(const hb_arena* a);
 

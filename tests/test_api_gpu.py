@@ -185,6 +185,100 @@ def test_project_on_the_device():                             # histbook/proj.py
     assert sum(v.sum() for v in g.project("c", "x")._content.values()) == 1000
 
 
+def _host_twin(h):
+    """A copy of ``h`` whose bins are host-resident (a plain numpy ``_content``): every read-side method takes the
+    reference's own code on it."""
+    t = h.copy()
+    t._content = numpy.array(histbook_b200.peek(h))
+    st = t.__dict__["_hb"]
+    assert st.host_valid
+    return t
+
+
+def test_table_select_and_fraction_on_the_device():           # histbook/proj.py:298-496 (select), 498-640 (table), 642-806 (fraction)
+    """The read side of a device-resident histogram: ``table`` computes its columns on the device (hb_arena_table), ``select``
+    slices there (hb_arena_slice) and the result stays on the device, ``fraction`` is built from both.  Every result is compared
+    bit for bit with the reference's own numpy code run on a host copy of the same bins."""
+    rs = numpy.random.RandomState(5)
+    n = 300000
+    x, y, z, w = rs.normal(0, 1, n), rs.normal(0, 1, n), rs.normal(0, 1, n), rs.uniform(-0.5, 1.5, n)     # (some negative weights)
+    hists = [Hist(bin("x", 40, -3, 3), cut("y > 0"), profile("z"), profile("z**2"), weight="w"),
+             Hist(bin("x", 40, -3, 3), split("y", (-1, 0, 1)), profile("z")),
+             Hist(bin("x", 25, -2, 2, underflow=False, nanflow=False), intbin("k", 0, 4), weight="w"),
+             Hist(bin("x", 30, -3, 3), filter="y > 0")]
+    k = rs.randint(-1, 7, n)
+    for h in hists:
+        h.fill(x=x, y=y, z=z, w=w, k=k)
+        twin = _host_twin(h)
+        st = h.__dict__["_hb"]
+        profs = [str(p.expr) for p in h._profile]
+        with numpy.errstate(all="ignore"):
+            for opts in ({}, {"error": False}, {"effcount": True}, {"count": False, "effcount": True}, {"recarray": False}, {"columns": True},
+                         {"count": False, "error": False, "effcount": True}):
+                for use in ([], profs[:1], profs):
+                    if not use and not opts.get("count", True) and not opts.get("effcount", False):
+                        continue
+                    got, exp = h.table(*use, **opts), twin.table(*use, **opts)
+                    if opts.get("columns"):
+                        assert got[1] == exp[1]
+                        got, exp = got[0], exp[0]
+                    assert got.dtype == exp.dtype and got.shape == exp.shape, (opts, use)
+                    assert got.tobytes() == exp.tobytes(), (opts, use)        # bit for bit, NaN included
+            assert st.dev_valid and not st.host_valid                          # table() did not pull the bins to the host
+            # normalized tables take the reference's path (host) and still agree
+            a, b = h.copy().table(normalized=True), twin.table(normalized=True)
+            assert a.tobytes() == b.tobytes()
+    with pytest.raises(TypeError):
+        hists[0].table(bogus=True)
+    with pytest.raises(IndexError):
+        hists[0].table("nosuch")
+
+    # select: slices along one fixed axis, on the device
+    h = hists[0]
+    twin = _host_twin(h)
+    for expr in ("x < 0", "x >= -1.5", "x >= -1.5 and x < 1.5", "y > 0", "x < 0 and y > 0"):
+        got, exp = h.select(expr), twin.select(expr)
+        gst = got.__dict__["_hb"]
+        assert gst.dev_valid and not gst.host_valid, expr                      # sliced and kept on the device
+        assert got == exp, expr                                                # axes and contents (Hist.__eq__)
+        assert numpy.array_equal(got._content, exp._content) and got._content.shape == tuple(got._shape)
+    h2, twin2 = hists[1], _host_twin(hists[1])
+    for expr in ("y >= 0", "y < -1", "x >= 0 and y >= 0 and y < 1"):
+        got, exp = h2.select(expr), twin2.select(expr)
+        assert got == exp and numpy.array_equal(got._content, exp._content), expr
+    with pytest.raises(ValueError):
+        h.select("x < 0.01")                                                   # not a bin edge: same error as the reference
+    # a selected histogram is an ordinary one: fill it further, tabulate it
+    sel = h.select("x >= 0")
+    before = sel._content.copy()
+    sel.fill(x=x[:1000], y=y[:1000], z=z[:1000], w=w[:1000])
+    assert not numpy.array_equal(sel._content, before)
+
+    # drop: every profile dropped = the trailing [sumw, sumw2] columns, on the device
+    d, dt = hists[0].drop(*hists[0]._profile), _host_twin(hists[0]).drop(*hists[0]._profile)
+    assert d.__dict__["_hb"].dev_valid and not d.__dict__["_hb"].host_valid
+    assert d == dt and numpy.array_equal(d._content, dt._content)
+    d, dt = hists[1].drop("z"), _host_twin(hists[1]).drop("z")                 # unweighted: [sumw]
+    assert d == dt and numpy.array_equal(d._content, dt._content)
+    with pytest.raises(IndexError):
+        hists[0].drop("nosuch")
+
+    # fraction (efficiency of a cut with its interval): drop + project + select underneath, all on the device
+    with numpy.errstate(all="ignore"):
+        for kw in ({}, {"error": "normal"}, {"error": "wilson"}, {"level": 2}):
+            try:
+                exp = _host_twin(hists[0]).fraction("y > 0", **kw)
+            except Exception as e:                                             # (whatever the reference raises, e.g. for a missing scipy)
+                with pytest.raises(type(e)):
+                    hists[0].fraction("y > 0", **kw)
+                continue
+            got = hists[0].fraction("y > 0", **kw)
+            assert hists[0].__dict__["_hb"].dev_valid and not hists[0].__dict__["_hb"].host_valid      # the bins never left the device
+            assert got.dtype == exp.dtype and got.shape == exp.shape
+            for name in got.dtype.names:
+                assert numpy.allclose(got[name], exp[name], rtol=1e-12, atol=0, equal_nan=True), (kw, name)
+
+
 def test_pickle_and_json_roundtrip():                         # tests/test_hist.py:437-449
     h = Hist(split("x", (1, 2, 3)), bin("y", 10, 0, 1), defs={"y": "x + 0.1"}, weight="sqrt(x)", filter="x > 2")
     assert h == pickle.loads(pickle.dumps(h))
