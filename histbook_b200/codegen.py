@@ -1134,6 +1134,7 @@ class Kernel(object):
         self.key = None
         self.group_aux = {}         # fill kernel: hist id -> aux slot of its dense slot map (this fill's key combinations -> slab slot)
         self.goal_aux = {}          # fill kernel: tree key of a group goal -> aux slot of the goal's key table of this fill
+        self.group_leader = {}      # fill kernel: hist id -> first histogram with the same group goals (its slot lookup may be shared)
         self.window = None          # hot-window histogram: dict(hid, bpb, wmax, totbins, ncol, col, nf)
         self.group_goals = []       # keys kernel: [(tree key, info dict)] in aux order
         self.fx_terms = []          # [(i, hist id, term index)] of the fixed-point terms; scale of term i in p.win[2 + i]
@@ -1915,22 +1916,30 @@ def _goal_lookup(g, aux_slot):
            "const int gn_%s = (int)gq_%s[0];" % (n, n)]
     if g.dtype.kind == "f" and not g.extra["nanflow"]:
         # nanflow=False: NaN rows are dropped (calc/__init__.py:189-192)
-        out.append("const int gd_%s = (%s != %s) ? -1 : hb_key_find(gq_%s + 2, gn_%s, hb_keybits(%s));" % (n, g.c, g.c, n, n, g.c))
+        out.append("const int gd_%s = (%s != %s) ? -1 : hb_key_find(gq_%s, hb_keybits(%s));" % (n, g.c, g.c, n, g.c))
     else:
-        out.append("const int gd_%s = hb_key_find(gq_%s + 2, gn_%s, hb_keybits(%s));" % (n, n, n, g.c))
+        out.append("const int gd_%s = hb_key_find(gq_%s, hb_keybits(%s));" % (n, n, g.c))
     return out
 
 
-def _group_lookup(hp, aux_slot):
+def _group_lookup(hp, aux_slot, leader=None):
     """C lines that turn the group keys of one event into the slab slot of hist ``hp`` (or reject the row): the
-    positions of its goals' keys (``_goal_lookup``) index the histogram's dense slot map of this fill."""
-    out = ["const int* const gm = reinterpret_cast<const int*>(p.aux[%d]);" % aux_slot]
-    okg = " && ".join("gd_%s >= 0" % g.c for g in hp.groups)
+    positions of its goals' keys (``_goal_lookup``) index the histogram's dense slot map of this fill.
+    Histograms that group by the same goals form a *signature*; its first histogram (``leader`` None) looks the slot up, the
+    others take that slot when the host passes a null map -- their maps are the same bytes (fillable._bind_stores), the usual
+    case for the histograms of a book -- and look it up in their own map otherwise: c4 does one map load per event, not eight."""
+    sig = "_".join(g.c for g in hp.groups)
     comb = "gd_%s" % hp.groups[0].c
     for g in hp.groups[1:]:
         comb = "(%s) * gn_%s + gd_%s" % (comb, g.c, g.c)
-    out.append("const bool okg = %s;" % okg)
-    out.append("const int slot = okg ? gm[%s] : -1;" % comb)
+    out = ["const int* const gm = reinterpret_cast<const int*>(p.aux[%d]);" % aux_slot]
+    if leader is None:
+        out.append("const bool okg = %s;" % " && ".join("gd_%s >= 0" % g.c for g in hp.groups))
+        out.append("const int slot = okg ? gm[%s] : -1;" % comb)
+        out.append("okg_%s = okg; slot_%s = slot;" % (sig, sig))
+    else:
+        out.append("const bool okg = okg_%s;" % sig)
+        out.append("const int slot = gm == nullptr ? slot_%s : (okg ? gm[%s] : -1);" % (sig, comb))
     return out
 
 
@@ -2116,6 +2125,8 @@ def generate(spec, coltypes, options=None):
 
     nfx_total = 1 + max([hp.fx_index[t] for hp in plans for t in hp.f64_terms if t in hp.fx_set] + [-1])
     group_aux = {}
+    group_sig = {}                                     # SSA names of a histogram's group goals -> the first histogram with these goals
+    group_leader = {}                                  # histogram -> that first histogram (whose slot it may share)
     goal_aux = {}                                      # tree key of a group goal -> aux slot of its key table
     ev = list(prog.body)
     done_goals = set()
@@ -2138,7 +2149,14 @@ def generate(spec, coltypes, options=None):
             if len(group_aux) + len(goal_aux) >= MAX_AUX - 4:
                 raise UnsupportedError("more than {0} histograms with group axes in one fill".format(MAX_AUX - 4 - len(goal_aux)))
             group_aux[hp.hid] = len(goal_aux) + len(group_aux)
-            ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
+            sig = "_".join(g.c for g in hp.groups)
+            if sig not in group_sig:
+                group_sig[sig] = hp.hid
+                ev.insert(len(ev) - 2, "bool okg_%s = false; int slot_%s = -1;" % (sig, sig))       # (in front of this histogram's block)
+                ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid]))
+            else:
+                group_leader[hp.hid] = group_sig[sig]
+                ev.extend("    " + x for x in _group_lookup(hp, group_aux[hp.hid], leader=group_sig[sig]))
             conds = ["okg", "slot >= 0"] + conds
         conds = ["live"] + conds
         # (lane pairing is for histograms whose every event is a global RED; the few lanes that fall outside a hot
@@ -2404,6 +2422,7 @@ def generate(spec, coltypes, options=None):
         k.sorted["staged"] = len(layout["staged"])
     k.inexact = set(prog.inexact)
     k.group_aux = group_aux
+    k.group_leader = group_leader
     k.goal_aux = goal_aux
     k.key = hashlib.sha256(k.source.encode()).hexdigest()
     return k

@@ -394,6 +394,34 @@ def _discover(plan, keys, kprog, cols, length):
             return discovered
 
 
+def perfect_multiplier(patterns):
+    """An odd 64-bit multiplier M for which (key * M mod 2**64) >> 60 differs for all of ``patterns`` (at most 8 keys over 16
+    entries: one candidate in eight works for 8 keys), or 0 if none of the candidates does."""
+    if not 0 < len(patterns) <= 8:
+        return 0
+    m = 0x9E3779B97F4A7C15
+    for _ in range(4096):
+        if len(set(((p * m) & 0xFFFFFFFFFFFFFFFF) >> 60 for p in patterns)) == len(patterns):
+            return m
+        m = (m * 0xD1342543DE82EF95 + 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF | 1
+    return 0
+
+
+def goal_table(patterns):
+    """Device table of one group goal (hb_template.cuh hb_key_find): [n, M, the fill's keys as ascending unsigned 64-bit
+    patterns (padded to 8), and -- for up to 8 keys -- sixteen (key, position) entries addressed by (key * M) >> 60]."""
+    patterns = tuple(patterns)
+    mult = perfect_multiplier(patterns)
+    words = [len(patterns), mult] + list(patterns) + [0] * max(0, 8 - len(patterns))
+    if mult:
+        entries = [(0, 0xFFFFFFFFFFFFFFFF)] * 16
+        for pos, p in enumerate(patterns):
+            entries[((p * mult) & 0xFFFFFFFFFFFFFFFF) >> 60] = (p, pos)
+        for key, pos in entries:
+            words.extend((key, pos))
+    return words
+
+
 def _bind_stores(plan, kern, hists, discovered):
     """The stores of ``hists`` made current on the device, group keys of this fill admitted; returns (stores, aux
     pointers of the kernel's group tables: per goal the fill's keys, per group histogram its dense slot map)."""
@@ -406,7 +434,7 @@ def _bind_stores(plan, kern, hists, discovered):
             patterns = tuple(sorted(int(x) for x in discovered[goalkey][0]))
             cached = plan.goal_tables.get(goalkey)
             if cached is None or cached[0] != patterns:
-                cached = plan.goal_tables[goalkey] = (patterns, engine.DeviceBuffer(numpy.array((len(patterns), 0) + patterns + (0,) * max(0, 8 - len(patterns)), dtype=numpy.uint64)))
+                cached = plan.goal_tables[goalkey] = (patterns, engine.DeviceBuffer(numpy.array(goal_table(patterns), dtype=numpy.uint64)))
             aux[slot] = cached[1].ptr
     stores = []
     for hid, (hist, hspec) in enumerate(zip(hists, plan.spec["hists"])):
@@ -428,7 +456,13 @@ def _bind_stores(plan, kern, hists, discovered):
             st.groups = infos
             st.to_device()
             st.admit(fill_keys)
-            aux[kern.group_aux[hid]] = st.table[1].ptr
+            # histograms that group by the same goals usually hold the same keys in the same slots (they were filled together):
+            # a null pointer tells the kernel to use the slot its signature's first histogram looked up (codegen._group_lookup)
+            leader = kern.group_leader.get(hid, hid)
+            if leader != hid and stores[leader].table is not None and stores[leader].table[2] == st.table[2]:
+                aux[kern.group_aux[hid]] = 0
+            else:
+                aux[kern.group_aux[hid]] = st.table[1].ptr
         else:
             st.to_device()
         stores.append(st)

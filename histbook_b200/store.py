@@ -100,7 +100,7 @@ class Store(object):
         # group bookkeeping (device side)
         self.tuples = collections.OrderedDict()      # tuple(patterns) -> slot
         self.skeleton = None                          # nested OrderedDict pattern -> ... -> slot, reference insertion order
-        self.table = None                             # (fill key lists, engine.DeviceBuffer): dense slot map of the last fill's key combinations
+        self.table = None                             # (fill key lists, engine.DeviceBuffer, the map's bytes): dense slot map of the last fill's key combinations
         # hot-window privatisation (fillable.choose_window): None = not placed yet, False = not worth it
         self.window = None            # {"table": DeviceBuffer, "bins", "rows"}
         self.window_key = None        # (rows, trail, wmax) of the kernel the window was placed for
@@ -261,4 +261,4 @@ class Store(object):
             import itertools
             for comb, tup in enumerate(itertools.product(*axes)):
                 slotmap[comb] = self.tuples[tup]
-        self.table = (axes, engine.DeviceBuffer(slotmap))
+        self.table = (axes, engine.DeviceBuffer(slotmap), slotmap.tobytes())
