@@ -685,10 +685,11 @@ def hist_index(hp):
 # ================================================================================================
 
 SORT_THREADS = 1024        # one block per SM
-SORT_EPT = 2               # events per thread and tile
+SORT_EPT = "auto"          # events per thread and tile: 3 where everything still fits the shared memory, else 2
 SORT_SUM = "chunks"        # how the sorted events of a tile are summed: "chunks" (balanced: a contiguous chunk per lane) | "bins" (sort_split lanes per bin);
                            # c4, one GPU, 1e9 events: chunks of 64 lanes per group 12.1 Gev/s, of 128 lanes 11.9, bins 11.75 (profiles/r02_sweeps.txt)
 SORT_MAX_BINS = 8192
+SORT_ALIAS_TAILS = True    # the tails of the chunked sums travel through the array of sorted event numbers (27 KB less for c4)
 SORT_PIPE = False          # producer / consumer warps with double-buffered tiles (_emit_kernel_sorted_pipe); "auto" = when it fits
 SORT_MAX_GROUPS = 12       # (key, rank) tickets of a tile live in registers: SORT_EPT x groups of them per thread
 SMEM_MAX = 227 * 1024
@@ -733,10 +734,13 @@ class SortGroup(object):
             hp.sslot[t] = j
             self.dests[j].extend((hp.hid, col, hp.ncol) for col in hp.dest[t])
 
-    def smem_bytes(self, tile, lanes, chunks=False):
+    def smem_bytes(self, tile, lanes, chunks=False, alias=False):
         nv = len(self.values)
         nvp = (nv + 1) // 2 * 2 if chunks else nv                         # chunks: rows of the table are [bin][values], padded to 16 bytes
         tails = (4 * lanes + lanes * 8 * max(nvp, 2)) if chunks else 0      # tail keys, tail values
+        if alias:
+            # the tails travel through the group's array of sorted event numbers (nobody reads it any more by then)
+            return (8 * nvp * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + max(2 * tile + 4 * lanes + 32, tails + 32) + 64) // 16 * 16 + 32
         return (8 * nvp * self.nbins + 4 * self.nbins + 4 * (self.nbins + 4) + 2 * tile + 4 * lanes + 32 + tails + 64) // 16 * 16 + 16
 
 
@@ -849,7 +853,7 @@ def choose_strategies(plans, options, prog=None, layout=None):
     sgroups, staged, sort_bytes = [], [], 0
     pipe = False
     sort_cap = int(options.get("sort_smem", SMEM_MAX - 1024))
-    base_tile = sort_tile = int(options.get("sort_threads", SORT_THREADS)) * int(options.get("sort_ept", SORT_EPT))
+    sort_tile, sort_ept = 0, 2
     sort_lanes = options.get("sort_lanes", "auto")
     group_slots = int(options.get("group_slots", 16))
     if prog is not None:
@@ -878,23 +882,32 @@ def choose_strategies(plans, options, prog=None, layout=None):
             want_pipe = bool(options.get("sort_pipe", SORT_PIPE)) and sort_chunks and len(sgroups) <= 12
             auto_lanes = lanes
             fits = False
-            for pipe in ([True, False] if want_pipe else [False]):
-                sort_tile, lanes = base_tile, auto_lanes
+            # events per thread and tile: bigger tiles mean fewer run ends per event in the summing phase and fewer barriers
+            # (c4: 11.5 / 13.9 / 14.6 Gev/s for tiles of 1024 / 2048 / 3072); "auto" takes 3 where EVERYTHING still fits
+            ept_opt = options.get("sort_ept", SORT_EPT)
+            ept_list = [3, 2] if ept_opt == "auto" else [int(ept_opt)]
+            sort_threads = int(options.get("sort_threads", SORT_THREADS))
+            for pipe, sort_ept in [(pp, ee) for pp in ([True, False] if want_pipe else [False]) for ee in ept_list]:
+                sort_tile, lanes = sort_threads * sort_ept, auto_lanes
                 if pipe:
                     lanes = 32
-                    pipe_threads = int(options.get("sort_threads", SORT_THREADS))
+                    pipe_threads = sort_threads
                     pipe_prod = pipe_threads - 32 * len(sgroups)
-                    sort_tile = pipe_prod * int(options.get("sort_ept", SORT_EPT))
+                    sort_tile = pipe_prod * sort_ept
                     if pipe_prod < 256 or sort_tile > 32768:
                         continue
+                all_fit = False
                 for slots in (group_slots, min(group_slots, 8)):
                     if pipe:
                         sort_bytes = (sum(_pipe_group_fixed(g) for g in sgroups)
                                       + 2 * (sum(_pipe_group_tick(g) + _pipe_sorted_bytes(sort_tile, g) for g in sgroups) + 16 + 8 * len(staged) * sort_tile) + 64)
                     else:
-                        sort_bytes = sum(g.smem_bytes(sort_tile, lanes, sort_chunks) for g in sgroups) + 8 * len(staged) * sort_tile + 64
+                        sort_bytes = sum(g.smem_bytes(sort_tile, lanes, sort_chunks, sort_chunks and bool(options.get("sort_alias_tails", SORT_ALIAS_TAILS))) for g in sgroups) + 8 * len(staged) * sort_tile + 64
                     if sort_bytes + direct_need(slots) <= sort_cap:
+                        all_fit = True
                         break
+                if sort_ept != ept_list[-1] and not all_fit:
+                    continue                               # a bigger tile is not worth a table pushed out to global memory
                 if sort_bytes + 16 * 1024 <= sort_cap:
                     fits = True
                     break
@@ -1075,7 +1088,7 @@ def choose_strategies(plans, options, prog=None, layout=None):
         tile_stride = used - tile0
         used += tile_stride                               # buffer 1
         sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "dump_off": dump_off, "e_off": e_off, "tile": sort_tile,
-                       "lanes": 32, "chunks": True, "threads": pipe_threads, "ept": int(options.get("sort_ept", SORT_EPT)),
+                       "lanes": 32, "chunks": True, "threads": pipe_threads, "ept": sort_ept,
                        "pipe": {"prod": pipe_prod, "tick_stride": tick_stride, "tile_stride": tile_stride, "tick_dump": tick_dump,
                                 "pad": _pipe_pad(sort_tile)}}
         if layout is not None:
@@ -1099,17 +1112,27 @@ def choose_strategies(plans, options, prog=None, layout=None):
         zero_end = used
         for g in sgroups:
             g.off["sorted"] = used
-            used += (2 * sort_tile + 15) // 16 * 16 + 4 * sort_lanes + 32     # (+ room for the chunk padding of HB_SPOS and the dump slot of masked events)
-            if options.get("sort_sum", SORT_SUM) == "chunks":
+            region = (2 * sort_tile + 15) // 16 * 16 + 4 * sort_lanes + 32     # (+ room for the chunk padding of HB_SPOS and the dump slot of masked events)
+            tails_bytes = (4 * sort_lanes + 15) // 16 * 16 + 8 * sort_lanes * max((len(g.values) + 1) // 2 * 2, 2)
+            if options.get("sort_sum", SORT_SUM) == "chunks" and options.get("sort_alias_tails", SORT_ALIAS_TAILS):
+                # tail keys and tail values of the group's lanes re-use the array of sorted event numbers: 27 KB of c4's shared
+                # memory, which buys tiles of 3072 events (sort_ept 3)
+                g.off["tkey"] = used
+                g.off["tval"] = used + (4 * sort_lanes + 15) // 16 * 16
+                used += (max(region, tails_bytes) + 15) // 16 * 16
+            elif options.get("sort_sum", SORT_SUM) == "chunks":
+                used += region
                 g.off["tkey"] = used
                 used += (4 * sort_lanes + 15) // 16 * 16
                 g.off["tval"] = used
                 used += 8 * sort_lanes * max((len(g.values) + 1) // 2 * 2, 2)
+            else:
+                used += region
         e_off = used
         used += 8 * len(staged) * sort_tile
         sort_layout = {"groups": sgroups, "staged": staged, "zero_end": zero_end, "dump_off": dump_off, "e_off": e_off, "tile": sort_tile,
                        "lanes": sort_lanes, "chunks": options.get("sort_sum", SORT_SUM) == "chunks", "threads": int(options.get("sort_threads", SORT_THREADS)),
-                       "ept": int(options.get("sort_ept", SORT_EPT))}
+                       "ept": sort_ept}
         if layout is not None:
             layout.update(sort_layout)
     return used, window
@@ -1587,6 +1610,9 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("                if (runend > p1) tkey = key;       // the run goes on in the next lane: a tail")
             src.append("                else { %s }" % flush)
             src.append("            }")
+            if g.off["tkey"] == g.off["sorted"]:
+                # (the tails re-use the sorted event numbers: every lane of the group must be done reading them)
+                src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))
             src.append("            tkeys[hb_l] = tkey;")
             src.append("            if (tkey >= 0) { %s }" % rowop("tvals + hb_l * %d" % nvp, "r[{h}] = make_double2(a{a}, a{b});", "r[{h}] = make_double2(a{a}, 0.0);"))
             src.append('            asm volatile("bar.sync %%0, %%1;" :: "r"(%d), "r"(HB_LANES) : "memory");' % (1 + wg))

@@ -135,7 +135,7 @@ class Plan(object):
                 if kern is not None and kern.sorted and len(kern.sorted["groups"]) >= int(options.get("parts_min_groups", 4)):
                     k = int(want)
                     extra = {"sort_threads": int(options.get("parts_threads", 512)), "sort_min_blocks": int(options.get("parts_min_blocks", 2)),
-                             "sort_ept": int(options.get("parts_ept", codegen.SORT_EPT)), "sort": True}
+                             "sort_ept": int(options.get("parts_ept", 2)), "sort": True}
             if k <= 1:
                 self.parts[sig] = None
             else:

@@ -205,6 +205,7 @@ OPTION_SETS = [
     {"sort": True, "sort_ept": 1}, {"sort": True, "sort_sum": "bins", "sort_split": 1}, {"sort": True, "sort_sum": "bins", "sort_split": 16}, {"sort": True, "sort_sum": "bins"}, {"sort": True, "sort_sum": "chunks", "sort_lanes": 32}, {"sort": True, "sort_sum": "bins", "sort_lanes": 256}, {"sort": False},
     {"sort": True, "sort_pipe": True}, {"sort": True, "sort_pipe": False}, {"sort": True, "sort_pipe": True, "sort_ept": 1},
     {"sort": True, "sort_pipe": True, "sort_ept": 4}, {"sort": True, "sort_pipe": True, "sort_threads": 512},
+    {"sort": True, "sort_ept": 3}, {"sort": True, "sort_alias_tails": False}, {"sort": True, "sort_ept": 3, "sort_lanes": 128},
 ]
 
 
@@ -285,7 +286,7 @@ def test_sorted_strategy_on_degenerate_distributions(lanes, summing):
             fillable.set_options(sort=True, sort_pipe=True)
         else:
             fillable.set_options(sort=True, sort_lanes=lanes, sort_sum=summing, sort_pipe=False)
-        for n in (1, 31, 1536, 1537, 2048, 2049, 4096 + 64, 303104 + 17, 454656 + 1, 700001):
+        for n in (1, 31, 1536, 1537, 2048, 2049, 3072, 3073, 4096 + 64, 303104 + 17, 454656 + 1, 700001):
             variants = []
             const = {"x": numpy.full(n, 0.25), "y": numpy.full(n, -0.75), "z": numpy.full(n, 1.5), "w": numpy.full(n, 1.25), "n": numpy.full(n, 4, dtype=numpy.int64)}
             variants.append(const)

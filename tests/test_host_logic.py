@@ -80,7 +80,7 @@ def test_pipelined_sorted_kernel_compiles_and_is_laid_out_twice():
     # a forced single group (any histogram with a float64 term)
     case = golden_util.load()["c3"]
     kern = codegen.generate(case["spec"], _coltypes(case), {"sort": True, "sort_pipe": True})
-    assert kern.sorted["pipe"]["consumer_warps"] == 1 and kern.tile == 992 * 2
+    assert kern.sorted["pipe"]["consumer_warps"] == 1 and kern.tile == 992 * kern.sorted["ept"]
     assert engine.compile_source(kern.source)[:4] == b"\x7fELF"
     # and the kernel with phases behind block barriers is still there
     kern = codegen.generate(golden_util.load()["c4"]["spec"], _coltypes(golden_util.load()["c4"]), {"sort_pipe": False})
@@ -236,7 +236,8 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     k = gen("c4")                                   # default: one sort group per axis expression holds its 4 histograms on bin("e", 100)
     assert k.sorted is not None and len(k.sorted["groups"]) == 8 and k.sorted["staged"] == 3 and not k.fx_terms
     assert all(g["nbins"] == 103 and g["values"] == 6 and len(g["hists"]) == 4 for g in k.sorted["groups"])
-    assert sorted(hp.strategy for hp in k.plans).count("sorted") == 32 and k.threads == 1024 and k.tile == 2048
+    assert sorted(hp.strategy for hp in k.plans).count("sorted") == 32 and k.threads == 1024 and k.tile == 3072      # (three events per thread where it all fits)
+    assert gen("c4", sort_ept=2).tile == 2048 and all(hp.strategy in ("sorted", "smem") for hp in k.plans)
     assert k.source.count("atomicAdd(") - k.source.count("hb_sadd_u32") <= 8 + 1     # one ticket per group and event
     k = gen("c3", sort=True)                        # forced on a small book: y and y^2 staged, y^4 = (y^2)^2 recomputed
     assert k.sorted["staged"] == 2 and k.sorted["groups"][0]["values"] == 3 and k.smem_bytes < 227 * 1024 and k.sorted["lanes"] == 64
