@@ -394,29 +394,35 @@ def _discover(plan, keys, kprog, cols, length):
             return discovered
 
 
-def perfect_multiplier(patterns):
-    """An odd 64-bit multiplier M for which (key * M mod 2**64) >> 60 differs for all of ``patterns`` (at most 8 keys over 16
-    entries: one candidate in eight works for 8 keys), or 0 if none of the candidates does."""
-    if not 0 < len(patterns) <= 8:
-        return 0
+def perfect_multiplier(patterns, bits):
+    """An odd 64-bit multiplier M for which (key * M mod 2**64) >> (64 - bits) differs for all of ``patterns``, or 0 if none
+    of the candidates does (with n keys over 2**bits >= n*n/2 entries about one candidate in three works)."""
     m = 0x9E3779B97F4A7C15
     for _ in range(4096):
-        if len(set(((p * m) & 0xFFFFFFFFFFFFFFFF) >> 60 for p in patterns)) == len(patterns):
+        if len(set(((p * m) & 0xFFFFFFFFFFFFFFFF) >> (64 - bits) for p in patterns)) == len(patterns):
             return m
         m = (m * 0xD1342543DE82EF95 + 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF | 1
     return 0
 
 
 def goal_table(patterns):
-    """Device table of one group goal (hb_template.cuh hb_key_find): [n, M, the fill's keys as ascending unsigned 64-bit
-    patterns (padded to 8), and -- for up to 8 keys -- sixteen (key, position) entries addressed by (key * M) >> 60]."""
+    """Device table of one group goal (hb_template.cuh hb_key_find): [n, M, shift, npad, the fill's keys as ascending
+    unsigned 64-bit patterns (npad of them, even, at least 8), and -- for up to 64 keys -- 2**bits (key, position) entries
+    addressed by (key * M) >> shift; M = 0: no hash, the kernel bisects the keys]."""
     patterns = tuple(patterns)
-    mult = perfect_multiplier(patterns)
-    words = [len(patterns), mult] + list(patterns) + [0] * max(0, 8 - len(patterns))
+    n = len(patterns)
+    npad = max(8, n + (n & 1))
+    bits, mult = 0, 0
+    if 0 < n <= 64:
+        bits = 4
+        while (1 << bits) < max(16, n * n // 2):
+            bits += 1
+        mult = perfect_multiplier(patterns, bits)
+    words = [n, mult, 64 - bits, npad] + list(patterns) + [0] * (npad - n)
     if mult:
-        entries = [(0, 0xFFFFFFFFFFFFFFFF)] * 16
+        entries = [(0, 0xFFFFFFFFFFFFFFFF)] * (1 << bits)
         for pos, p in enumerate(patterns):
-            entries[((p * mult) & 0xFFFFFFFFFFFFFFFF) >> 60] = (p, pos)
+            entries[((p * mult) & 0xFFFFFFFFFFFFFFFF) >> (64 - bits)] = (p, pos)
         for key, pos in entries:
             words.extend((key, pos))
     return words
