@@ -53,6 +53,7 @@ class Plan(object):
         self.nhists = len(self.spec["hists"])
         self.fields = hbspec.spec_fields(self.spec)
         self.kernels = {}           # dtype signature -> (fill Kernel, Program, keys Kernel, keys Program, range Kernel, range Program)
+        self.generated = {}         # dtype signature -> (generated fill Kernel, its options, column types): kernel_for compiles on demand
         self.generation = Plan.generation
         self.keysets = None
         self.goal_tables = None     # tree key of a group goal -> (key patterns of the last fill, their device table)
@@ -71,25 +72,33 @@ class Plan(object):
         self.fx_seen = 0            # ... its value when last looked at
         self.fx_last = None         # (signature, events, fills) since the miss counter was last looked at
 
-    def kernel_for(self, cols, dense=False, nobox=False):
-        """The kernels for these column dtypes.  ``dense`` selects the second variant of a hot-window kernel (see
-        fill_hists): part of the window's float64 terms in fixed point, plain REDs for the few events outside."""
+    def generated_for(self, cols, dense=False, nobox=False, gfast=False):
+        """(signature, generated -- not yet compiled -- fill kernel, its options) for these column dtypes and this variant."""
         self._fresh()
-        sig = tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields) + (("dense",) if dense else ()) + (("nobox",) if nobox else ())
-        if sig not in self.kernels:
+        sig = (tuple((n, cols[n].dtype.str, cols[n].is_scalar) for n in self.fields) + (("dense",) if dense else ()) + (("nobox",) if nobox else ())
+               + (("gfast",) if gfast else ()))
+        if sig not in self.generated:
             coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in self.fields)
             options = dict(_options, **self.options)
             if dense:
                 options["win_dense"] = True
             if nobox:
                 options["box"] = False
-            kern = codegen.generate(self.spec, coltypes, options)
+            options["group_fast"] = bool(gfast)
+            self.generated[sig] = (codegen.generate(self.spec, coltypes, options), options, coltypes)
+        return (sig,) + self.generated[sig][:2]
+
+    def kernel_for(self, cols, dense=False, nobox=False, gfast=False):
+        """The kernels for these column dtypes.  ``dense`` selects the second variant of a hot-window kernel (see
+        fill_hists): part of the window's float64 terms in fixed point, plain REDs for the few events outside.  ``gfast``
+        selects the variant of a book with group axes for fills in which the histograms of a signature share their slot
+        maps and hold no more slots than are privatised in shared memory (fill_hists decides per fill)."""
+        sig, kern, options = self.generated_for(cols, dense=dense, nobox=nobox, gfast=gfast)
+        if sig not in self.kernels:
+            coltypes = self.generated[sig][2]
             prog = engine.Program(engine.compile_source(kern.source), kern.name, kern.threads, kern.smem_bytes, tile=kern.tile,
                                   max_blocks_per_sm=int(options.get("max_blocks_per_sm", 0)))
-            keys = codegen.generate_keys(self.spec, coltypes, options)
-            kprog = None
-            if keys is not None:
-                kprog = engine.Program(engine.compile_source(keys.source), keys.name, keys.threads, keys.smem_bytes)
+            keys, kprog = self.discovery_for(cols)
             rng = rprog = None
             if kern.fx_terms:
                 rng = codegen.generate_range(self.spec, coltypes, options)
@@ -100,6 +109,7 @@ class Plan(object):
     def _fresh(self):
         if self.generation != Plan.generation:
             self.kernels.clear()
+            self.generated.clear()
             self.parts.clear()
             self.discovery.clear()
             self.generation = Plan.generation
@@ -475,6 +485,26 @@ def _bind_stores(plan, kern, hists, discovered):
     return stores, aux
 
 
+def _group_fast(plan, kern, stores, aux, cols):
+    """Whether this fill may run the ``gfast`` variant of a book's kernel (codegen option group_fast): every histogram that
+    shares its group goals with an earlier one also shares that one's slot map (``_bind_stores`` passed a null map), and
+    every histogram with group axes that is privatised in shared memory holds no more slab slots than are privatised there
+    -- then the kernel needs neither the per-histogram map loads nor the global-memory path of the slots beyond. The
+    usual case for the histograms of a book, which are always filled together (c4: 11 keys, 16 privatised slots)."""
+    if not kern.group_leader or not _options.get("group_fast", True) or kern.window is not None or kern.deterministic:
+        return False
+    if any(aux[kern.group_aux[hid]] != 0 for hid in kern.group_leader):
+        return False
+    vkern = plan.generated_for(cols, gfast=True)[1]
+    if vkern.group_aux != kern.group_aux or vkern.goal_aux != kern.goal_aux or vkern.naux != kern.naux:
+        return False
+    for hid in vkern.group_aux:
+        hp = vkern.plans[hid]
+        if hp.strategy == "smem" and len(stores[hid].tuples) > hp.gcap:
+            return False
+    return True
+
+
 def _fill_parts(plan, parts, hists, cols, length, timed):
     """A split book (Plan.parts_for): one discovery pass, one pass over the columns, one kernel per part and chunk."""
     on_device = [c for c in cols.values() if c.location == 1]
@@ -531,7 +561,9 @@ def fill_hists(plan, hists, arrays, timed=False):
         parts = plan.parts_for(cols)
         if parts is not None:
             return _fill_parts(plan, parts, hists, cols, length, timed)
-        sig, (kern, prog, keys, kprog, rng, rprog) = plan.kernel_for(cols)
+        # (generated, not compiled yet: which variant of the kernel runs is decided below, once the group keys are known)
+        sig, kern, _kopts = plan.generated_for(cols)
+        keys, kprog = plan.discovery_for(cols)
         # device columns produced on another stream (torch's current one): CUDA does not order a non-blocking stream
         # with the engine's, so the fill waits for the producer here and the producer for the fill at the end
         on_device = [c for c in cols.values() if c.location == 1]
@@ -550,6 +582,9 @@ def fill_hists(plan, hists, arrays, timed=False):
         discovered = _discover(plan, keys, kprog, cols, length)
 
         stores, aux = _bind_stores(plan, kern, hists, discovered)
+
+        gfast = _group_fast(plan, kern, stores, aux, cols)
+        sig, (kern, prog, _keys, _kprog, rng, rprog) = plan.kernel_for(cols, gfast=gfast)
 
         stats = {"events": length, "launches": 0}
         used = (sig, kern, prog, rng, rprog)

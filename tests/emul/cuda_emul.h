@@ -1,0 +1,145 @@
+// cuda_emul.h -- TEST INFRASTRUCTURE ONLY (tests/emul_util.py).  A minimal host-side stand-in for the CUDA execution
+// model, enough to run the *generated* fill kernels (histbook_b200/codegen.py + csrc/hb_template.cuh) of a book on CPU
+// threads: one std::thread per CUDA thread of a block, blocks one after the other, block / named / warp barriers as
+// mutex + condition-variable barriers, warp shuffles as an exchange through a per-warp buffer, shared memory as one global
+// array, atomics as GCC __atomic builtins.  It exists so that the code generator's logic (tickets, scatter, chunked sums,
+// tails, flags, group-slot lookups ...) can be checked against the oracle in the `-m "not gpu"` suite.  It is never
+// imported, linked or executed by the product path, which has no CPU fallback (engine.py raises without the device).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __shared__
+#define __constant__ static const
+#define __align__(n) alignas(n)
+#define __launch_bounds__(...)
+#define HB_EMU_NOASM(...) do { } while (0)
+
+struct hb_emu_dim { unsigned x, y, z; };
+static thread_local hb_emu_dim threadIdx = {0, 0, 0};
+static thread_local hb_emu_dim blockIdx = {0, 0, 0};
+static hb_emu_dim blockDim = {1, 1, 1};
+static hb_emu_dim gridDim = {1, 1, 1};
+
+alignas(128) static unsigned char hb_smem[256 * 1024];
+
+struct double2 { double x, y; };
+struct uint2 { unsigned x, y; };
+struct ulonglong2 { unsigned long long x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+static inline long long min(long long a, int b) { return a < b ? a : (long long)b; }
+static inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
+
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
+static inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }
+static inline int __double2loint(double d) { return (int)(__double_as_longlong(d) & 0xffffffffLL); }
+// cvt.rmi.s32.f64: round toward -inf, saturate, NaN -> 0
+static inline int __double2int_rd(double t) {
+    if (t != t) return 0;
+    const double f = floor(t);
+    if (f >= 2147483648.0) return 2147483647;
+    if (f < -2147483648.0) return -2147483647 - 1;
+    return (int)f;
+}
+static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline void __nanosleep(unsigned) { }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (unsigned)((v << (shift & 31u)) >> 32);
+}
+static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
+
+// ---- barriers -------------------------------------------------------------------------------------------------------
+struct hb_emu_barrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned gen = 0;
+    void sync(int count) {
+        std::unique_lock<std::mutex> l(m);
+        const unsigned g = gen;
+        if (++waiting >= count) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(l, [&] { return gen != g; });
+    }
+};
+static hb_emu_barrier hb_emu_block_bar;
+static hb_emu_barrier hb_emu_named[16];
+struct hb_emu_warp { hb_emu_barrier bar; unsigned long long buf[32]; };
+static hb_emu_warp hb_emu_warps[64];
+
+static inline void __syncthreads() { hb_emu_block_bar.sync((int)blockDim.x); }
+static inline void hb_emu_bar(int id, int count) { hb_emu_named[id & 15].sync(count); }
+
+template <typename T> static inline T hb_emu_exchange(T v, int src) {
+    hb_emu_warp& w = hb_emu_warps[threadIdx.x >> 5];
+    const int lane = (int)(threadIdx.x & 31u);
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    w.buf[lane] = bits;
+    w.bar.sync(32);
+    const unsigned long long got = w.buf[(src >= 0 && src < 32) ? src : lane];
+    w.bar.sync(32);
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+// (full-warp forms only: every caller in hb_template.cuh passes 0xffffffff)
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) { const int lane = (int)(threadIdx.x & 31u); return hb_emu_exchange(v, lane >= d ? lane - d : lane); }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int d) { return hb_emu_exchange(v, (int)(threadIdx.x & 31u) ^ d); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return hb_emu_exchange(v, src & 31); }
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l) out |= (hb_emu_exchange<unsigned>(pred ? 1u : 0u, l) & 1u) << l;
+    return out;
+}
+static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
+static inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+static inline unsigned __activemask() { return 0xffffffffu; }
+template <typename T> static inline unsigned __match_any_sync(unsigned, T v) {
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l) if (hb_emu_exchange<T>(v, l) == v) out |= 1u << l;
+    return out;
+}
+
+// ---- atomics --------------------------------------------------------------------------------------------------------
+static inline unsigned atomicAdd(unsigned* a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicCAS(unsigned long long* a, unsigned long long cmp, unsigned long long v) {
+    __atomic_compare_exchange_n(a, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+static inline unsigned long long atomicExch(unsigned long long* a, unsigned long long v) { return __atomic_exchange_n(a, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    for (;;) {
+        double d;
+        memcpy(&d, &old, 8);
+        d += v;
+        unsigned long long want;
+        memcpy(&want, &d, 8);
+        if (__atomic_compare_exchange_n(p, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) { memcpy(&d, &old, 8); return d; }
+    }
+}
+// red.global.add.f64 (hb_template.cuh hb_red_f64): the emulated form the preprocessed template calls
+static inline void hb_red_f64(double* addr, double v) { atomicAdd(addr, v); }

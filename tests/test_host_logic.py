@@ -234,11 +234,17 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     assert k.nfx == 6 and k.source.count("hb_fx_decode<") == 6        # w, w^2, z, z^2, filtered w, filtered w^2: decoded once per event
     assert k.source.count("hb_event(p, hb_smem") == 1
     k = gen("c4")                                   # default: one sort group per axis expression holds its 4 histograms on bin("e", 100)
-    assert k.sorted is not None and len(k.sorted["groups"]) == 8 and k.sorted["staged"] == 3 and not k.fx_terms
+    # (w and z are staged; the filtered weight where(n >= 3, 1, 0) * w travels as one flag bit beside the sorted event numbers)
+    assert k.sorted is not None and len(k.sorted["groups"]) == 8 and k.sorted["staged"] == 2 and k.sorted["flags"] == 1 and not k.fx_terms
+    assert gen("c4", sort_gate=False).sorted["staged"] == 3 and gen("c4", sort_gate=False).sorted["flags"] == 0
+    assert "hb_event<true>" in k.source and "hb_event<true>" not in gen("c4", sort_full=False).source      # full tiles: `live` folded away
     assert all(g["nbins"] == 103 and g["values"] == 6 and len(g["hists"]) == 4 for g in k.sorted["groups"])
     assert sorted(hp.strategy for hp in k.plans).count("sorted") == 32 and k.threads == 1024 and k.tile == 3072      # (three events per thread where it all fits)
     assert gen("c4", sort_ept=2).tile == 2048 and all(hp.strategy in ("sorted", "smem") for hp in k.plans)
     assert k.source.count("atomicAdd(") - k.source.count("hb_sadd_u32") <= 8 + 1     # one ticket per group and event
+    f = gen("c4", group_fast=True)                  # the variant fillable picks when the histograms of a signature share their slot maps
+    assert f.source.count("gm[") == 1 and k.source.count("gm[") == 8 and "hb_red_f64(row" not in f.source.split("hb_fill_kernel")[0]
+    assert f.group_aux == k.group_aux and f.goal_aux == k.goal_aux and f.naux == k.naux and f.smem_bytes == k.smem_bytes
     k = gen("c3", sort=True)                        # forced on a small book: y and y^2 staged, y^4 = (y^2)^2 recomputed
     assert k.sorted["staged"] == 2 and k.sorted["groups"][0]["values"] == 3 and k.smem_bytes < 227 * 1024 and k.sorted["lanes"] == 64
     k = gen("c2", deterministic=True)
