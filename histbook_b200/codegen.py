@@ -154,6 +154,8 @@ class Program(object):
         self.zeroed = {}        # (weight, weight^2) SSA names -> their NaN-zeroed forms (hist.py:422-427), shared by a book's histograms
         self.nonneg = set()     # SSA names known to be >= +0 or NaN (squares, absolute values): the fixed-point add skips the sign path
         self.square_of = {}     # SSA name of a float64 product x * x -> SSA name of x (the sorted strategy stages x only)
+        self.bin_sites = {}     # SSA name of a float64 value -> closed-low bin axes computed on it: [{i, low, scale, numbins, shift, at}]
+        self.split_sites = []   # split axes lowered as compare chains: what generate() needs to re-write them as table look-ups
         self.indicator = {}     # SSA name of where(c, 1, 0) -> C expression of c
         self.gated = {}         # SSA name of the float64 product where(c, 1, 0) * y -> (C expression of c, SSA name of y)
         self.zeroed_of = {}     # SSA name of a float64 weight -> SSA name of its NaN-zeroed form
@@ -420,6 +422,9 @@ class Program(object):
             self.body.append("const int %s = hb_bin_axis<%s, %s>(%s, %s, %s, %d, %s);" % (
                 name, ctype(r), ", ".join("true" if c != "_" and c != "H" else "false" for c in f),
                 self.cast(v, r), lit(float(low), r), lit(scale, r), int(numbins), ok))
+            if r == numpy.float64 and v.dtype == numpy.float64 and f[3] == "L":
+                self.bin_sites.setdefault(v.c, []).append({"i": name, "low": float(low), "scale": float(scale), "numbins": int(numbins),
+                                                           "shift": 1 if f[0] == "U" else 0, "nanflow": f[2] == "N", "at": len(self.body) - 1})
             return Value(name, numpy.int32, kind="index", extra=ok)
 
         if fcn.startswith("histbook.intbin"):
@@ -466,6 +471,10 @@ class Program(object):
                 onedge = " || ".join("(%s == %s)" % (e, vv) for e in lits)
                 self.body.append("const int %s = hb_split_index<%s>(%s, %s, %s, %d, %s);" % (
                     name, flags, count, ("(%s)" % onedge) if f[3] in "_H" else "false", isnan, len(edges), ok))
+                if v.dtype == numpy.float64 and cmp_t == numpy.float64:
+                    self.split_sites.append({"at": len(self.body) - 1, "name": name, "ok": ok, "v": v.c, "vv": vv, "flags": flags,
+                                             "closedhigh": f[3] in "_H", "edges": [float(e) for e in numpy.array(edges).astype(cmp_t).tolist()],
+                                             "slow": self.body[-1][len("const int %s = " % name):]})
             else:
                 cname = self.new("hb_edges")
                 self.consts.append("__constant__ hb_i64 %s[%d] = {%s};" % (
@@ -1585,6 +1594,9 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append('extern "C" __global__ void __launch_bounds__(HB_THREADS, %d) hb_fill_kernel(const HbParams p)\n{' % int(options.get("sort_min_blocks", 1)))
     src.append("    extern __shared__ __align__(16) unsigned char hb_smem[];")
     src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<hb_u32*>(hb_smem)[i] = 0u;" % (layout["zero_end"] // 4))
+    for cname, off, entries in layout.get("split_tables", []):
+        # (bin index -> digitize count of the split axes on the same value: _apply_split_tables)
+        src.append("    for (int i = threadIdx.x; i < %d; i += HB_THREADS) reinterpret_cast<int*>(hb_smem + %d)[i] = %s[i];" % (4 * entries, off, cname))
     if int(options.get("sort_stagger_us", 0)) > 0:
         # two blocks share an SM: the second starts late, so that its phases fall between the first one's
         src.append("    if (blockIdx.x >= (gridDim.x + 1) / 2 || (p.flags & 2)) { for (int i = 0; i < %d; ++i) __nanosleep(1000); }" % int(options["sort_stagger_us"]))
@@ -2209,6 +2221,83 @@ def _emit_global_adds(hp, options, rowidx, indent):
     return out
 
 
+def split_table(edges, low, scale, numbins):
+    """Table that turns the index of a closed-low float64 ``bin`` axis into the digitize count of a ``split`` axis on the SAME
+    value: [(edge, count)] per regular bin b, or None where the look-up is not valid.
+
+    T(v) = fl(fl(v - low) * scale) is what hb_bin_axis floors; it is monotone in v (two correctly rounded monotone
+    operations), so with k_e = floor(T(e)) for an edge e and b = floor(T(v)):  b > k_e  implies  v > e,  and  b < k_e  implies
+    v < e.  Only an edge with k_e == b has to be compared with v itself.  Hence, where every regular bin holds at most one
+    such edge, the number of edges <= v is  count[b] + (edge[b] <= v)  with count[b] = #{e: k_e < b} and edge[b] = the edge
+    in bin b, +inf if there is none (calc/__init__.py:286-290 computes it as numpy.digitize, hb_split_index from a compare
+    chain).  Values whose bin index is not a regular bin (underflow, overflow, NaN, the int32 cast quirk) keep the chain."""
+    edges = [float(e) for e in edges]
+    if not edges or any(e != e for e in edges) or any(a >= b for a, b in zip(edges, edges[1:])):
+        return None
+    ks = []
+    for e in edges:
+        with numpy.errstate(all="ignore"):
+            t = (numpy.float64(e) - numpy.float64(low)) * numpy.float64(scale)
+        if t != t:
+            return None
+        ks.append(float(numpy.floor(t)))
+    table = []
+    for b in range(int(numbins)):
+        inside = [e for e, k in zip(edges, ks) if k == float(b)]
+        if len(inside) > 1:
+            return None
+        table.append((inside[0] if inside else float("inf"), sum(1 for k in ks if k < float(b))))
+    return table
+
+
+def _apply_split_tables(prog, layout, smem, cap):
+    """Big books: split axes on a value that also has a closed-low float64 bin axis take their index from that axis'
+    bin index and ONE 16-byte shared-memory load (``split_table``) instead of a chain of compares against every edge -- 22
+    instructions per axis and event become 8 on c4, where the event phase is bound by issue slots, not by shared memory.
+    Re-writes the statements in prog.body; returns the new shared-memory size."""
+    tables = []                                             # [(constant name, byte offset, entries)]
+    shared = {}
+    for site in prog.split_sites:
+        cands = [b for b in prog.bin_sites.get(site["v"], []) if b["at"] < site["at"]]
+        best = None
+        for b in sorted(cands, key=lambda b: -b["numbins"]):
+            tab = split_table(site["edges"], b["low"], b["scale"], b["numbins"])
+            if tab is not None:
+                best = (b, tab)
+                break
+        if best is None:
+            continue
+        b, tab = best
+        key = tuple(tab)
+        if key not in shared:
+            off = (smem + 15) // 16 * 16
+            if off + 16 * len(tab) > cap:
+                continue
+            cname = "hb_stab%d" % len(tables)
+            words = []
+            for edge, count in tab:
+                bits = int(numpy.array([edge], dtype=numpy.float64).view(numpy.uint64)[0])
+                lo, hi = bits & 0xFFFFFFFF, bits >> 32
+                words.extend([lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi, int(count), 0])
+            prog.consts.append("__constant__ int %s[%d] = {%s};" % (cname, len(words), ", ".join(
+                "(-2147483647 - 1)" if w == -(1 << 31) else str(w) for w in words)))
+            shared[key] = (cname, off)
+            tables.append((cname, off, len(tab)))
+            smem = off + 16 * len(tab)
+        cname, off = shared[key]
+        fast = "hb_split_index<%s>(sq.z + (int)(se <= %s), %s, false, %d, %s)" % (
+            site["flags"], site["vv"], ("(se == %s)" % site["vv"]) if site["closedhigh"] else "false", len(site["edges"]), site["ok"])
+        # (a bin axis without a NaN bin leaves the index of a NaN value wherever the conversion put it -- bin 0 -- and only
+        #  masks the row: the value itself has to be looked at then)
+        regular = "sfb < %du" % b["numbins"] if b["nanflow"] else "sfb < %du && %s == %s" % (b["numbins"], site["vv"], site["vv"])
+        prog.body[site["at"]] = (
+            "int %s; { const unsigned sfb = (unsigned)(%s - %d); if (" + regular.replace("%", "%%") + ") { const int4 sq = reinterpret_cast<const int4*>(hb_smem + %d)[sfb]; "
+            "const double se = __hiloint2double(sq.y, sq.x); %s = %s; } else { %s = %s } }") % (
+                site["name"], b["i"], b["shift"], off, site["name"], fast, site["name"], site["slow"])
+    layout["split_tables"] = tables
+    return smem
+
+
 def generate(spec, coltypes, options=None):
     """The fill kernel of a spec for one set of column dtypes."""
     options = options or {}
@@ -2218,6 +2307,8 @@ def generate(spec, coltypes, options=None):
         raise UnsupportedError("more than 128 histograms in one fill")
     layout = {}
     smem, window = choose_strategies(plans, options, prog, layout)
+    if layout and not layout.get("pipe") and options.get("split_table", True):
+        smem = _apply_split_tables(prog, layout, smem, int(options.get("sort_smem", SMEM_MAX - 1024)))
     if len(prog.cols) > 32:
         raise UnsupportedError("more than 32 input fields in one fill")
     # resident threads per SM stay near 1024 whatever the shared-memory footprint: the fixed-point adds are chains

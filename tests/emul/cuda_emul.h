@@ -37,6 +37,7 @@ alignas(128) static unsigned char hb_smem[256 * 1024];
 struct double2 { double x, y; };
 struct uint2 { unsigned x, y; };
 struct ulonglong2 { unsigned long long x, y; };
+struct int4 { int x, y, z, w; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 
@@ -49,6 +50,7 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
+static inline double __hiloint2double(int hi, int lo) { return __longlong_as_double((long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo)); }
 static inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }
 static inline int __double2loint(double d) { return (int)(__double_as_longlong(d) & 0xffffffffLL); }
 // cvt.rmi.s32.f64: round toward -inf, saturate, NaN -> 0

@@ -90,3 +90,106 @@ def test_followers_with_their_own_slot_maps():
     """the generic kernel with every histogram's own map (what fillable passes when the maps differ)"""
     spec = golden_util.load()["c4"]["spec"]
     _check(spec, _columns(4000, 8), {}, null_follower_maps=False)
+
+
+def _bin_axis(field, numbins, low, high, flags="UONL"):
+    return {"goal": ["call", "histbook.bin" + flags, ["name", field], ["const", numbins], ["const", float(low)], ["const", float(high)]],
+            "kind": "bin", "totbins": numbins + sum(1 for c in flags[:3] if c != "_")}
+
+
+def _split_axis(field, edges, flags="UONL"):
+    return {"goal": ["call", "histbook.split" + flags, ["name", field], ["const", {"tuple": [float(e) for e in edges]}]],
+            "kind": "split", "totbins": len(edges) - 1 + sum(1 for c in flags[:3] if c != "_")}
+
+
+def _hist(fixed, weight=None):
+    shape = [a["totbins"] for a in fixed] + [1 if weight is None else 2]
+    w = None if weight is None else {"w": ["name", weight], "w2": ["call", "numpy.multiply", ["name", weight], ["name", weight]]}
+    return {"fixed": fixed, "group": [], "profile": [], "shape": shape, "sumw": 0, "sumw2": None if weight is None else 1, "weight": w}
+
+
+def test_split_index_from_the_bin_index():
+    """codegen._apply_split_tables: a split axis on a value that also has a closed-low bin axis takes its digitize count from
+    the bin index and one table look-up.  Values ON the edges, one ulp beside them, on and beside the bin edges, far outside,
+    NaN and +-inf; edges that are bin edges, edges that are not, closed-high splits, splits without flow bins, a bin axis
+    without underflow (no shift), and a combination whose bins hold two edges (must keep the compare chain)."""
+    from histbook_b200 import codegen
+    combos = [
+        ("a", (100, -5.0, 5.0, "UONL"), ((-2.0, -1.0, -0.5, 0.0, 0.5, 1.0, 2.0), "UONL")),          # c4's own
+        ("b", (37, -3.3, 4.1, "UONL"), ((-2.05, 0.1, 0.7, 3.3), "UONH")),                              # nothing aligned, closed high
+        ("c", (50, 0.0, 1.0, "_ONL"), ((0.1, 0.3, 0.30000000000000004, 0.9), "___L")),                 # two edges one ulp apart: one bin holds both -> chain
+        ("d", (64, -1.0, 1.0, "_O_L"), ((-0.5, 0.25, 0.75), "_ONL")),                                   # no underflow bin: index without shift
+        ("e", (10, -1e6, 1e6, "UONL"), ((-7e5, -1.0, 1.0, 3e5), "UO_H")),
+    ]
+    hists, arrays = [], {}
+    rs = numpy.random.RandomState(21)
+    n = 6000
+    arrays["w"] = rs.uniform(0.5, 1.5, n)
+    for field, (numbins, low, high, bflags), (edges, sflags) in combos:
+        hists.append(_hist([_bin_axis(field, numbins, low, high, bflags)], weight="w"))       # the sort group of this value
+        hists.append(_hist([_split_axis(field, edges, sflags)]))
+        hists.append(_hist([_bin_axis(field, numbins, low, high, bflags), _split_axis(field, edges, sflags)]))
+        hists.append(_hist([_split_axis(field, edges, sflags)], weight="w"))
+        width = (high - low) / numbins
+        special = list(edges) + [low + k * width for k in range(0, numbins + 1, max(1, numbins // 7))] + [low, high]
+        vals = []
+        for v in special:
+            v = numpy.float64(v)
+            vals.extend([v, numpy.nextafter(v, numpy.inf), numpy.nextafter(v, -numpy.inf), numpy.nextafter(numpy.nextafter(v, numpy.inf), numpy.inf)])
+        vals.extend([numpy.nan, numpy.inf, -numpy.inf, 1e300, -1e300, 3e9 * width + low, 0.0, -0.0])
+        col = rs.uniform(low - 0.1 * (high - low), high + 0.1 * (high - low), n)
+        pos = rs.permutation(n)[:len(vals) * 3]
+        col[pos] = numpy.tile(numpy.array(vals, dtype=numpy.float64), 3)
+        arrays[field] = col
+    spec = {"version": 1, "hists": hists}
+    assert len(hists) > 16
+    coltypes = dict((k, (v.dtype, False)) for k, v in arrays.items())
+    kern = codegen.generate(spec, coltypes, {})
+    assert kern.sorted is not None
+    assert kern.source.count("const int4 sq") == 4                # combos a, b, d, e (each split goal is lowered once); c keeps the chain
+    _check(spec, arrays, {})
+    _check(spec, arrays, {"split_table": False})
+
+
+def test_split_table_is_refused_where_it_is_not_valid():
+    from histbook_b200 import codegen
+    assert codegen.split_table([0.3, 0.30000000000000004], 0.0, 50.0, 50) is None            # both edges in bin 15
+    assert codegen.split_table([1.0, 0.5], 0.0, 1.0, 10) is None and codegen.split_table([float("nan")], 0.0, 1.0, 10) is None
+    tab = codegen.split_table([-2.0, 0.0, 0.5], -5.0, 10.0, 100)
+    assert len(tab) == 100 and tab[29] == (float("inf"), 0) and tab[30] == (-2.0, 0) and tab[31] == (float("inf"), 1)
+    assert tab[50] == (0.0, 1) and tab[55] == (0.5, 2) and tab[99] == (float("inf"), 3)
+    # an edge outside the axis: counted from the first bin on (below) or never (above)
+    tab = codegen.split_table([-9.0, 9.0], -5.0, 10.0, 100)
+    assert tab[0] == (float("inf"), 1) and tab[99] == (float("inf"), 1)
+
+
+def _emulable(name):
+    """golden cases the emulator harness takes with the sorted strategy forced on: one fill of plain numeric arrays, a
+    float64 term on a fixed-axis histogram (something to sort), at most one group axis per histogram, exact arithmetic"""
+    from histbook_b200 import codegen
+    case = golden_util.load()[name]
+    fills = golden_util.fills(case)
+    if len(fills) != 1:
+        return False
+    arrays = fills[0]
+    fields = emul_util.hbspec.spec_fields(case["spec"])
+    if not fields or any(n not in arrays or not isinstance(arrays[n], numpy.ndarray) or arrays[n].dtype.kind not in "fiub" or arrays[n].ndim != 1
+                         for n in fields):
+        return False
+    if any(len(h["group"]) > 1 for h in case["spec"]["hists"]):
+        return False
+    try:
+        kern = codegen.generate(case["spec"], dict((n, (arrays[n].dtype, False)) for n in fields), {"sort": True})
+    except Exception:
+        return False
+    return kern.sorted is not None and kern.window is None and not kern.fx_terms and not kern.inexact
+
+
+@pytest.mark.parametrize("name", golden_util.names())
+def test_golden_cases_sorted_on_the_emulator(name):
+    """every golden case the harness can take, through the sorted kernel (forced on), against the oracle"""
+    if not _emulable(name):
+        pytest.skip("not a case for the emulator harness")
+    case = golden_util.load()[name]
+    arrays = golden_util.fills(case)[0]
+    _check(case["spec"], arrays, {"sort": True}, grid=2)
