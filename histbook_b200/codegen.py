@@ -154,6 +154,7 @@ class Program(object):
         self.zeroed = {}        # (weight, weight^2) SSA names -> their NaN-zeroed forms (hist.py:422-427), shared by a book's histograms
         self.nonneg = set()     # SSA names known to be >= +0 or NaN (squares, absolute values): the fixed-point add skips the sign path
         self.square_of = {}     # SSA name of a float64 product x * x -> SSA name of x (the sorted strategy stages x only)
+        self.always_ok = set()  # names of `ok` flags that can never become false (bin axes with underflow, overflow and NaN bins)
         self.bin_sites = {}     # SSA name of a float64 value -> closed-low bin axes computed on it: [{i, low, scale, numbins, shift, at}]
         self.split_sites = []   # split axes lowered as compare chains: what generate() needs to re-write them as table look-ups
         self.indicator = {}     # SSA name of where(c, 1, 0) -> C expression of c
@@ -422,6 +423,8 @@ class Program(object):
             self.body.append("const int %s = hb_bin_axis<%s, %s>(%s, %s, %s, %d, %s);" % (
                 name, ctype(r), ", ".join("true" if c != "_" and c != "H" else "false" for c in f),
                 self.cast(v, r), lit(float(low), r), lit(scale, r), int(numbins), ok))
+            if f[0] == "U" and f[1] == "O" and f[2] == "N":
+                self.always_ok.add(ok)
             if r == numpy.float64 and v.dtype == numpy.float64 and f[3] == "L":
                 self.bin_sites.setdefault(v.c, []).append({"i": name, "low": float(low), "scale": float(scale), "numbins": int(numbins),
                                                            "shift": 1 if f[0] == "U" else 0, "nanflow": f[2] == "N", "at": len(self.body) - 1})
@@ -1522,10 +1525,19 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     src.append("#define HB_FXMISS (reinterpret_cast<hb_u32*>(hb_smem))")
     chunks = bool(layout.get("chunks"))
     chunk = tile // lanes
-    if chunks:
-        # where sorted position `pos` lives in a group's array of event numbers: the chunks of consecutive lanes are an odd
-        # number of 32-bit words apart, so the 32 lanes of a warp, each reading its own chunk, hit 32 different banks
-        # (unpadded: 16-way conflicts, a quarter of the kernel's shared-memory wavefronts)
+    odd = chunks and bool(options.get("sort_chunk_odd", True))
+    if odd:
+        # where sorted position `pos` lives in a group's array of event numbers: the chunks of consecutive lanes must be an odd
+        # number of 32-bit words apart, so that the 32 lanes of a warp, each reading its own chunk, hit 32 different banks
+        # (chunks of 48: 16-way conflicts, a quarter of the kernel's shared-memory wavefronts).  A chunk LENGTH of an odd number
+        # of words (50 event numbers for tiles of 3072: 62 of the 64 lanes work) needs no padding, hence no division by the
+        # chunk length in the scatter of every event and group.
+        chunk = -(-tile // lanes)
+        while chunk % 4 != 2:
+            chunk += 1
+        src.append("#define HB_SPOS(pos) (pos)")
+    elif chunks:
+        # (the padded form: chunks of tile / lanes event numbers, two halfwords of padding behind each)
         assert chunk * lanes == tile
         src.append("#define HB_SPOS(pos) ((pos) + (((pos) / %du) << 1))" % chunk)
     else:
@@ -1647,14 +1659,29 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("        const unsigned short en%d = (unsigned short)((%d * HB_THREADS + threadIdx.x) | (fl%d << %d));" % (k, k, k, ebits))
         else:
             src.append("        const unsigned short en%d = (unsigned short)(%d * HB_THREADS + threadIdx.x);" % (k, k))
-        for g in groups:
-            if options.get("sort_branchfree", True):
-                # (an event that is masked for this group writes its number to a dump slot behind the array)
-                src.append("        { const bool v = kr%d[%d] != 0xffffffffu; const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[v ? (kr%d[%d] >> 16) : 0u] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[v ? HB_SPOS(sp) : %du] = en%d; }" % (
-                    k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], tile + 2 * lanes + 4, k))
-            else:
-                src.append("        if (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[HB_SPOS(sp)] = en%d; }" % (
-                    k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
+
+    def scatter(ind, full_tile):
+        for k in range(ept):
+            for g in groups:
+                if full_tile and all(c in prog.always_ok for c in g.conds):
+                    # (a full tile, and no axis of this group can mask a row: every ticket is a real one)
+                    src.append("%s{ const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[HB_SPOS(sp)] = en%d; }" % (
+                        ind, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
+                elif options.get("sort_branchfree", True):
+                    # (an event that is masked for this group writes its number to a dump slot behind the array)
+                    src.append("%s{ const bool v = kr%d[%d] != 0xffffffffu; const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[v ? (kr%d[%d] >> 16) : 0u] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[v ? HB_SPOS(sp) : %du] = en%d; }" % (
+                        ind, k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], tile + 2 * lanes + 4, k))
+                else:
+                    src.append("%sif (kr%d[%d] != 0xffffffffu) { const hb_u32 sp = reinterpret_cast<const hb_u32*>(hb_smem + %d)[kr%d[%d] >> 16] + (kr%d[%d] & 0xffffu); reinterpret_cast<unsigned short*>(hb_smem + %d)[HB_SPOS(sp)] = en%d; }" % (
+                        ind, k, g.gid, g.off["tick"], k, g.gid, k, g.gid, g.off["sorted"], k))
+    if full and any(all(c in prog.always_ok for c in g.conds) for g in groups):
+        src.append("        if (first + HB_TILE <= p.n) {")
+        scatter("            ", True)
+        src.append("        } else {")
+        scatter("            ", False)
+        src.append("        }")
+    else:
+        scatter("        ", False)
     src.append("        __syncthreads();")
     if chunks:
         # the balanced variant: every lane walks a contiguous chunk of the sorted events; a run that ends inside the chunk is
@@ -1674,7 +1701,7 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("            const hb_u32 ng = st[%d];" % g.nbins)
             src.append("            const hb_u32 p0 = (hb_u32)hb_l * %du, p1 = min(p0 + %du, ng);" % (chunk, chunk))
             # every position of this lane's chunk has pos / chunk == hb_l: HB_SPOS(pos) == pos + 2 * hb_l, no division per event
-            src.append("            const unsigned short* const sop = so + 2 * hb_l;")
+            src.append("            const unsigned short* const sop = so + %s;" % ("0" if odd else "2 * hb_l"))
             src.append("            " + " ".join("double a%d = 0.0;" % j for j in range(nv)))
             src.append("            int tkey = -1;")
             nvp = (nv + 1) // 2 * 2

@@ -49,6 +49,8 @@ C4_VARIANTS = [
     {"sort_full": False, "group_fast": True},
     {"sort_ept": 2, "group_fast": True},            # tiles of 2048 events
     {"sort_lanes": 128},
+    {"sort_chunk_odd": False},                      # chunks of tile / lanes event numbers with padding (and its division) instead of 50
+    {"sort_chunk_odd": False, "sort_full": False, "split_table": False, "sort_gate": False},      # the kernel as it was before these options
     {"sort_alias_tails": False},
     {"sort_sum": "bins"},
     {"sort_branchfree": False},
