@@ -117,11 +117,9 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
 static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
 static inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 static inline unsigned __activemask() { return 0xffffffffu; }
-template <typename T> static inline unsigned __match_any_sync(unsigned, T v) {
-    unsigned out = 0;
-    for (int l = 0; l < 32; ++l) if (hb_emu_exchange<T>(v, l) == v) out |= 1u << l;
-    return out;
-}
+// (called from divergent code -- hb_keyset_insert behind `if (live)` and an early return: no rendezvous here; every lane is
+//  its own peer group, i.e. inserts its key itself -- the warp-level deduplication is an optimisation, not semantics)
+template <typename T> static inline unsigned __match_any_sync(unsigned, T) { return 1u << (threadIdx.x & 31u); }
 
 // ---- atomics --------------------------------------------------------------------------------------------------------
 static inline unsigned atomicAdd(unsigned* a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }

@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE ONLY: a stand-in for histbook_b200.engine that runs the generated kernels on the CPU emulator
+(tests/emul_util.py), so that the product's HOST path -- fillable.fill_hists, key discovery, goal tables, slot maps, the
+choice of the kernel variant, Store -- can be exercised end to end in the `-m "not gpu"` suite and compared with the oracle.
+
+``installed()`` is a context manager that swaps the handful of engine entry points the fill path uses (compile_source,
+Program, Arena, KeySet, DeviceBuffer, fill, init, streams) for emulated ones and restores them afterwards.  "Device
+memory" is numpy memory of this process.  Nothing here is reachable from the product: without this context manager the
+engine raises EngineError on a machine without a GPU (tests/test_host_logic.py::test_no_cpu_fallback)."""
+import contextlib
+import ctypes
+
+import numpy
+
+import emul_util
+from histbook_b200 import engine, fillable
+
+_ITEMSIZE = [8, 4, 8, 4, 2, 1, 8, 4, 2, 1, 1]
+HB_KEY_EMPTY = 0xFFF0DEADBEEFCAFE
+LAUNCHES = []                   # (kernel name, threads, events) of every emulated launch, for the tests to look at
+
+
+def compile_source(source, lineinfo=True):
+    return source if isinstance(source, bytes) else source.encode()
+
+
+class Program(object):
+    def __init__(self, cubin, kernel_name, threads, smem_bytes, tile=None, max_blocks_per_sm=0):
+        self.source = cubin.decode()
+        self.lib = emul_util.build(self.source)
+        self.lib.hb_emu_run.argtypes = [ctypes.POINTER(emul_util.HbParams), ctypes.c_int, ctypes.c_int]
+        self.threads, self.smem_bytes, self.tile = int(threads), int(smem_bytes), tile
+        self.regs, self.static_smem, self.blocks_per_sm = 0, 0, 1
+
+
+class Arena(object):
+    def __init__(self, ndoubles=None, _array=None):
+        self.a = numpy.zeros(int(ndoubles), dtype=numpy.float64) if _array is None else _array
+
+    @property
+    def size(self):
+        return self.a.size
+
+    @property
+    def ptr(self):
+        return self.a.ctypes.data
+
+    @property
+    def _h(self):
+        return self
+
+    def clear(self):
+        self.a[:] = 0.0
+
+    def clone(self):
+        return Arena(_array=self.a.copy())
+
+    def resize(self, ndoubles):
+        grown = numpy.zeros(int(ndoubles), dtype=numpy.float64)
+        grown[:min(self.a.size, grown.size)] = self.a[:grown.size]
+        self.a = grown
+
+    def read(self, offset=0, count=None):
+        count = self.a.size - offset if count is None else count
+        return self.a[int(offset):int(offset) + int(count)].copy()
+
+    def write(self, array, offset=0):
+        array = numpy.ascontiguousarray(array, dtype=numpy.float64).reshape(-1)
+        self.a[int(offset):int(offset) + array.size] = array
+
+
+class KeySet(object):
+    """hb_template.cuh: [0] capacity, [2] overflow flag, [4...] slots (HB_KEY_EMPTY = free)"""
+
+    def __init__(self, capacity=1 << 12):
+        self.capacity = capacity
+        self.t = numpy.empty(4 + capacity, dtype=numpy.uint64)
+        self.clear()
+
+    @property
+    def ptr(self):
+        return self.t.ctypes.data
+
+    def clear(self):
+        self.t[:4] = (self.capacity, 0, 0, 0)
+        self.t[4:] = HB_KEY_EMPTY
+
+    def read(self):
+        slots = self.t[4:]
+        return slots[slots != numpy.uint64(HB_KEY_EMPTY)].copy(), bool(self.t[2])
+
+
+class DeviceBuffer(object):
+    def __init__(self, array):
+        self.a = numpy.ascontiguousarray(array).copy()
+        self.nbytes = self.a.nbytes
+
+    @property
+    def ptr(self):
+        return self.a.ctypes.data
+
+    def read(self, dtype):
+        return self.a.view(numpy.uint8)[:self.nbytes].view(dtype).copy()
+
+    def write(self, array):
+        array = numpy.ascontiguousarray(array)
+        self.a.view(numpy.uint8)[:array.nbytes] = array.view(numpy.uint8).reshape(-1)
+
+
+def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exact=None):
+    assert exact is None, "the emulator does not run the deterministic mode"
+    p = emul_util.HbParams()
+    for slot, c in enumerate(columns):
+        if c[0] == "scalar":
+            p.scal[slot] = c[2]
+        else:
+            assert c[2] == 0, "emulated fills take host columns"
+            p.cols[slot] = (c[0] + offset * _ITEMSIZE[c[1]]) if c[0] else 0
+    for hid, a in enumerate(arenas):
+        p.hist[hid] = a.ptr
+    for k, x in enumerate(aux):
+        p.aux[k] = int(x) or None
+    for k, x in enumerate(win):
+        p.win[k] = int(x)
+    p.n = int(n)
+    p.vec_ok = 0                                # (the scalar-load path of the per-event kernels: their vector loads are inline PTX)
+    grid = 2
+    LAUNCHES.append((program.source.count("hb_event<true>") > 0, program.threads, int(n), "group_fast" if program.source.count("gm[") <= 1 and "gd_" in program.source else ""))
+    if n > 0:
+        assert program.lib.hb_emu_run(ctypes.byref(p), grid, program.threads) == 0
+    return {"events": int(n), "h2d_bytes": 0, "launches": 1 if n > 0 else 0, "grid": grid, "blocks_per_sm": 1, "ms_kernel": 0.0}
+
+
+@contextlib.contextmanager
+def installed():
+    names = ["compile_source", "Program", "Arena", "KeySet", "DeviceBuffer", "fill", "init", "producer_stream", "stream_wait", "sync"]
+    saved = dict((n, getattr(engine, n)) for n in names)
+    engine.compile_source = compile_source
+    engine.Program = Program
+    engine.Arena = Arena
+    engine.KeySet = KeySet
+    engine.DeviceBuffer = DeviceBuffer
+    engine.fill = fill
+    engine.init = lambda device=None: 0
+    engine.producer_stream = lambda: 0
+    engine.stream_wait = lambda waiter, signaler: None
+    engine.sync = lambda: None
+    fillable.Plan.generation += 1               # no kernel compiled for the real engine survives into the emulated one
+    del LAUNCHES[:]
+    try:
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(engine, n, f)
+        fillable.Plan.generation += 1

@@ -1,0 +1,105 @@
+"""The product's HOST path (fillable.SpecFill -> fill_hists: column binding, key discovery, goal tables, slot maps, choice of the
+kernel variant, Store) run end to end on CPU: the engine's device entry points are swapped for the emulator
+(tests/emul_engine.py), the generated kernels execute on CPU threads, the results are compared with the golden outputs of the
+unmodified reference and with the oracle -- the same comparisons as tests/test_gpu_parity.py makes on the B200.
+
+Not covered here (GPU tests only): hot windows, fixed-point accumulation, the deterministic mode and the vector-load path --
+their inline PTX has no host form -- so these cases run with fx / window / box switched off."""
+import numpy
+import pytest
+
+import emul_engine
+import golden_util
+from oracle import fill_oracle
+from test_gpu_parity import compare, LIBM_CASES
+
+PLAIN = dict(fx=False, window=False, box=False)
+
+
+def _run(spec, fills, **options):
+    from histbook_b200 import fillable
+    saved = dict((k, fillable._options.get(k)) for k in options)
+    with emul_engine.installed():
+        try:
+            fillable.set_options(**options)
+            sf = fillable.SpecFill(spec)
+            for arrays in fills:
+                sf.fill(arrays)
+            return sf.contents(), list(emul_engine.LAUNCHES), dict(fillable.last_stats)
+        finally:
+            fillable.set_options(**saved)
+
+
+def _emulable_case(name):
+    case = golden_util.load()[name]
+    if name in LIBM_CASES:
+        return False
+    for arrays in golden_util.fills(case):
+        for v in arrays.values():
+            if isinstance(v, numpy.ndarray) and v.dtype.kind not in "fiub":
+                return False                            # string keys: dictionary-encoded on the host, fine, but keep this suite small
+    return True
+
+
+@pytest.mark.parametrize("name", [n for n in golden_util.names() if n not in ("c2", "c3", "c5", "c2_nanlaced")])
+def test_golden_cases_through_the_host_path(name):
+    """every golden case of the reference (several fills, scalars, group axes ...) through SpecFill on the emulated engine"""
+    if not _emulable_case(name):
+        pytest.skip("not a case for the emulated engine")
+    case = golden_util.load()[name]
+    fills = golden_util.fills(case)
+    if sum(len(next((v for v in arrays.values() if isinstance(v, numpy.ndarray) and v.ndim == 1), [])) for arrays in fills) > 400000:
+        pytest.skip("too many events for CPU threads")
+    got, launches, stats = _run(case["spec"], fills, **PLAIN)
+    bound = None
+    for arrays in fills:
+        bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
+    compare(name, case["spec"], got, golden_util.outputs(case), bound)
+
+
+def _c4_columns(n, seed, nmax=None):
+    rs = numpy.random.RandomState(seed)
+    cols = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n), "z": rs.normal(0, 1, n), "w": rs.uniform(0.5, 1.5, n),
+            "n": rs.poisson(3, n).astype(numpy.int64)}
+    if nmax is not None:
+        cols["n"] = rs.randint(0, nmax, n).astype(numpy.int64)
+    return cols
+
+
+def test_c4_book_picks_the_group_fast_variant_and_leaves_it_when_it_must():
+    """three fills of the north-star book: the first two hold few group keys -> the ``gfast`` kernel (one slot-map load per
+    event, no global path for slots beyond the privatised ones); the third brings 30 keys -> more slab slots than are
+    privatised -> the generic kernel.  Contents accumulate over the fills like the oracle's."""
+    spec = golden_util.load()["c4"]["spec"]
+    fills = [_c4_columns(5000, 1), _c4_columns(4000, 2), _c4_columns(4000, 3, nmax=60)]
+    got, launches, stats = _run(spec, fills)
+    fill_launches = [l for l in launches if l[1] == 1024]
+    assert [l[3] for l in fill_launches] == ["group_fast", "group_fast", ""], launches
+    assert all(l[0] for l in fill_launches)                                   # the full-tile copy of the event code is there
+    exp = bound = None
+    for arrays in fills:
+        exp = fill_oracle.fill(spec, arrays, exp)
+        bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+    compare("c4", spec, got, [golden_util.flatten(e) for e in exp], bound)
+
+
+def test_group_fast_can_be_switched_off():
+    spec = golden_util.load()["c4"]["spec"]
+    fills = [_c4_columns(3500, 9)]
+    got, launches, stats = _run(spec, fills, group_fast=False)
+    assert [l[3] for l in launches if l[1] == 1024] == [""]
+    exp = fill_oracle.fill(spec, fills[0])
+    bound = fill_oracle.fill(spec, fills[0], absolute=True)
+    compare("c4", spec, got, [golden_util.flatten(e) for e in exp], bound)
+
+
+def test_empty_fill_and_refill():
+    spec = golden_util.load()["c4"]["spec"]
+    empty = dict((k, v[:0]) for k, v in _c4_columns(10, 1).items())
+    fills = [empty, _c4_columns(3000, 4), empty]
+    got, launches, stats = _run(spec, fills)
+    exp = bound = None
+    for arrays in fills:
+        exp = fill_oracle.fill(spec, arrays, exp)
+        bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+    compare("c4", spec, got, [golden_util.flatten(e) for e in exp], bound)
