@@ -938,7 +938,10 @@ def choose_strategies(plans, options, prog=None, layout=None):
             # the block's warps are dealt out to the groups (4 warps = 128 lanes per group for c4's 8 groups)
             if sort_lanes == "auto":
                 lanes = 32
-                while lanes * 2 <= min(64 if sort_chunks else 256, int(options.get("sort_threads", SORT_THREADS)) // len(sgroups)):
+                # (chunked sums: 128 lanes per group where the block has them -- c4's 8 groups then keep all 32 warps busy in the
+                #  summing phase: 17.2 against 16.1 Gev/s with 64, profiles/r02_sweeps.txt; in round 2's second session, with the
+                #  event phase 40 % longer, it made no difference)
+                while lanes * 2 <= min(int(options.get("sort_max_lanes", 128)) if sort_chunks else 256, int(options.get("sort_threads", SORT_THREADS)) // len(sgroups)):
                     lanes *= 2
             else:
                 lanes = int(sort_lanes)
@@ -1683,6 +1686,19 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     else:
         scatter("        ", False)
     src.append("        __syncthreads();")
+    if options.get("sort_prefetch", False):
+        # the columns of this block's next tile: one L2 prefetch per 32-byte sector, sent before the summing phase (the loads at
+        # the top of a tile wait for DRAM otherwise: 6.7 % of the kernel's stall samples, profiles/r02_c4_ncu.txt)
+        src.append("        { const hb_i64 nfirst = (tile + gridDim.x) * HB_TILE;")
+        src.append("          if (nfirst + HB_TILE <= p.n) {")
+        for slot, (name, dtype, is_scalar) in enumerate(prog.cols):
+            if is_scalar:
+                continue
+            per = max(1, 32 // dtype.itemsize)                  # threads per sector
+            for k in range(ept):
+                src.append("              if ((threadIdx.x %% %du) == 0u) hb_prefetch_l2(reinterpret_cast<const char*>(p.cols[%d]) + (nfirst + %d * HB_THREADS + threadIdx.x) * %d);" % (
+                    per, slot, k, dtype.itemsize))
+        src.append("          } }")
     if chunks:
         # the balanced variant: every lane walks a contiguous chunk of the sorted events; a run that ends inside the chunk is
         # flushed on the spot (it ends in no other lane's chunk), a run that goes on in the next lane is a "tail", added
@@ -1719,31 +1735,52 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
             src.append("            if (p0 < ng%s) {" % (" && p.n < 0" if options.get("sort_skip_sum") else ""))
             src.append("                int key = hb_sort_find(st, %d, p0);" % g.nbins)
             src.append("                hb_u32 runend = st[key + 1];")
-            src.append("                for (hb_u32 pos = p0; pos < p1; ++pos) {")
-            src.append("                    if (pos >= runend) {       // the run of `key` ends in this lane's chunk, and in no other lane's")
-            src.append("                        " + flush)
-            src.append("                        do { ++key; runend = st[key + 1]; } while (pos >= runend);")
-            src.append("                    }")
-            if flags:
-                src.append("                    const unsigned er = sop[pos], e = er & %du;" % ((1 << ebits) - 1))
+            advance = ["if (pos%s >= runend) {       // the run of `key` ends in this lane's chunk, and in no other lane's",
+                       "    " + flush,
+                       "    do { ++key; runend = st[key + 1]; } while (pos%s >= runend);",
+                       "}"]
+
+            def accumulate(ind, sfx):
+                """C lines adding the gathered values v<k><sfx> of one event (flag bits in er<sfx>) to the running sums"""
+                squared = set()
+                for j, st_ in enumerate(g.stage):
+                    kind, k = st_[0], st_[1]
+                    if kind in ("sq", "gsq") and k not in squared:
+                        squared.add(k)
+                        src.append("%sconst double q%d%s = hb_mul<double>(v%d%s, v%d%s);" % (ind, k, sfx, k, sfx, k, sfx))
+                    if kind == "E":
+                        src.append("%sa%d += v%d%s;" % (ind, j, k, sfx))
+                    elif kind == "sq":
+                        src.append("%sa%d += q%d%s;" % (ind, j, k, sfx))
+                    elif kind == "gate":
+                        src.append("%sa%d += (er%s & %du) ? v%d%s : 0.0;" % (ind, j, sfx, 1 << (ebits + st_[2]), k, sfx))
+                    else:
+                        assert kind == "gsq"
+                        src.append("%sa%d += (er%s & %du) ? q%d%s : 0.0;" % (ind, j, sfx, 1 << (ebits + st_[2]), k, sfx))
+            emask = (1 << ebits) - 1 if flags else 0xffff
+            pair = odd and chunk % 2 == 0 and bool(options.get("sort_pair", False))
+            if pair:
+                # two events per round: ONE 32-bit load brings both event numbers (the chunk starts on an even position), both
+                # gathers are in flight before the first run-end test -- the loop is a chain of dependent shared-memory loads
+                # (short-scoreboard stalls lead the kernel's stall reasons, profiles/r02_c4_ncu.txt)
+                src.append("                hb_u32 pos = p0;")
+                src.append("                for (; pos + 1u < p1; pos += 2u) {")
+                src.append("                    const unsigned ee = *reinterpret_cast<const unsigned*>(sop + pos);")
+                src.append("                    const unsigned er_a = ee & 0xffffu, er_b = ee >> 16, e_a = er_a & %du, e_b = er_b & %du;" % (emask, emask))
+                src.extend(gather("                    ", used_slots, "e_a", "_a"))
+                src.extend(gather("                    ", used_slots, "e_b", "_b"))
+                src.extend("                    " + x % "" if "%s" in x else "                    " + x for x in advance)
+                accumulate("                    ", "_a")
+                src.extend("                    " + x % " + 1u" if "%s" in x else "                    " + x for x in advance)
+                accumulate("                    ", "_b")
+                src.append("                }")
+                src.append("                if (pos < p1) {")
             else:
-                src.append("                    const unsigned e = sop[pos];")
+                src.append("                for (hb_u32 pos = p0; pos < p1; ++pos) {")
+            src.extend("                    " + x % "" if "%s" in x else "                    " + x for x in advance)
+            src.append("                    const unsigned er = sop[pos], e = er & %du;" % emask)
             src.extend(gather("                    ", used_slots, "e"))
-            squared = set()
-            for j, st_ in enumerate(g.stage):
-                kind, k = st_[0], st_[1]
-                if kind in ("sq", "gsq") and k not in squared:
-                    squared.add(k)
-                    src.append("                    const double q%d = hb_mul<double>(v%d, v%d);" % (k, k, k))
-                if kind == "E":
-                    src.append("                    a%d += v%d;" % (j, k))
-                elif kind == "sq":
-                    src.append("                    a%d += q%d;" % (j, k))
-                elif kind == "gate":
-                    src.append("                    a%d += (er & %du) ? v%d : 0.0;" % (j, 1 << (ebits + st_[2]), k))
-                else:
-                    assert kind == "gsq"
-                    src.append("                    a%d += (er & %du) ? q%d : 0.0;" % (j, 1 << (ebits + st_[2]), k))
+            accumulate("                    ", "")
             src.append("                }")
             src.append("                if (runend > p1) tkey = key;       // the run goes on in the next lane: a tail")
             src.append("                else { %s }" % flush)
@@ -2334,7 +2371,9 @@ def generate(spec, coltypes, options=None):
         raise UnsupportedError("more than 128 histograms in one fill")
     layout = {}
     smem, window = choose_strategies(plans, options, prog, layout)
-    if layout and not layout.get("pipe") and options.get("split_table", True):
+    # (measured on c4: 17.2 Gev/s without, 16.1 with -- the 16-byte look-ups by 32 different bins cost more shared-memory
+    #  wavefronts than the 14 instructions they save are worth, the kernel being bound by that pipe; an option, off by default)
+    if layout and not layout.get("pipe") and options.get("split_table", False):
         smem = _apply_split_tables(prog, layout, smem, int(options.get("sort_smem", SMEM_MAX - 1024)))
     if len(prog.cols) > 32:
         raise UnsupportedError("more than 32 input fields in one fill")

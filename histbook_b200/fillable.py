@@ -728,6 +728,7 @@ def fill_hists(plan, hists, arrays, timed=False):
             stats["fx_missed_total"] = int(plan.fx_stat.read(numpy.uint64)[0])
         stats["deterministic"] = kern.deterministic
         stats["sorted"] = kern.sorted
+        stats["group_fast"] = bool(gfast)
         stats["regs"] = prog.regs
         stats["smem_bytes"] = kern.smem_bytes
         stats["keys_launches"] = 1 if (keys is not None and length > 0) else 0

@@ -76,6 +76,7 @@ def test_c4_book_picks_the_group_fast_variant_and_leaves_it_when_it_must():
     fill_launches = [l for l in launches if l[1] == 1024]
     assert [l[3] for l in fill_launches] == ["group_fast", "group_fast", ""], launches
     assert all(l[0] for l in fill_launches)                                   # the full-tile copy of the event code is there
+    assert stats["group_fast"] is False and stats["sorted"]["flags"] == 1     # (the last fill's statistics)
     exp = bound = None
     for arrays in fills:
         exp = fill_oracle.fill(spec, arrays, exp)

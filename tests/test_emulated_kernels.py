@@ -48,7 +48,10 @@ C4_VARIANTS = [
     {"sort_gate": False},
     {"sort_full": False, "group_fast": True},
     {"sort_ept": 2, "group_fast": True},            # tiles of 2048 events
-    {"sort_lanes": 128},
+    {"sort_lanes": 64},
+    {"split_table": True, "group_fast": True},
+    {"sort_pair": True, "group_fast": True},        # two events per round of the summing loop
+    {"sort_pair": True, "sort_prefetch": True, "sort_threads": 768, "sort_ept": 4},
     {"sort_chunk_odd": False},                      # chunks of tile / lanes event numbers with padding (and its division) instead of 50
     {"sort_chunk_odd": False, "sort_full": False, "split_table": False, "sort_gate": False},      # the kernel as it was before these options
     {"sort_alias_tails": False},
@@ -146,11 +149,12 @@ def test_split_index_from_the_bin_index():
     spec = {"version": 1, "hists": hists}
     assert len(hists) > 16
     coltypes = dict((k, (v.dtype, False)) for k, v in arrays.items())
-    kern = codegen.generate(spec, coltypes, {})
+    kern = codegen.generate(spec, coltypes, {"split_table": True})
     assert kern.sorted is not None
     assert kern.source.count("const int4 sq") == 4                # combos a, b, d, e (each split goal is lowered once); c keeps the chain
+    assert "const int4 sq" not in codegen.generate(spec, coltypes, {}).source      # (an option: measured slower on c4)
+    _check(spec, arrays, {"split_table": True})
     _check(spec, arrays, {})
-    _check(spec, arrays, {"split_table": False})
 
 
 def test_split_table_is_refused_where_it_is_not_valid():

@@ -246,7 +246,7 @@ def test_accumulation_kinds_chosen_for_the_baseline_configs():
     assert f.source.count("gm[") == 1 and k.source.count("gm[") == 8 and "hb_red_f64(row" not in f.source.split("hb_fill_kernel")[0]
     assert f.group_aux == k.group_aux and f.goal_aux == k.goal_aux and f.naux == k.naux and f.smem_bytes == k.smem_bytes
     k = gen("c3", sort=True)                        # forced on a small book: y and y^2 staged, y^4 = (y^2)^2 recomputed
-    assert k.sorted["staged"] == 2 and k.sorted["groups"][0]["values"] == 3 and k.smem_bytes < 227 * 1024 and k.sorted["lanes"] == 64
+    assert k.sorted["staged"] == 2 and k.sorted["groups"][0]["values"] == 3 and k.smem_bytes < 227 * 1024 and k.sorted["lanes"] == 128
     k = gen("c2", deterministic=True)
     assert k.deterministic and len(k.fx_terms) == 2 and "hb_fxg_add128" in k.source and "hb_red_pair(" not in k.source.split("hb_event")[1]
 
