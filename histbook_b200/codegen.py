@@ -1686,7 +1686,7 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     else:
         scatter("        ", False)
     src.append("        __syncthreads();")
-    if options.get("sort_prefetch", False):
+    if options.get("sort_prefetch", True):
         # the columns of this block's next tile: one L2 prefetch per 32-byte sector, sent before the summing phase (the loads at
         # the top of a tile wait for DRAM otherwise: 6.7 % of the kernel's stall samples, profiles/r02_c4_ncu.txt)
         src.append("        { const hb_i64 nfirst = (tile + gridDim.x) * HB_TILE;")
