@@ -1495,10 +1495,6 @@ def _emit_kernel(prog, event_lines, smem, merge_lines, threads, minblocks, windo
     return "\n".join(src) + "\n"
 
 
-def chunks_early(layout):
-    return bool(layout.get("chunks"))
-
-
 def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     """Kernel of a big book with sort groups.  Per tile of HB_TILE events, one 1024-thread block per SM:
       1. every thread evaluates HB_EPT events (one coalesced scalar load per column): histograms outside the groups are
@@ -1550,7 +1546,9 @@ def _emit_kernel_sorted(prog, event_lines, merge_lines, layout, options):
     # full tiles -- all but the last one of a fill -- run a copy of the event function in which ``live`` is a compile-time
     # true: the dump-word selects of the count atomics, tickets and scatter keys fold away (option sort_full)
     full = bool(options.get("sort_full", True))
-    flags, ebits = (layout.get("flags") or []) if chunks_early(layout) else [], int(layout.get("ebits", 16))
+    # (filtered weights that travel as flag bits beside the sorted event numbers: stage_values; the chunked sums only)
+    flags = list(layout.get("flags") or []) if layout.get("chunks") else []
+    ebits = int(layout.get("ebits", 16))
     sig = ["const HbParams& p", "unsigned char* hb_smem", "const bool live_", "const int eid", "hb_u32 (&kr)[HB_NSG]"]
     if flags:
         sig.append("hb_u32& fl")
