@@ -5,6 +5,8 @@ unmodified reference and with the oracle -- the same comparisons as tests/test_g
 
 Not covered here (GPU tests only): hot windows, fixed-point accumulation, the deterministic mode and the vector-load path --
 their inline PTX has no host form -- so these cases run with fx / window / box switched off."""
+import shutil
+
 import numpy
 import pytest
 
@@ -12,6 +14,8 @@ import emul_engine
 import golden_util
 from oracle import fill_oracle
 from test_gpu_parity import compare, LIBM_CASES
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the kernel emulator is compiled with g++")
 
 PLAIN = dict(fx=False, window=False, box=False)
 

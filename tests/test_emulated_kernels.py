@@ -2,12 +2,16 @@
 with the oracle: counts bit-exact, float sums within 1e-12 * sum|term| -- the same bar as the GPU parity tests.  This is
 how a change of the code generator (tickets, scatter, chunked sums, tails, flag bits, group-slot variants ...) is checked
 where there is no GPU; the `-m gpu` tests remain the parity tests proper (they run the real thing through the C ABI)."""
+import shutil
+
 import numpy
 import pytest
 
 import emul_util
 import golden_util
 from oracle import fill_oracle
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the kernel emulator is compiled with g++")
 
 
 def _columns(n, seed, laced=False):

@@ -1,5 +1,7 @@
 """histbook_b200.ingest: fills from Parquet / Arrow IPC / .npy files and from iterables of batches, batch by batch through the
 product's host path on the emulated engine (tests/emul_engine.py), against the oracle fed the same batches."""
+import shutil
+
 import numpy
 import pytest
 
@@ -7,6 +9,8 @@ import emul_engine
 import golden_util
 from oracle import fill_oracle
 from test_gpu_parity import compare
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the kernel emulator is compiled with g++")
 
 
 def _columns(n, seed):
