@@ -121,7 +121,48 @@ static inline unsigned __activemask() { return 0xffffffffu; }
 //  its own peer group, i.e. inserts its key itself -- the warp-level deduplication is an optimisation, not semantics)
 template <typename T> static inline unsigned __match_any_sync(unsigned, T) { return 1u << (threadIdx.x & 31u); }
 
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l) { const unsigned o = hb_emu_exchange<unsigned>(v, l); out = o > out ? o : out; }
+    return out;
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { hb_emu_warps[threadIdx.x >> 5].bar.sync(32); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
+// ---- the inline PTX of hb_template.cuh's fixed-point adds, as host functions (tests/emul_util.py substitutes them) ----------
+static inline unsigned hb_emu_bfe_20_11(unsigned hi) { return (hi >> 20) & 0x7ffu; }
+static inline void hb_emu_neg96(unsigned& q0, unsigned& q1, unsigned& q2) {          // sub.cc / subc.cc / subc: 0 - (q2:q1:q0)
+    const unsigned b0 = q0 != 0u ? 1u : 0u;
+    const unsigned b1 = (q1 != 0u || b0) ? 1u : 0u;
+    q0 = 0u - q0;
+    q1 = 0u - q1 - b0;
+    q2 = 0u - q2 - b1;
+}
+static inline unsigned hb_emu_carry(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a + b) >> 32); }
+static inline void hb_emu_stage1a(unsigned& a1, unsigned& a2, unsigned& pre, unsigned x1, unsigned x2, unsigned carry) {
+    const unsigned long long s1 = (unsigned long long)x1 + carry;                     // add.cc a1 = x1 + carry
+    a1 = (unsigned)s1;
+    const unsigned long long s2 = (unsigned long long)x2 + (unsigned)(s1 >> 32);      // addc.cc a2 = x2 + 0 + c
+    a2 = (unsigned)s2;
+    pre = (unsigned)(s2 >> 32);                                                       // addc pre = 0 + 0 + c
+}
+static inline void hb_emu_stage1b(unsigned& a2, unsigned& pre, unsigned o, unsigned a1) {
+    const unsigned c = hb_emu_carry(o, a1);                                           // add.cc t = o + a1
+    const unsigned long long s2 = (unsigned long long)a2 + c;                         // addc.cc a2 = a2 + 0 + c
+    a2 = (unsigned)s2;
+    pre = pre + (unsigned)(s2 >> 32);                                                 // addc pre = pre + 0 + c
+}
+static inline unsigned hb_emu_stage2(unsigned o, unsigned a2, unsigned hi, unsigned ext) {
+    return hi + ext + hb_emu_carry(o, a2);                                            // add.cc u = o + a2; addc top = hi + ext + c
+}
+
 // ---- atomics --------------------------------------------------------------------------------------------------------
+static inline unsigned atomicMax(unsigned* a, unsigned v) {
+    unsigned old = __atomic_load_n(a, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) { }
+    return old;
+}
 static inline unsigned atomicAdd(unsigned* a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicCAS(unsigned long long* a, unsigned long long cmp, unsigned long long v) {

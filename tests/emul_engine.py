@@ -16,6 +16,7 @@ from histbook_b200 import engine, fillable
 
 _ITEMSIZE = [8, 4, 8, 4, 2, 1, 8, 4, 2, 1, 1]
 HB_KEY_EMPTY = 0xFFF0DEADBEEFCAFE
+VEC_OK = 1
 LAUNCHES = []                   # (kernel name, threads, events) of every emulated launch, for the tests to look at
 
 
@@ -66,6 +67,12 @@ class Arena(object):
     def write(self, array, offset=0):
         array = numpy.ascontiguousarray(array, dtype=numpy.float64).reshape(-1)
         self.a[int(offset):int(offset) + array.size] = array
+
+    def project(self, shape, ncol, keep):
+        """hb_arena_project: sum over the fixed axes with keep[k] false"""
+        full = self.a[:int(numpy.prod(shape)) * int(ncol)].reshape(tuple(int(x) for x in shape) + (int(ncol),))
+        drop = tuple(k for k, kept in enumerate(keep) if not kept)
+        return Arena(_array=numpy.ascontiguousarray(full.sum(axis=drop)).reshape(-1))
 
 
 class KeySet(object):
@@ -122,7 +129,7 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exa
     for k, x in enumerate(win):
         p.win[k] = int(x)
     p.n = int(n)
-    p.vec_ok = 0                                # (the scalar-load path of the per-event kernels: their vector loads are inline PTX)
+    p.vec_ok = VEC_OK                           # 1: the four-events-per-thread path of the per-event kernels (their loads have a host form)
     grid = 2
     LAUNCHES.append((program.source.count("hb_event<true>") > 0, program.threads, int(n), "group_fast" if program.source.count("gm[") <= 1 and "gd_" in program.source else ""))
     if n > 0:

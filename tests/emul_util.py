@@ -33,6 +33,23 @@ class HbParams(ctypes.Structure):
                 ("flags", ctypes.c_int), ("win", ctypes.c_int * 128), ("sched", ctypes.c_void_p)]
 
 
+# (exact text in csrc/hb_template.cuh, host form)
+PTX_FORMS = [
+    ("    hb_loader<T>::load4(reinterpret_cast<const T*>(base) + tile_first, tid, nthreads, o);",
+     "    for (int k = 0; k < 4; ++k) o[k] = reinterpret_cast<const T*>(base)[tile_first + (hb_i64)(k >> 1) * 2 * nthreads + (hb_i64)tid * 2 + (k & 1)];"),
+    ('    asm("bfe.u32 %0, %1, 20, 11;" : "=r"(e) : "r"(hi));', "    e = hb_emu_bfe_20_11(hi);"),
+    ('    if (neg) asm("sub.cc.u32 %0, 0, %0;\\n\\tsubc.cc.u32 %1, 0, %1;\\n\\tsubc.u32 %2, 0, %2;" : "+r"(q0), "+r"(q1), "+r"(q2));',
+     "    if (neg) hb_emu_neg96(q0, q1, q2);"),
+    ('    asm("{\\n\\t.reg .u32 t;\\n\\tadd.cc.u32 t, %1, %2;\\n\\taddc.u32 %0, 0, 0;\\n\\t}" : "=r"(c) : "r"(o), "r"(f.x0));',
+     "    c = hb_emu_carry(o, f.x0);"),
+    ('    asm("add.cc.u32 %0, %3, %5;\\n\\taddc.cc.u32 %1, %4, 0;\\n\\taddc.u32 %2, 0, 0;"\n        : "=r"(a1), "=r"(a2), "=r"(pre) : "r"(f.x1), "r"(f.x2), "r"(carry));',
+     "    hb_emu_stage1a(a1, a2, pre, f.x1, f.x2, carry);"),
+    ('    asm("{\\n\\t.reg .u32 t;\\n\\tadd.cc.u32 t, %2, %3;\\n\\taddc.cc.u32 %0, %0, 0;\\n\\taddc.u32 %1, %1, 0;\\n\\t}"\n        : "+r"(a2), "+r"(pre) : "r"(o), "r"(a1));',
+     "    hb_emu_stage1b(a2, pre, o, a1);"),
+    ('    asm("{\\n\\t.reg .u32 u;\\n\\tadd.cc.u32 u, %1, %2;\\n\\taddc.u32 %0, %3, %4;\\n\\t}" : "=r"(top) : "r"(o), "r"(a2), "r"((hb_u32)(t >> 32)), "r"(f.ext));',
+     "    top = hb_emu_stage2(o, a2, (hb_u32)(t >> 32), f.ext);"),
+]
+
 RUNNER = r"""
 extern "C" int hb_emu_run(const HbParams* p, int grid, int threads)
 {
@@ -55,11 +72,17 @@ def host_source(kernel_source):
     with open(TEMPLATE) as f:
         template = f.read()
     template = template.replace("#pragma once", "")
-    # the one inline-PTX helper the emulated kernels need has a host form in the shim; every other asm statement (vector
-    # loads of the per-event kernels, the carry chains of the fixed-point adds) belongs to paths this harness does not run
+    # inline PTX -> host forms (tests/emul/cuda_emul.h).  Every substitution must hit exactly once: a change of the template
+    # that the emulator does not know about fails here, not silently in a test.
     template = template.replace("void hb_red_f64(double* addr, double v) {", "void hb_red_f64_ptx(double* addr, double v) {")
+    for ptx, host in PTX_FORMS:
+        assert template.count(ptx) == 1, "hb_template.cuh changed: no unique match for %r" % ptx[:60]
+        template = template.replace(ptx, host)
+    # what is left: the vector loads inside hb_loader (hb_load4 is redirected above them), the L2 prefetch hint and the
+    # cache-hinted RED of hb_red_f64_ptx (not called)
     template = re.sub(r"asm\s+volatile\s*\(", "HB_EMU_NOASM(", template)
-    template = re.sub(r"\basm\s*\(", "HB_EMU_NOASM(", template)
+    template = template.replace('asm("createpolicy', 'HB_EMU_NOASM("createpolicy')
+    assert not re.search(r"\basm\s*\(", template), "an asm statement of hb_template.cuh has no host form"
     src = kernel_source.replace('#include "hb_template.cuh"', '#include "cuda_emul.h"\n' + template)
     src, nbar = re.subn(r'asm volatile\("bar\.sync %0, %1;" :: "r"\(([^)]*)\), "r"\(([^)]*)\) : "memory"\);', r"hb_emu_bar(\1, \2);", src)
     assert "asm volatile" not in src.split("hb_fill_kernel")[-1], "an inline-PTX statement of the generated kernel has no host form"

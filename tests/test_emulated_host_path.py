@@ -3,8 +3,11 @@ kernel variant, Store) run end to end on CPU: the engine's device entry points a
 (tests/emul_engine.py), the generated kernels execute on CPU threads, the results are compared with the golden outputs of the
 unmodified reference and with the oracle -- the same comparisons as tests/test_gpu_parity.py makes on the B200.
 
-Not covered here (GPU tests only): hot windows, fixed-point accumulation, the deterministic mode and the vector-load path --
-their inline PTX has no host form -- so these cases run with fx / window / box switched off."""
+The inline PTX of the template has host forms in the shim (the carry chains of the fixed-point adds, the vector loads;
+tests/emul_util.PTX_FORMS), so hot windows, fixed-point accumulation and the four-events-per-thread path run here too: every
+golden case is run twice, with fx / window / box switched off and -- where that changes the kernel -- with the defaults.
+Not covered (GPU tests only): the deterministic mode (its finalisation is a kernel of csrc/hbfill.cu) and everything else that
+lives in the engine itself (staging, streams, arenas on the device)."""
 import shutil
 
 import numpy
@@ -45,8 +48,21 @@ def _emulable_case(name):
     return True
 
 
+def _kernel_text(case, options):
+    """the fill kernel these options generate for the case's first fill (None if its columns are not plain arrays)"""
+    from histbook_b200 import codegen, columns, spec as hbspec
+    try:
+        fields = hbspec.spec_fields(case["spec"])
+        cols, length = columns.bind_all(fields, golden_util.fills(case)[0])
+        coltypes = dict((n, (cols[n].dtype, cols[n].is_scalar)) for n in fields)
+        return codegen.generate(case["spec"], coltypes, options).source
+    except Exception:
+        return None
+
+
+@pytest.mark.parametrize("mode", ["plain", "default"])
 @pytest.mark.parametrize("name", [n for n in golden_util.names() if n not in ("c2", "c3", "c5", "c2_nanlaced")])
-def test_golden_cases_through_the_host_path(name):
+def test_golden_cases_through_the_host_path(name, mode):
     """every golden case of the reference (several fills, scalars, group axes ...) through SpecFill on the emulated engine"""
     if not _emulable_case(name):
         pytest.skip("not a case for the emulated engine")
@@ -54,7 +70,9 @@ def test_golden_cases_through_the_host_path(name):
     fills = golden_util.fills(case)
     if sum(len(next((v for v in arrays.values() if isinstance(v, numpy.ndarray) and v.ndim == 1), [])) for arrays in fills) > 400000:
         pytest.skip("too many events for CPU threads")
-    got, launches, stats = _run(case["spec"], fills, **PLAIN)
+    if mode == "default" and _kernel_text(case, {}) == _kernel_text(case, PLAIN):
+        pytest.skip("the defaults generate the same kernel as fx / window / box off")
+    got, launches, stats = _run(case["spec"], fills, **(PLAIN if mode == "plain" else {}))
     bound = None
     for arrays in fills:
         bound = fill_oracle.fill(case["spec"], arrays, bound, absolute=True)
@@ -108,3 +126,34 @@ def test_empty_fill_and_refill():
         exp = fill_oracle.fill(spec, arrays, exp)
         bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
     compare("c4", spec, got, [golden_util.flatten(e) for e in exp], bound)
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5"])
+def test_baseline_configurations_with_their_default_kernels(name):
+    """the five BASELINE configurations as the product runs them: c1 u32 counts, c2 pilot -> ragged hot window (dense variant,
+    fixed point inside), c3 fixed-point pilot + fixed-point profile sums, c4 sorted big book, c5 box window that is not placed ->
+    paired global REDs; two fills each, NaN / inf laced, through SpecFill on the emulated engine"""
+    spec = golden_util.load()[name]["spec"]
+    n = 30000
+    rs = numpy.random.RandomState(3)
+    cols = {"x": rs.normal(0, 1, n), "y": rs.normal(0, 1, n), "z": rs.normal(0, 1, n), "w": rs.uniform(0.5, 1.5, n),
+            "n": rs.poisson(3, n).astype(numpy.int64)}
+    cols["x"][::997] = numpy.nan
+    cols["w"][1::1009] = numpy.nan
+    cols["y"][2::1013] = numpy.inf
+    from histbook_b200 import spec as hbspec
+    fields = hbspec.spec_fields(spec)
+    fills = [dict((k, cols[k][:n // 2 + 7]) for k in fields), dict((k, cols[k][n // 2 + 7:]) for k in fields)]
+    got, launches, stats = _run(spec, fills)
+    if name == "c2":
+        assert stats["window"] is not None and stats["window"]["dense"] and stats["window_coverage"] > 0.95
+        assert len(launches) == 3                               # pilot through the global path, fixed-point range pilot, windowed fill
+    if name == "c3":
+        assert len(launches) == 3                               # range pilot + two fills
+    if name == "c5":
+        assert stats["window"] is None and stats["window_coverage"] < 0.25
+    exp = bound = None
+    for arrays in fills:
+        exp = fill_oracle.fill(spec, arrays, exp)
+        bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+    compare(name, spec, got, [golden_util.flatten(e) for e in exp], bound)
