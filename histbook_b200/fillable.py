@@ -227,6 +227,72 @@ def _fx_scales(plan, sig, kern, rng, rprog, cols, length):
 
 WINDOW_MIN_COVERAGE = 0.25      # below this (estimated) fraction of events a window is not worth its merge
 WINDOW_DENSE_COVERAGE = 0.95    # the dense variant (fixed point inside, plain REDs outside) needs its smaller window to hold this much
+WINDOW_CHECK_FILLS = 64         # a placed window is looked at again after this many fills ...
+WINDOW_CHECK_EVENTS = 8 * 10**9   # ... or this many events, whichever comes first (one read of the histogram: a host synchronisation)
+WINDOW_DRIFT = 0.05             # ... and placed anew when it holds this much less of the recent fills than a new one would
+
+
+def _ragged_density(wst, info):
+    """|sum of weights| the histogram holds per (row of the leading axes, bin of the trailing axes): what a window is placed from"""
+    content = wst.arena.read(0, info["rows"] * info["trail"] * info["ncol"])
+    density = numpy.abs(content.reshape(info["rows"], info["trail"], info["ncol"])[:, :, info["col"]])
+    density[~numpy.isfinite(density)] = 0.0
+    return density
+
+
+def _place_ragged(plan, cols, kern, info, wst, density):
+    """Place the ragged hot window of histogram store ``wst`` from ``density`` (choose_ragged): the dense kernel variant if its
+    smaller window still holds WINDOW_DENSE_COVERAGE of it, else the sparse one if that holds WINDOW_MIN_COVERAGE, else none."""
+    wst.window = False
+    if _options.get("fx", "auto") == "auto" and not kern.deterministic and len(kern.plans[info["hid"]].f64_terms) >= 2:
+        dinfo = plan.kernel_for(cols, dense=True)[1][0].window
+        if dinfo is not None:
+            first, nlen, coverage = choose_ragged(density, dinfo["wmax"])
+            if coverage >= WINDOW_DENSE_COVERAGE:
+                table, bins = window_table(first, nlen, dinfo["table_bits"])
+                wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum()), "dense": True,
+                              "first": first, "length": nlen}
+                wst.window_coverage = coverage
+    if not wst.window:
+        first, nlen, coverage = choose_ragged(density, info["wmax"])
+        wst.window_coverage = coverage
+        if coverage >= WINDOW_MIN_COVERAGE:
+            table, bins = window_table(first, nlen, info["table_bits"])
+            wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum()), "dense": False,
+                          "first": first, "length": nlen}
+
+
+def _watch_window(plan, cols, kern, info, wst, length):
+    """A window is placed from what the histogram held at its first fills; data that drifts away from there would fall to the
+    global-RED path for good.  Every WINDOW_CHECK_FILLS fills (or WINDOW_CHECK_EVENTS events) the histogram is read once:
+    the share of the fills SINCE the last look that the window caught becomes ``window_coverage`` (what last_stats reports), and
+    if a window placed from those recent fills alone would hold WINDOW_DRIFT more, it replaces the old one."""
+    wst.window_fills += 1
+    wst.window_events += length
+    if wst.window_fills < WINDOW_CHECK_FILLS and wst.window_events < WINDOW_CHECK_EVENTS:
+        return
+    density = _ragged_density(wst, info)
+    seen, wst.window_seen = wst.window_seen, density
+    wst.window_fills = wst.window_events = 0
+    if seen is None or seen.shape != density.shape:
+        return
+    recent = numpy.abs(density - seen)
+    total = float(recent.sum())
+    if total <= 0.0 or not numpy.isfinite(total):
+        return
+    current = 0.0
+    if wst.window:
+        trail = numpy.arange(density.shape[1])[None, :]
+        first, nlen = wst.window["first"], wst.window["length"]
+        current = float(recent[(trail >= first[:, None]) & (trail < (first + nlen)[:, None])].sum()) / total
+    wmax = info["wmax"]
+    if wst.window and wst.window["dense"]:
+        wmax = plan.kernel_for(cols, dense=True)[1][0].window["wmax"]
+    best = choose_ragged(recent, wmax)[2]
+    if best >= current + WINDOW_DRIFT and best >= WINDOW_MIN_COVERAGE:
+        _place_ragged(plan, cols, kern, info, wst, recent)
+    else:
+        wst.window_coverage = current if wst.window else best
 
 
 def choose_ragged(density, wmax):
@@ -667,25 +733,12 @@ def fill_hists(plan, hists, arrays, timed=False):
                         base["aux"][info["aux"]] = 0          # null row table = no window
                         done = min(length, max(kern.tile, PILOT_EVENTS // kern.tile * kern.tile))
                         extra = launch(base, done, [0, 0])["ms_kernel"]
-                    content = wst.arena.read(0, info["rows"] * info["trail"] * info["ncol"])
-                    density = numpy.abs(content.reshape(info["rows"], info["trail"], info["ncol"])[:, :, info["col"]])
-                    density[~numpy.isfinite(density)] = 0.0
+                    density = _ragged_density(wst, info)
                     wst.window_key = key
-                    wst.window = False
-                    if _options.get("fx", "auto") == "auto" and not kern.deterministic and len(kern.plans[info["hid"]].f64_terms) >= 2:
-                        dinfo = plan.kernel_for(cols, dense=True)[1][0].window
-                        if dinfo is not None:
-                            first, nlen, coverage = choose_ragged(density, dinfo["wmax"])
-                            if coverage >= WINDOW_DENSE_COVERAGE:
-                                table, bins = window_table(first, nlen, dinfo["table_bits"])
-                                wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum()), "dense": True}
-                                wst.window_coverage = coverage
-                    if not wst.window:
-                        first, nlen, coverage = choose_ragged(density, info["wmax"])
-                        wst.window_coverage = coverage
-                        if coverage >= WINDOW_MIN_COVERAGE:
-                            table, bins = window_table(first, nlen, info["table_bits"])
-                            wst.window = {"table": engine.DeviceBuffer(table), "bins": bins, "rows": int((nlen > 0).sum()), "dense": False}
+                    _place_ragged(plan, cols, kern, info, wst, density)
+                    wst.window_seen, wst.window_fills, wst.window_events = density, 0, 0
+                elif info.get("box") is None:
+                    _watch_window(plan, cols, kern, info, wst, length)
                 if wst.window and wst.window["dense"]:
                     dsig, (dkern, dprog, _k, _kp, drng, drprog) = plan.kernel_for(cols, dense=True)
                     used = (dsig, dkern, dprog, drng, drprog)

@@ -105,6 +105,9 @@ class Store(object):
         self.window = None            # {"table": DeviceBuffer, "bins", "rows"}
         self.window_key = None        # (rows, trail, wmax) of the kernel the window was placed for
         self.window_coverage = None
+        self.window_seen = None       # |sum of weights| per (row, trailing bin) when the window was placed or last checked (fillable._watch_window)
+        self.window_fills = 0         # fills / events since then
+        self.window_events = 0
         self._admitted = None         # the key lists of the last fill (admit)
         self.exact = None             # deterministic mode: engine.Arena of 128-bit accumulators (zero between fills)
         self.nonempty = False                         # the device copy holds at least one fill / uploaded content
@@ -139,6 +142,7 @@ class Store(object):
                 self.arena.write(self._check(self.host))
             self.nonempty = self.host is not None
             self.window = None
+            self.window_seen = None
         else:
             self._upload_groups()
         self.dev_valid = True

@@ -157,3 +157,37 @@ def test_baseline_configurations_with_their_default_kernels(name):
         exp = fill_oracle.fill(spec, arrays, exp)
         bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
     compare(name, spec, got, [golden_util.flatten(e) for e in exp], bound)
+
+
+def test_hot_window_follows_data_that_drifts(monkeypatch):
+    """c2's ragged hot window is placed from the first fills; when the data moves away, the periodic look at the histogram
+    (fillable._watch_window) places a new window from the recent fills alone -- or, where a new one would not be better by
+    WINDOW_DRIFT, at least reports the share of the recent fills the old one really caught (last_stats "window_coverage")."""
+    from histbook_b200 import fillable
+    monkeypatch.setattr(fillable, "WINDOW_CHECK_FILLS", 2)
+    spec = golden_util.load()["c2"]["spec"]
+
+    def run(drift):
+        monkeypatch.setattr(fillable, "WINDOW_DRIFT", drift)
+        rs = numpy.random.RandomState(12)
+
+        def batch(n, shift):
+            return {"x": rs.normal(shift, 0.3, n), "y": rs.normal(shift, 0.3, n), "w": rs.uniform(0.5, 1.5, n)}
+        fills = [batch(12000, 0.0), batch(6000, 0.0)] + [batch(6000, 1.2) for _ in range(5)]
+        seen = []
+        with emul_engine.installed():
+            sf = fillable.SpecFill(spec)
+            exp = bound = None
+            for arrays in fills:
+                sf.fill(arrays)
+                st = dict(fillable.last_stats)
+                seen.append((st["window"]["bins"] if st["window"] else 0, round(st["window_coverage"], 3)))
+                exp = fill_oracle.fill(spec, arrays, exp)
+                bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+            compare("c2", spec, sf.contents(), [golden_util.flatten(e) for e in exp], bound)
+        return seen
+    seen = run(0.05)
+    assert seen[0][1] > 0.95 and seen[1] == seen[0]               # placed on the first fill
+    assert seen[4][0] != seen[0][0] and seen[-1][1] > 0.95        # after two fills of moved data: a new window, placed from them alone
+    seen = run(2.0)                                               # never replace: the look reports what the old window caught
+    assert all(b == seen[0][0] for b, c in seen) and seen[-1][1] < 0.05
