@@ -42,8 +42,12 @@ def issue_roofline(workload):
         return None
     if "warp_inst_per_event" not in entry:
         return None
-    return {"bound": "issue", "warp_inst_per_event": entry["warp_inst_per_event"], "peak_events_per_s": 148 * 4 * 1.965e9 / entry["warp_inst_per_event"],
-            "source": entry.get("source"), "note": "148 SMs x 4 issue slots x 1.965 GHz / warp instructions per event; the HBM figure above is what the metric asks for"}
+    out = {"bound": "issue", "warp_inst_per_event": entry["warp_inst_per_event"], "peak_events_per_s": 148 * 4 * 1.965e9 / entry["warp_inst_per_event"],
+           "source": entry.get("source"), "note": "148 SMs x 4 issue slots x 1.965 GHz / warp instructions per event; the HBM figure above is what the metric asks for"}
+    if "smem_wavefronts_per_event" in entry:
+        # the other pipe the kernel sits on: one shared-memory wavefront per clock and SM
+        out["smem_pipe"] = {"wavefronts_per_event": entry["smem_wavefronts_per_event"], "peak_events_per_s": 148 * 1.965e9 / entry["smem_wavefronts_per_event"]}
+    return out
 
 
 def ncu_traffic(workload, n):
@@ -405,6 +409,8 @@ def run_gpu(args):
         second = issue_roofline(workload)
         if second is not None:
             second["frac"] = (n / (ms_k / args.steps * 1e-3)) / second["peak_events_per_s"]
+            if "smem_pipe" in second:
+                second["smem_pipe"]["frac"] = (n / (ms_k / args.steps * 1e-3)) / second["smem_pipe"]["peak_events_per_s"]
             line["roofline"]["second_bound"] = second
         if other_scaling:
             line["other_scaling"] = other_scaling
