@@ -68,6 +68,45 @@ class Arena(object):
         array = numpy.ascontiguousarray(array, dtype=numpy.float64).reshape(-1)
         self.a[int(offset):int(offset) + array.size] = array
 
+    # (numpy restatements of the engine's utility kernels in csrc/hbfill.cu -- enough for the API glue above them to run; the
+    #  kernels themselves are covered by the GPU tests only)
+    def axpy(self, other, alpha=1.0):
+        n = min(self.a.size, other.a.size)
+        self.a[:n] = self.a[:n] + float(alpha) * other.a[:n] if alpha != 1.0 else self.a[:n] + other.a[:n]
+
+    def axpy_at(self, dst_off, other, src_off, count, alpha=1.0):
+        d, q, c = int(dst_off), int(src_off), int(count)
+        self.a[d:d + c] = self.a[d:d + c] + (other.a[q:q + c] if alpha == 1.0 else float(alpha) * other.a[q:q + c])
+
+    def scale(self, alpha):
+        self.a[:] = self.a * float(alpha)
+
+    def slice(self, outer, length, inner, start, step, count):
+        full = self.a[:int(outer) * int(length) * int(inner)].reshape(int(outer), int(length), int(inner))
+        idx = int(start) + int(step) * numpy.arange(int(count))
+        return Arena(_array=numpy.ascontiguousarray(full[:, idx, :]).reshape(-1))
+
+    def table(self, nrows, ncol, sumw, sumw2, count, error, effcount, profiles):
+        rows = self.a[:int(nrows) * int(ncol)].reshape(int(nrows), int(ncol))
+        w = rows[:, sumw]
+        w2 = rows[:, sumw2] if sumw2 is not None else None
+        good = w > 0.0
+        out = []
+        with numpy.errstate(all="ignore"):
+            eff = (w * w) / w2 if w2 is not None else w
+            if count:
+                out.append(w)
+                if error:
+                    out.append(numpy.sqrt(w2 if w2 is not None else w))
+            if effcount:
+                out.append(numpy.where(good, eff, 0.0))
+            for x, x2 in profiles:
+                mean = rows[:, x] / w
+                out.append(numpy.where(good, mean, 0.0))
+                if error:
+                    out.append(numpy.where(good, numpy.sqrt((rows[:, x2] / w - mean * mean) / eff), 0.0))
+        return Arena(_array=numpy.ascontiguousarray(numpy.stack(out, axis=1)).reshape(-1))
+
     def project(self, shape, ncol, keep):
         """hb_arena_project: sum over the fixed axes with keep[k] false"""
         full = self.a[:int(numpy.prod(shape)) * int(ncol)].reshape(tuple(int(x) for x in shape) + (int(ncol),))
@@ -130,7 +169,7 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exa
         p.win[k] = int(x)
     p.n = int(n)
     p.vec_ok = VEC_OK                           # 1: the four-events-per-thread path of the per-event kernels (their loads have a host form)
-    grid = 2
+    grid = 2 if n > (program.tile or 4 * program.threads) else 1        # (a second block only where it gets a tile: threads are not free here)
     LAUNCHES.append((program.source.count("hb_event<true>") > 0, program.threads, int(n), "group_fast" if program.source.count("gm[") <= 1 and "gd_" in program.source else ""))
     if n > 0:
         assert program.lib.hb_emu_run(ctypes.byref(p), grid, program.threads) == 0
