@@ -152,9 +152,37 @@ class DeviceBuffer(object):
         self.a.view(numpy.uint8)[:array.nbytes] = array.view(numpy.uint8).reshape(-1)
 
 
+def fx_finalize(content, exact, nrows, ncol, ks, masks):
+    """csrc/hbfill.cu hb_fx_finalize, with Python integers: per (row, float64 slot) the two 192-bit two's-complement windows
+    (upper: lsb 2^s, lower: lsb 2^(s - 51), s = k - 1075) are added exactly, rounded to float64 ONCE (Fraction -> float is
+    correctly rounded) and added to the slot's destination columns; the accumulators are zeroed."""
+    from fractions import Fraction
+    words = exact.a.view(numpy.uint64)
+    nslots = len(ks)
+    used = words[:int(nrows) * nslots * 6].reshape(-1, 6)
+    for i in numpy.flatnonzero(used.any(axis=1)):
+        w = [int(x) for x in used[i]]
+
+        def signed(a):
+            v = a[0] | (a[1] << 64) | (a[2] << 128)
+            return v - (1 << 192) if v >> 191 else v
+        total = signed(w[:3]) * (1 << 51) + signed(w[3:])
+        row, j = divmod(int(i), nslots)
+        v = float(Fraction(total) * Fraction(2) ** (int(ks[j]) - 1075 - 51))
+        used[i] = 0
+        m, c = int(masks[j]), 0
+        while m:
+            if m & 1:
+                content.a[row * int(ncol) + c] += v
+            m >>= 1
+            c += 1
+
+
 def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exact=None):
-    assert exact is None, "the emulator does not run the deterministic mode"
     p = emul_util.HbParams()
+    for hid, a in enumerate(exact or ()):
+        if a is not None:
+            p.fxg[hid] = a.ptr                      # deterministic mode: the histogram's exact accumulators
     for slot, c in enumerate(columns):
         if c[0] == "scalar":
             p.scal[slot] = c[2]
@@ -178,7 +206,7 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exa
 
 @contextlib.contextmanager
 def installed():
-    names = ["compile_source", "Program", "Arena", "KeySet", "DeviceBuffer", "fill", "init", "producer_stream", "stream_wait", "sync"]
+    names = ["compile_source", "Program", "Arena", "KeySet", "DeviceBuffer", "fill", "fx_finalize", "init", "producer_stream", "stream_wait", "sync"]
     saved = dict((n, getattr(engine, n)) for n in names)
     engine.compile_source = compile_source
     engine.Program = Program
@@ -186,6 +214,7 @@ def installed():
     engine.KeySet = KeySet
     engine.DeviceBuffer = DeviceBuffer
     engine.fill = fill
+    engine.fx_finalize = fx_finalize
     engine.init = lambda device=None: 0
     engine.producer_stream = lambda: 0
     engine.stream_wait = lambda waiter, signaler: None

@@ -6,8 +6,8 @@ unmodified reference and with the oracle -- the same comparisons as tests/test_g
 The inline PTX of the template has host forms in the shim (the carry chains of the fixed-point adds, the vector loads;
 tests/emul_util.PTX_FORMS), so hot windows, fixed-point accumulation and the four-events-per-thread path run here too: every
 golden case is run twice, with fx / window / box switched off and -- where that changes the kernel -- with the defaults.
-Not covered (GPU tests only): the deterministic mode (its finalisation is a kernel of csrc/hbfill.cu) and everything else that
-lives in the engine itself (staging, streams, arenas on the device)."""
+The deterministic mode has its own file (tests/test_deterministic_emulated.py).  Not covered (GPU tests only): what lives in the
+engine itself (staging, streams, arenas on the device, its utility kernels)."""
 import shutil
 
 import numpy
