@@ -190,14 +190,16 @@ def bind(name, value):
         return _scalar(col, value)
     if value.ndim != 1:
         raise UnsupportedError("field {0!r}: only one-dimensional arrays can be filled".format(name))
-    if value.dtype.name not in DTYPE_CODE:
+    code = _code(value.dtype)                              # (cached per dtype: dtype.name costs 3 us, this sits on the per-fill path)
+    if code is None and value.dtype.name not in DTYPE_CODE:
         raise UnsupportedError("field {0!r}: dtype {1} is not supported by the B200 fill backend "
                                "(strings/objects need dictionary encoding first)".format(name, value.dtype))
     if not value.flags.c_contiguous or value.dtype.byteorder == ">":
         value = numpy.ascontiguousarray(value, dtype=value.dtype.newbyteorder("="))
+        code = _code(value.dtype)
     col.dtype = value.dtype
-    col.code = _code(value.dtype)
-    col.ptr = value.ctypes.data if value.shape[0] > 0 else 0
+    col.code = code
+    col.ptr = value.__array_interface__["data"][0] if value.shape[0] > 0 else 0      # (value.ctypes.data builds a ctypes object: 1.5 us)
     col.location = 0
     col.length = int(value.shape[0])
     col.keepalive = value
