@@ -1,7 +1,7 @@
 """The product's fill path on the EMULATED engine (tests/emul_engine.py) against the UNMODIFIED reference on seeded random
 histogram definitions -- the CPU twin of tests/test_random_definitions_gpu.py (same generator, same comparisons), once with
 the default kernels and once with the sorted strategy of big books forced on (tickets, scatter, chunked sums, flag bits for
-filtered weights ... on whatever the generator draws).  Offline hunts over more seeds (10 with the defaults, 5 sorted: 198
+filtered weights ... on whatever the generator draws).  Offline hunts over 25 more seeds and six option sets (424
 definitions) found no mismatch."""
 import shutil
 import warnings
