@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -72,16 +73,29 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
 static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 
 // ---- barriers -------------------------------------------------------------------------------------------------------
+// A barrier nobody completes (a kernel whose threads do not all arrive: a bug of the generator, or a construct this stand-in does
+// not model) must fail the test, not hang it: after HB_EMU_BARRIER_TIMEOUT seconds the launch is marked failed, every barrier
+// opens, the threads run to their end and hb_emu_run reports the failure.
+#ifndef HB_EMU_BARRIER_TIMEOUT
+#define HB_EMU_BARRIER_TIMEOUT 120
+#endif
+static std::atomic<int> hb_emu_failed{0};
 struct hb_emu_barrier {
     std::mutex m;
     std::condition_variable cv;
     int waiting = 0;
     unsigned gen = 0;
     void sync(int count) {
+        if (hb_emu_failed.load()) return;
         std::unique_lock<std::mutex> l(m);
         const unsigned g = gen;
         if (++waiting >= count) { waiting = 0; ++gen; cv.notify_all(); }
-        else cv.wait(l, [&] { return gen != g; });
+        else if (!cv.wait_for(l, std::chrono::seconds(HB_EMU_BARRIER_TIMEOUT), [&] { return gen != g || hb_emu_failed.load() != 0; })) {
+            hb_emu_failed.store(1);
+            waiting = 0;
+            ++gen;
+            cv.notify_all();
+        }
     }
 };
 static hb_emu_barrier hb_emu_block_bar;

@@ -55,14 +55,15 @@ extern "C" int hb_emu_run(const HbParams* p, int grid, int threads)
 {
     blockDim.x = (unsigned)threads;
     gridDim.x = (unsigned)grid;
-    for (int b = 0; b < grid; ++b) {
+    hb_emu_failed.store(0);
+    for (int b = 0; b < grid && !hb_emu_failed.load(); ++b) {
         std::vector<std::thread> pool;
         pool.reserve(threads);
         for (int t = 0; t < threads; ++t)
             pool.emplace_back([=] { threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)b; hb_fill_kernel(*p); });
         for (auto& th : pool) th.join();
     }
-    return 0;
+    return hb_emu_failed.load();           // 1: a barrier timed out (cuda_emul.h)
 }
 """
 

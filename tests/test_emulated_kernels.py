@@ -203,3 +203,22 @@ def test_golden_cases_sorted_on_the_emulator(name):
     case = golden_util.load()[name]
     arrays = golden_util.fills(case)[0]
     _check(case["spec"], arrays, {"sort": True}, grid=2)
+
+
+def test_a_barrier_nobody_completes_fails_the_launch_instead_of_hanging_it():
+    """the stand-in's watchdog (tests/emul/cuda_emul.h): one thread leaves before the block barrier"""
+    import ctypes
+    source = ('#define HB_EMU_BARRIER_TIMEOUT 1\n#include "hb_template.cuh"\n'
+              'extern "C" __global__ void hb_fill_kernel(const HbParams p)\n{\n'
+              '    extern __shared__ __align__(16) unsigned char hb_smem[];\n'
+              '    if (threadIdx.x == 3 && p.n == 1) return;\n    __syncthreads();\n'
+              '    if (threadIdx.x == 0) reinterpret_cast<double*>(p.hist[0])[0] += 1.0;\n}\n')
+    lib = emul_util.build(source)
+    lib.hb_emu_run.argtypes = [ctypes.POINTER(emul_util.HbParams), ctypes.c_int, ctypes.c_int]
+    out = numpy.zeros(1)
+    p = emul_util.HbParams()
+    p.hist[0] = out.ctypes.data
+    p.n = 0
+    assert lib.hb_emu_run(ctypes.byref(p), 2, 64) == 0 and out[0] == 2.0          # every thread arrives: two blocks, two adds
+    p.n = 1
+    assert lib.hb_emu_run(ctypes.byref(p), 1, 64) == 1                            # thread 3 never arrives: reported after the timeout
