@@ -204,9 +204,23 @@ def fill(program, columns, n, arenas, aux=(), win=(), timed=False, offset=0, exa
     return {"events": int(n), "h2d_bytes": 0, "launches": 1 if n > 0 else 0, "grid": grid, "blocks_per_sm": 1, "ms_kernel": 0.0}
 
 
+def fill_multi(parts, columns, n, timed=False, offset=0):
+    """hb_fill_multi: several programs over the same columns in one pass -- here one emulated launch per part"""
+    out = None
+    for part in parts:
+        cols = [columns[i] for i in part["colmap"]]
+        st = fill(part["program"], cols, n, part["arenas"], aux=part.get("aux", ()), win=part.get("win", ()), timed=timed, offset=offset,
+                  exact=part.get("exact"))
+        if out is None:
+            out = st
+        else:
+            out["launches"] += st["launches"]
+    return out or {"events": int(n), "h2d_bytes": 0, "launches": 0, "grid": 0, "blocks_per_sm": 0, "ms_kernel": 0.0}
+
+
 @contextlib.contextmanager
 def installed():
-    names = ["compile_source", "Program", "Arena", "KeySet", "DeviceBuffer", "fill", "fx_finalize", "init", "producer_stream", "stream_wait", "sync"]
+    names = ["compile_source", "Program", "Arena", "KeySet", "DeviceBuffer", "fill", "fill_multi", "fx_finalize", "init", "producer_stream", "stream_wait", "sync"]
     saved = dict((n, getattr(engine, n)) for n in names)
     engine.compile_source = compile_source
     engine.Program = Program
@@ -215,6 +229,7 @@ def installed():
     engine.DeviceBuffer = DeviceBuffer
     engine.fill = fill
     engine.fx_finalize = fx_finalize
+    engine.fill_multi = fill_multi
     engine.init = lambda device=None: 0
     engine.producer_stream = lambda: 0
     engine.stream_wait = lambda waiter, signaler: None

@@ -191,3 +191,21 @@ def test_hot_window_follows_data_that_drifts(monkeypatch):
     assert seen[4][0] != seen[0][0] and seen[-1][1] > 0.95        # after two fills of moved data: a new window, placed from them alone
     seen = run(2.0)                                               # never replace: the look reports what the old window caught
     assert all(b == seen[0][0] for b, c in seen) and seen[-1][1] < 0.05
+
+
+def test_a_book_beyond_one_kernels_parameter_block_is_filled_in_parts():
+    """130 histograms: two kernels (fillable.Plan.parts_for, PART_MAX_HISTS = 96) in one pass over the columns, one key
+    discovery for the whole book; the parts run the generic kernels (fillable._fill_parts)"""
+    from histbook_b200 import fillable
+    base = golden_util.load()["c4"]["spec"]
+    hists = list(base["hists"]) * 2 + list(base["hists"][:2])
+    spec = dict(base, hists=hists)
+    assert len(hists) == 130 > fillable.PART_MAX_HISTS
+    fills = [_c4_columns(4000, 31), _c4_columns(3500, 32)]
+    got, launches, stats = _run(spec, fills)
+    assert stats.get("parts") == 2
+    exp = bound = None
+    for arrays in fills:
+        exp = fill_oracle.fill(spec, arrays, exp)
+        bound = fill_oracle.fill(spec, arrays, bound, absolute=True)
+    compare("c4 x 2", spec, got, [golden_util.flatten(e) for e in exp], bound)
