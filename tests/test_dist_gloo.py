@@ -112,11 +112,12 @@ def _host_filler(spec, contents, arrays):
     return sf
 
 
-def _merger_worker(rank, world, port, case_name, out_dir, lazy_rank):
+def _merger_worker(rank, world, port, case_name, out_dir, lazy_rank, emulated=False):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    import contextlib
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import golden_util
@@ -124,33 +125,48 @@ def _merger_worker(rank, world, port, case_name, out_dir, lazy_rank):
     from oracle import fill_oracle
     case = golden_util.load()[case_name]
     arrays = golden_util.fills(case)[0]
-    if lazy_rank == rank:
-        sf = fillable.SpecFill(case["spec"])              # this rank never calls fill: no store at all
-    else:
-        if lazy_rank is None:
-            mine = hbdist.shard_columns(arrays, rank, world)
+    engine_scope = contextlib.nullcontext()
+    if emulated:
+        import emul_engine
+        engine_scope = emul_engine.installed()            # the rank's fill really runs: generated kernels on CPU threads
+    with engine_scope:
+        if lazy_rank == rank:
+            sf = fillable.SpecFill(case["spec"])              # this rank never calls fill: no store at all
         else:
-            mine = arrays                                 # the other rank fills everything
-        sf = _host_filler(case["spec"], fill_oracle.fill(case["spec"], mine), mine)
-    merger = hbdist.Merger(sf).start()
-    merged = merger.contents()
+            if lazy_rank is None:
+                mine = hbdist.shard_columns(arrays, rank, world)
+            else:
+                mine = arrays                                 # the other rank fills everything
+            if emulated:
+                sf = fillable.SpecFill(case["spec"])
+                sf.fill(mine)
+            else:
+                sf = _host_filler(case["spec"], fill_oracle.fill(case["spec"], mine), mine)
+        merger = hbdist.Merger(sf).start()
+        merged = merger.contents()
     flat = [[(k, a) for k, a in golden_util.flatten(c)] for c in merged]
     numpy.save(os.path.join(out_dir, "rank%d.npy" % rank), numpy.array([flat, merger.collectives], dtype=object), allow_pickle=True)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case_name,lazy_rank", [("c2", None), ("groupbin_nan_refill", None), ("groupby_groupbin_num", None), ("c4", None),
-                                                 ("c4", 1), ("book_fill", None)])
-def test_merger_is_one_collective_and_equals_one_fill(case_name, lazy_rank, tmp_path):
+@pytest.mark.parametrize("case_name,lazy_rank,emulated", [("c2", None, False), ("groupbin_nan_refill", None, False), ("groupby_groupbin_num", None, False),
+                                                          ("c4", None, False), ("c4", 1, False), ("book_fill", None, False),
+                                                          ("c4", None, True), ("c4", 1, True)])
+def test_merger_is_one_collective_and_equals_one_fill(case_name, lazy_rank, emulated, tmp_path):
     """Two ranks, contents on the host, gloo: the whole book merges with ONE all_reduce (plus one key all-gather when it
     has group axes), the result equals one fill of everything, and a rank that never filled (``lazy_rank``) joins the
-    same collectives instead of hanging the others."""
+    same collectives instead of hanging the others.  ``emulated``: the ranks do not take their contents from the oracle but
+    fill their shards through the product's host path on the emulated engine (tests/emul_engine.py) -- shard, fill, merge, as
+    under torchrun on the GPUs, with the kernels on CPU threads and gloo for NCCL."""
+    import shutil
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(REPO, "tests"))
     import golden_util
     from oracle import fill_oracle
+    if emulated and shutil.which("g++") is None:
+        pytest.skip("the kernel emulator is compiled with g++")
     port = _free_port()
-    mp.spawn(_merger_worker, args=(2, port, case_name, str(tmp_path), lazy_rank), nprocs=2, join=True)
+    mp.spawn(_merger_worker, args=(2, port, case_name, str(tmp_path), lazy_rank, emulated), nprocs=2, join=True)
     case = golden_util.load()[case_name]
     arrays = golden_util.fills(case)[0]
     whole = fill_oracle.fill(case["spec"], arrays)
